@@ -1,0 +1,225 @@
+/*
+ * popnet_b200 -- C ABI of the B200-native depth-pose hot path
+ * (rtpose_light3d forward -> heat-map/PAF decode -> 2D-to-3D lift -> best-match PCK / mAP matching).
+ *
+ * The reference (oppo-us-research/PoP-Net, MP-3DHP release) has no FFI / plugin layer for this path:
+ * its only native code (third_party_methods/lib/pafprocess/pafprocess.h:53-59, SWIG) is COCO-only,
+ * keeps results in process globals (pafprocess.cpp:12-13) and is not called (paf_to_pose.py:7).  The
+ * boundary that callers see is a set of Python signatures; every entry point below is the native
+ * half of one of them and cites it.  the popnet_b200 Python package holds the Python half with the reference's
+ * names and argument meaning; INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; all pointers are DEVICE pointers unless
+ * the name ends in _host; `stream` is a cudaStream_t passed as void* (NULL = default stream); calls
+ * enqueue work and return without synchronising; no allocation, no global state, re-entrant.
+ * Return value: POPNET_OK or a negative PopnetStatus.  Nothing throws.
+ */
+#ifndef POPNET_B200_H_
+#define POPNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POPNET_ABI_VERSION 1
+
+#define POPNET_MAX_JOINTS 24      /* K upper bound (15 MP-3DHP/ITOP, 18 COCO)                      */
+#define POPNET_MAX_LIMBS 24       /* L upper bound (14 / 19)                                       */
+#define POPNET_MAX_PEAKS 64       /* per joint type and frame (reference: unbounded)               */
+#define POPNET_MAX_PERSONS 64     /* assembled persons per frame before pruning (ref.: unbounded)  */
+
+typedef enum PopnetStatus {
+  POPNET_OK = 0,
+  POPNET_ERR_INVALID_ARG = -1,
+  POPNET_ERR_UNSUPPORTED = -2,    /* shape / topology outside the compiled capacities              */
+  POPNET_ERR_WORKSPACE = -3,      /* workspace too small                                           */
+  POPNET_ERR_CUDA = -4,           /* a CUDA call failed; popnet_last_cuda_error() has the code     */
+  POPNET_ERR_NO_DEVICE = -5
+} PopnetStatus;
+
+/* per-frame overflow flags written by popnet_decode (reference lists are unbounded; a flagged frame
+ * is a parity failure by definition and is counted as such by the tests) */
+#define POPNET_FLAG_PEAK_OVERFLOW 1u
+#define POPNET_FLAG_PERSON_OVERFLOW 2u
+
+int popnet_abi_version(void);
+int popnet_last_cuda_error(void);
+/* number of kernels this library has launched since load (all entry points); bench.py reports the
+ * delta over its timed region as "gpu_launches" */
+long long popnet_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decode + lift.  Replaces, batched and on the device:
+ *   paf_to_pose(heatmaps, pafs, config)              third_party_methods/lib/utils/paf_to_pose.py:354-377
+ *     NMS / find_peaks / bicubic refinement          paf_to_pose.py:33-153
+ *     find_connected_joints                          paf_to_pose.py:156-264
+ *     group_limbs_of_same_person                     paf_to_pose.py:267-351
+ *   paf_to_human_list(joint_list, assoc)             third_party_methods/lib/utils/common.py:5-32
+ *   retrieve_depth_heat_weighted(c, depth, heat, 1)  third_party_methods/lib/utils/common.py:272-293
+ *   de-normalise / rescale / back-project            evaluate/evaluation_rtpose_light3d_kdh3d_mpreal_ablation.py:179-263
+ * The five yacs fields the reference reads (MODEL.NUM_KEYPOINTS, MODEL.DOWNSAMPLE, TEST.THRESH_HEATMAP,
+ * TEST.THRESH_PAF, TEST.NUM_INTERMED_PTS_BETWEEN_KEYPOINTS; lib/config/default.py:128-130), the skeleton
+ * that paf_to_pose.py:28-30 binds at import, and the camera constants (util/util_functions.py:4,11-13)
+ * travel in one POD block.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct PopnetDecodeParams {
+  int32_t num_joints;                       /* K                                                  */
+  int32_t num_limbs;                        /* L                                                  */
+  int32_t limbs[POPNET_MAX_LIMBS][2];       /* (src type, dst type); PAF channels (2l, 2l+1)      */
+  int32_t grid_h, grid_w;                   /* 28 x 28                                            */
+  int32_t stride;                           /* MODEL.DOWNSAMPLE = 8 (the only compiled value)     */
+  int32_t num_intermed_pts;                 /* 10                                                 */
+  float thresh_heat;                        /* 0.1, compared in fp32 like the reference           */
+  float depth_mean, depth_std;              /* applied in fp32: d * std + mean                    */
+  double thresh_paf;                        /* 0.05                                               */
+  double input_size;                        /* 224: 2D rescale is X / input_size * w_org          */
+  double w_org, h_org;
+  double fx, fy, cx, cy;
+  int32_t flip_y;                           /* ITOP: Y3 negated (evaluation_rtpose_light3d_itop.py:206) */
+  int32_t max_peaks;                        /* <= POPNET_MAX_PEAKS                                 */
+  int32_t max_persons;                      /* <= POPNET_MAX_PERSONS                               */
+  int32_t reserved;
+} PopnetDecodeParams;
+
+/* Output buffers; any pointer except n_person/flags may be NULL to skip that product.
+ * Strides use the capacities in PopnetDecodeParams (P = max_peaks, M = max_persons, K, L). */
+typedef struct PopnetDecodeOut {
+  int32_t* peak_count;     /* [B][K]                                                              */
+  int16_t* peak_xy;        /* [B][K][P][2]   refined (X, Y) in input pixels, integers              */
+  float* peak_score;       /* [B][K][P]      bicubic value at the refined maximum                  */
+  int32_t* conn_count;     /* [B][L]                                                              */
+  int16_t* conn_ij;        /* [B][L][P][2]   (src index, dst index) within their joint types       */
+  double* conn_score;      /* [B][L][P]                                                           */
+  int32_t* n_person;       /* [B]            persons that survive pruning                          */
+  int16_t* person_peak;    /* [B][M][K]      peak index within the joint type, -1 = missing        */
+  double* person_score;    /* [B][M]         row[-2] of person_to_joint_assoc                      */
+  int32_t* person_njoint;  /* [B][M]         row[-1]                                               */
+  double* pose2d;          /* [B][M][K][2]   original-resolution pixels; (-1,-1) = missing         */
+  double* pose3d;          /* [B][M][K][3]   metres (camera frame)                                 */
+  double* pose_conf;       /* [B][M][K]      peak score, 0 = missing                               */
+  uint32_t* flags;         /* [B]            POPNET_FLAG_*                                         */
+} PopnetDecodeOut;
+
+/* heat [B][K+1][gh][gw], paf [B][2L][gh][gw], depth [B][K][gh][gw]: fp32, channel-major (the layout
+ * the network writes; the reference transposes to HWC on the host, ...mpreal_ablation.py:176-178).
+ * depth may be NULL (2D only: pose3d / Z are then not written). */
+int popnet_decode(const float* heat, const float* paf, const float* depth, int batch,
+                  const PopnetDecodeParams* params_host, const PopnetDecodeOut* out_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Evaluator.  Ragged lists-of-lists are CSR-packed by the host: humans of frame f are rows
+ * off[f] .. off[f+1]-1; a human is K joints of D doubles; a missing joint is (-1, -1).
+ *
+ * popnet_eval_pck replaces the per-frame matching of
+ *   eval_human_dataset_2d / _2d_PCKh / _3d            util/eval_pck.py:20-77, 80-154, 313-374
+ *   match_humans_2d / match_humans_3d                 util/eval_pck.py:266-310, 377-430
+ *   compute_bbox_from_humans, bbox_ious               util/eval_pck.py:433-475
+ * (identical copies: third_party_methods/evaluate/eval_pose_mp.py).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct PopnetPckArgs {
+  const double* pred2d;        /* [SP][K][2]                                                       */
+  const double* pred3d;        /* [SP][K][3] or NULL -> 2D distances                               */
+  const int32_t* pred_off;     /* [N+1]                                                            */
+  const double* gt2d;          /* [SG][K][2]                                                       */
+  const double* gt3d;          /* [SG][K][3] or NULL                                               */
+  const int32_t* gt_off;       /* [N+1]                                                            */
+  const uint8_t* gt_vis;       /* [SG][K] or NULL (= all visible); 0 forces distance -1            */
+  const double* gt_thresh;     /* [SG] per-GT hit threshold (PCKh: hsz*h_th, host-computed) or NULL */
+  double dist_th;              /* used when gt_thresh == NULL; hit iff 0 <= d < th                  */
+  double iou_th;
+  int32_t num_frames;          /* N                                                                */
+  int32_t num_joints;          /* K                                                                */
+  double* dists;               /* out [SG][K]: matched joint distance or -1                        */
+  uint8_t* hit;                /* out [SG][K] or NULL                                              */
+  int32_t* matched_pred;       /* out [SG] or NULL: frame-local index of the matched prediction, -1 */
+  long long* hit_cnt;          /* out [K], zeroed by the call                                      */
+  long long* valid_cnt;        /* out [K], zeroed by the call: #(d >= 0)                           */
+  int32_t* status;             /* out [N] or NULL: 1 = a GT human has no valid joint (the reference
+                                  raises IndexError there, eval_pck.py:441-443,462)                */
+} PopnetPckArgs;
+
+int popnet_eval_pck(const PopnetPckArgs* args_host, void* stream);
+
+/* popnet_eval_map_assign replaces assignGTmulti          util/eval_mAP.py:60-157
+ * (callers eval_ap_mpii_v2 :272-332 and eval_ap_3D :335-395; copy in evaluate/eval_ap_mpii.py).
+ * D = 2 (refDist = head size, host-computed with the reference's own expression) or 3 (refDist = 1). */
+typedef struct PopnetMapArgs {
+  const double* pred;          /* [SP][K][D]                                                       */
+  const int32_t* pred_off;     /* [N+1]                                                            */
+  const double* gt;            /* [SG][K][D]                                                       */
+  const int32_t* gt_off;       /* [N+1]                                                            */
+  const uint8_t* gt_vis;       /* [SG][K] or NULL (= all visible)                                  */
+  const double* ref_dist;      /* [SG]                                                             */
+  double thresh;               /* match iff dist / ref_dist <= thresh                              */
+  int32_t num_frames, num_joints, dim;
+  uint8_t* labels;             /* out [SP][K]: 1 = this predicted joint is a true positive         */
+  int32_t* matched_gt;         /* out [SP]: frame-local GT index this prediction was assigned, -1   */
+  long long* n_gt;             /* out [K], zeroed by the call: annotated (visible) GT joints        */
+  long long* n_pos;            /* out [K], zeroed by the call: #labels == 1                         */
+} PopnetMapArgs;
+
+int popnet_eval_map_assign(const PopnetMapArgs* args_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Network forward.  Replaces rtpose_light3d.forward   third_party_methods/lib/network/rtpose_light3d.py:326-356
+ * (ResPreprocessNet :201-216, BasicBlock :56-72, make_stages :222-246) for num_stages = 2.
+ * Weights are folded (eval-mode BatchNorm into scale/shift, then bf16) and packed once by
+ * popnet_pack_weights from the 234 tensors of the reference state dict, passed in the canonical
+ * order returned by popnet_weight_manifest (the Python mirror keeps the reference key names so a
+ * reference checkpoint loads unchanged).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct PopnetNetConfig {
+  int32_t num_parts;           /* 15                                                               */
+  int32_t num_limbs;           /* 14                                                               */
+  int32_t input_dim;           /* 1 (depth); the only compiled value                               */
+  int32_t height, width;       /* 224 x 224; must be multiples of 8                                */
+} PopnetNetConfig;
+
+/* number of conv layers (39) and, per layer l, the element counts the packer expects */
+int popnet_num_conv_layers(const PopnetNetConfig* cfg);
+/* packed-weight blob size (device) */
+size_t popnet_packed_weight_bytes(const PopnetNetConfig* cfg);
+/* workspace (activations) size for a batch */
+size_t popnet_workspace_bytes(const PopnetNetConfig* cfg, int batch);
+
+/* Host-side description of one conv layer after BN folding (all host pointers, fp32):
+ * weight [cout][cin][kh][kw] (PyTorch OIHW), scale[cout] and shift[cout] so that
+ * y = act(scale * conv(x, weight) + shift). */
+typedef struct PopnetConvHost {
+  const float* weight_host;
+  const float* scale_host;
+  const float* shift_host;
+  int32_t cout, cin, ksize;
+} PopnetConvHost;
+
+/* packs (host -> device blob): bf16 weights with `scale` folded in, fp32 shift; synchronous */
+int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvHost* layers_host, int num_layers,
+                        void* packed_dev, size_t packed_bytes, void* stream);
+
+#define POPNET_FWD_IMPL_TCGEN05 0   /* product path: tcgen05/TMEM implicit GEMM                    */
+#define POPNET_FWD_IMPL_SIMT 1      /* plain CUDA-core check kernel (tests / bring-up only)        */
+
+/* x [B][1][H][W] fp32 (normalised depth).  Outputs fp32 channel-major like the reference's NCHW:
+ * paf [B][2L][H/8][W/8], heat [B][K+1][..], depth [B][L+1][..]; stage1_* are the first-stage maps
+ * (saved_for_loss[0..2], rtpose_light3d.py:340-342) and may be NULL. */
+int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev, const float* x, int batch,
+                   float* paf, float* heat, float* depth,
+                   float* stage1_paf, float* stage1_heat, float* stage1_depth,
+                   void* workspace, size_t workspace_bytes, int impl, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * "Next" row 1: eval-time preprocessing on the device.  Replaces
+ *   Cvt2ndarray + Resize(224) (cv2.INTER_LINEAR)   lib/datasets/data_augmentation_2d3d.py:70-89, 497-522
+ *   clamp [0, depth_max], (x - mean) / std          lib/datasets/datasets_kdh3d_rtpose_mpreal.py:CR229-246
+ * src [B][src_h][src_w] fp32 metres -> dst [B][1][dst_h][dst_w] fp32 normalised.
+ * ---------------------------------------------------------------------------------------------- */
+int popnet_preprocess_depth(const float* src, int batch, int src_h, int src_w, float* dst, int dst_h,
+                            int dst_w, float depth_max, float depth_mean, float depth_std, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POPNET_B200_H_ */

@@ -26,6 +26,12 @@ extern "C" {
 
 #define POPNET_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define POPNET_API __attribute__((visibility("default")))
+#else
+#define POPNET_API
+#endif
+
 #define POPNET_MAX_JOINTS 24      /* K upper bound (15 MP-3DHP/ITOP, 18 COCO)                      */
 #define POPNET_MAX_LIMBS 24       /* L upper bound (14 / 19)                                       */
 #define POPNET_MAX_PEAKS 64       /* per joint type and frame (reference: unbounded)               */
@@ -45,11 +51,11 @@ typedef enum PopnetStatus {
 #define POPNET_FLAG_PEAK_OVERFLOW 1u
 #define POPNET_FLAG_PERSON_OVERFLOW 2u
 
-int popnet_abi_version(void);
-int popnet_last_cuda_error(void);
+POPNET_API int popnet_abi_version(void);
+POPNET_API int popnet_last_cuda_error(void);
 /* number of kernels this library has launched since load (all entry points); bench.py reports the
  * delta over its timed region as "gpu_launches" */
-long long popnet_launch_count(void);
+POPNET_API long long popnet_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Decode + lift.  Replaces, batched and on the device:
@@ -84,7 +90,7 @@ typedef struct PopnetDecodeParams {
   int32_t reserved;
 } PopnetDecodeParams;
 
-/* Output buffers; any pointer except n_person/flags may be NULL to skip that product.
+/* Output buffers (see popnet_decode for which may be NULL).
  * Strides use the capacities in PopnetDecodeParams (P = max_peaks, M = max_persons, K, L). */
 typedef struct PopnetDecodeOut {
   int32_t* peak_count;     /* [B][K]                                                              */
@@ -105,8 +111,10 @@ typedef struct PopnetDecodeOut {
 
 /* heat [B][K+1][gh][gw], paf [B][2L][gh][gw], depth [B][K][gh][gw]: fp32, channel-major (the layout
  * the network writes; the reference transposes to HWC on the host, ...mpreal_ablation.py:176-178).
- * depth may be NULL (2D only: pose3d / Z are then not written). */
-int popnet_decode(const float* heat, const float* paf, const float* depth, int batch,
+ * depth may be NULL (2D only: pose3d / Z are then not written).
+ * peak_* and conn_* double as the stage-to-stage storage of the three decode kernels and are
+ * mandatory, as are n_person and flags; person_* and pose* may be NULL. */
+POPNET_API int popnet_decode(const float* heat, const float* paf, const float* depth, int batch,
                   const PopnetDecodeParams* params_host, const PopnetDecodeOut* out_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -141,7 +149,7 @@ typedef struct PopnetPckArgs {
                                   raises IndexError there, eval_pck.py:441-443,462)                */
 } PopnetPckArgs;
 
-int popnet_eval_pck(const PopnetPckArgs* args_host, void* stream);
+POPNET_API int popnet_eval_pck(const PopnetPckArgs* args_host, void* stream);
 
 /* popnet_eval_map_assign replaces assignGTmulti          util/eval_mAP.py:60-157
  * (callers eval_ap_mpii_v2 :272-332 and eval_ap_3D :335-395; copy in evaluate/eval_ap_mpii.py).
@@ -161,7 +169,7 @@ typedef struct PopnetMapArgs {
   long long* n_pos;            /* out [K], zeroed by the call: #labels == 1                         */
 } PopnetMapArgs;
 
-int popnet_eval_map_assign(const PopnetMapArgs* args_host, void* stream);
+POPNET_API int popnet_eval_map_assign(const PopnetMapArgs* args_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Network forward.  Replaces rtpose_light3d.forward   third_party_methods/lib/network/rtpose_light3d.py:326-356
@@ -179,11 +187,11 @@ typedef struct PopnetNetConfig {
 } PopnetNetConfig;
 
 /* number of conv layers (39) and, per layer l, the element counts the packer expects */
-int popnet_num_conv_layers(const PopnetNetConfig* cfg);
+POPNET_API int popnet_num_conv_layers(const PopnetNetConfig* cfg);
 /* packed-weight blob size (device) */
-size_t popnet_packed_weight_bytes(const PopnetNetConfig* cfg);
+POPNET_API size_t popnet_packed_weight_bytes(const PopnetNetConfig* cfg);
 /* workspace (activations) size for a batch */
-size_t popnet_workspace_bytes(const PopnetNetConfig* cfg, int batch);
+POPNET_API size_t popnet_workspace_bytes(const PopnetNetConfig* cfg, int batch);
 
 /* Host-side description of one conv layer after BN folding (all host pointers, fp32):
  * weight [cout][cin][kh][kw] (PyTorch OIHW), scale[cout] and shift[cout] so that
@@ -196,7 +204,7 @@ typedef struct PopnetConvHost {
 } PopnetConvHost;
 
 /* packs (host -> device blob): bf16 weights with `scale` folded in, fp32 shift; synchronous */
-int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvHost* layers_host, int num_layers,
+POPNET_API int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvHost* layers_host, int num_layers,
                         void* packed_dev, size_t packed_bytes, void* stream);
 
 #define POPNET_FWD_IMPL_TCGEN05 0   /* product path: tcgen05/TMEM implicit GEMM                    */
@@ -205,7 +213,7 @@ int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvHost* layers
 /* x [B][1][H][W] fp32 (normalised depth).  Outputs fp32 channel-major like the reference's NCHW:
  * paf [B][2L][H/8][W/8], heat [B][K+1][..], depth [B][L+1][..]; stage1_* are the first-stage maps
  * (saved_for_loss[0..2], rtpose_light3d.py:340-342) and may be NULL. */
-int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev, const float* x, int batch,
+POPNET_API int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev, const float* x, int batch,
                    float* paf, float* heat, float* depth,
                    float* stage1_paf, float* stage1_heat, float* stage1_depth,
                    void* workspace, size_t workspace_bytes, int impl, void* stream);
@@ -216,7 +224,7 @@ int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev, const flo
  *   clamp [0, depth_max], (x - mean) / std          lib/datasets/datasets_kdh3d_rtpose_mpreal.py:CR229-246
  * src [B][src_h][src_w] fp32 metres -> dst [B][1][dst_h][dst_w] fp32 normalised.
  * ---------------------------------------------------------------------------------------------- */
-int popnet_preprocess_depth(const float* src, int batch, int src_h, int src_w, float* dst, int dst_h,
+POPNET_API int popnet_preprocess_depth(const float* src, int batch, int src_h, int src_w, float* dst, int dst_h,
                             int dst_w, float depth_max, float depth_mean, float depth_std, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,114 @@
+"""The one backend of the product: device buffers through torch, compute through libpopnet_b200.so.
+
+torch is plumbing here (allocation, streams, H2D/D2H); every kernel is in popnet_b200/csrc.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi, _lib
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.PopnetError("popnet_b200 needs a CUDA device (no CPU fallback exists)")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _to_dev(a, dtype=None):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        t = a
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.cuda().contiguous()
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def alloc_decode_out(B, params, device="cuda"):
+    K, L, P, M = params.num_joints, params.num_limbs, params.max_peaks, params.max_persons
+    z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
+    return {
+        "peak_count": z((B, K), torch.int32), "peak_xy": z((B, K, P, 2), torch.int16),
+        "peak_score": z((B, K, P), torch.float32), "conn_count": z((B, L), torch.int32),
+        "conn_ij": z((B, L, P, 2), torch.int16), "conn_score": z((B, L, P), torch.float64),
+        "n_person": z((B,), torch.int32), "person_peak": z((B, M, K), torch.int16),
+        "person_score": z((B, M), torch.float64), "person_njoint": z((B, M), torch.int32),
+        "pose2d": z((B, M, K, 2), torch.float64), "pose3d": z((B, M, K, 3), torch.float64),
+        "pose_conf": z((B, M, K), torch.float64), "flags": z((B,), torch.int32),
+    }
+
+
+class CudaBackend:
+    name = "cuda-sm100a"
+
+    def __init__(self):
+        _require_cuda()
+        self.lib = _lib.get()
+
+    # ------------------------------------------------------------------ evaluator
+    def pck(self, arrs, *, dist_th, iou_th, K):
+        d = {k: _to_dev(v) for k, v in arrs.items()}
+        SG = d["gt2d"].shape[0]
+        N = d["gt_off"].shape[0] - 1
+        out = {"dists": torch.empty((SG, K), dtype=torch.float64, device="cuda"),
+               "hit": torch.empty((SG, K), dtype=torch.uint8, device="cuda"),
+               "matched_pred": torch.empty((SG,), dtype=torch.int32, device="cuda"),
+               "hit_cnt": torch.empty((K,), dtype=torch.int64, device="cuda"),
+               "valid_cnt": torch.empty((K,), dtype=torch.int64, device="cuda"),
+               "status": torch.zeros((max(N, 1),), dtype=torch.int32, device="cuda")}
+        a = _abi.PckArgs(pred2d=_ptr(d["pred2d"]), pred3d=_ptr(d.get("pred3d")), pred_off=_ptr(d["pred_off"]),
+                         gt2d=_ptr(d["gt2d"]), gt3d=_ptr(d.get("gt3d")), gt_off=_ptr(d["gt_off"]),
+                         gt_vis=_ptr(d.get("gt_vis")), gt_thresh=_ptr(d.get("gt_thresh")),
+                         dist_th=dist_th, iou_th=iou_th, num_frames=N, num_joints=K,
+                         **{k: _ptr(v) for k, v in out.items()})
+        _lib.check(self.lib.popnet_eval_pck(C.byref(a), _stream()), "popnet_eval_pck")
+        res = {k: v.cpu().numpy() for k, v in out.items()}
+        res["status"] = res["status"][:N]
+        return res
+
+    def map_assign(self, arrs, *, thresh, K, D):
+        d = {k: _to_dev(v) for k, v in arrs.items()}
+        SP = d["pred"].shape[0]
+        N = d["gt_off"].shape[0] - 1
+        out = {"labels": torch.zeros((SP, K), dtype=torch.uint8, device="cuda"),
+               "matched_gt": torch.full((SP,), -1, dtype=torch.int32, device="cuda"),
+               "n_gt": torch.empty((K,), dtype=torch.int64, device="cuda"),
+               "n_pos": torch.empty((K,), dtype=torch.int64, device="cuda")}
+        a = _abi.MapArgs(pred=_ptr(d["pred"]), pred_off=_ptr(d["pred_off"]), gt=_ptr(d["gt"]),
+                         gt_off=_ptr(d["gt_off"]), gt_vis=_ptr(d.get("gt_vis")), ref_dist=_ptr(d["ref_dist"]),
+                         thresh=thresh, num_frames=N, num_joints=K, dim=D,
+                         **{k: _ptr(v) for k, v in out.items()})
+        _lib.check(self.lib.popnet_eval_map_assign(C.byref(a), _stream()), "popnet_eval_map_assign")
+        return {k: v.cpu().numpy() for k, v in out.items()}
+
+    # ------------------------------------------------------------------ decode
+    def decode_device(self, heat, paf, depth, params, out=None):
+        """Device tensors in, device tensors out (no synchronisation); `out` buffers may be reused."""
+        B = heat.shape[0]
+        if out is None:
+            out = alloc_decode_out(B, params)
+        o = _abi.DecodeOut(**{k: _ptr(v) for k, v in out.items()})
+        _lib.check(self.lib.popnet_decode(_ptr(heat), _ptr(paf), _ptr(depth), B, C.byref(params), C.byref(o),
+                                          _stream()), "popnet_decode")
+        return out
+
+    def decode(self, heat, paf, depth, params):
+        """NumPy (or torch) maps in, dict of NumPy arrays out -- same keys/strides as the C oracle."""
+        h, p_, d = _to_dev(heat, torch.float32), _to_dev(paf, torch.float32), _to_dev(depth, torch.float32)
+        out = self.decode_device(h, p_, d, params)
+        res = {k: v.cpu().numpy() for k, v in out.items()}
+        res["flags"] = res["flags"].view(np.uint32)
+        return res

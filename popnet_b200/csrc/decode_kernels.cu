@@ -1,0 +1,494 @@
+// Heat-map / PAF decode and 2D->3D lift on the device.
+//
+// Reference being replaced (third_party_methods/): lib/utils/paf_to_pose.py:33-377 (find_peaks, NMS with
+// cv2 bicubic refinement, find_connected_joints, group_limbs_of_same_person), lib/utils/common.py:5-32,
+// 272-293 (paf_to_human_list, retrieve_depth_heat_weighted) and the per-frame glue of
+// evaluate/evaluation_rtpose_light3d_kdh3d_mpreal_ablation.py:179-263.
+//
+// Three kernels per batch, all reading the network's channel-major fp32 maps in place:
+//   peaks_kernel     grid (K, B)  one CTA per (frame, joint type): 4-neighbour NMS with ordered
+//                                 compaction, then one warp per peak evaluates the 8x bicubic of the
+//                                 clipped 5x5 patch and takes the first arg-max.
+//   limbs_kernel     grid (L, B)  one CTA per (frame, limb): every (src, dst) pair is scored from 10
+//                                 on-the-fly bicubic PAF samples (the 224x224x28 upsample the reference
+//                                 materialises is never built), then greedy one-to-one matching.
+//   assemble_kernel  grid (B)     one warp per frame: sequential person assembly, pruning, depth lift,
+//                                 rescale and back-projection; writes the pose records.
+// Compiled with -fmad=false so fp32/fp64 expressions round exactly like OpenCV's C++ path and NumPy;
+// the two places the reference goes through BLAS use explicit fma().
+//
+// Bound: HBM in principle (181,888 B of maps per frame); the work per frame is tiny,
+// so throughput comes from frames in flight (B x 15 / B x 14 / B CTAs), not from any single CTA.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kThreads = 128;
+constexpr int kMaxCells = 64 * 64;      // largest supported grid_h * grid_w
+
+// OpenCV INTER_CUBIC at scale 8: phase r = dst % 8 -> first-tap offset and the four Keys(A=-0.75)
+// weights; all values are dyadic rationals, exact in fp32 (oracle/decode_np.py::phase_table).
+__constant__ int c_ofs[8];
+__constant__ float c_coef[8][4];
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// value of the 8x bicubic upsample of an H x W array (row pitch `pitch`) at integer point (X, Y):
+// horizontal ((s0*a0+s1*a1)+s2*a2)+s3*a3 on the four source rows, then vertical r0*b0+(r1*b1+(r2*b2+r3*b3))
+__device__ __forceinline__ float bicubic_at(const float* m, int pitch, int H, int W, int X, int Y) {
+  const int rx = X & 7, ry = Y & 7;
+  const int bx = (X >> 3) + c_ofs[rx], by = (Y >> 3) + c_ofs[ry];
+  const float a0 = c_coef[rx][0], a1 = c_coef[rx][1], a2 = c_coef[rx][2], a3 = c_coef[rx][3];
+  const int x0 = clampi(bx - 1, 0, W - 1), x1 = clampi(bx, 0, W - 1), x2 = clampi(bx + 1, 0, W - 1),
+            x3 = clampi(bx + 2, 0, W - 1);
+  float rows[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float* row = m + clampi(by - 1 + j, 0, H - 1) * pitch;
+    rows[j] = ((row[x0] * a0 + row[x1] * a1) + row[x2] * a2) + row[x3] * a3;
+  }
+  return rows[0] * c_coef[ry][0] + (rows[1] * c_coef[ry][1] + (rows[2] * c_coef[ry][2] + rows[3] * c_coef[ry][3]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// D1 + D2: peaks
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) peaks_kernel(const float* __restrict__ heat, PopnetDecodeParams p,
+                                                         PopnetDecodeOut o) {
+  extern __shared__ float s_map[];                       // H*W
+  __shared__ int s_cell[POPNET_MAX_PEAKS];
+  __shared__ int s_warp_cnt[kThreads / 32];
+  __shared__ int s_total;
+  __shared__ float s_tmp[kThreads / 32][5 * 40];         // per-warp horizontal pass of a <=5x5 patch
+
+  const int k = blockIdx.x, b = blockIdx.y;
+  const int H = p.grid_h, W = p.grid_w, cells = H * W;
+  const int K = p.num_joints, MP = p.max_peaks;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* m = heat + ((size_t)b * (K + 1) + k) * cells;
+  for (int i = tid; i < cells; i += kThreads) s_map[i] = m[i];
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+
+  // ordered (row-major) compaction of the peak cells
+  for (int base = 0; base < cells; base += kThreads) {
+    const int i = base + tid;
+    bool pk = false;
+    if (i < cells) {
+      const int y = i / W, x = i - y * W;
+      const float v = s_map[i];
+      pk = v > p.thresh_heat;
+      if (pk && y > 0) pk = !(s_map[i - W] > v);
+      if (pk && y < H - 1) pk = !(s_map[i + W] > v);
+      if (pk && x > 0) pk = !(s_map[i - 1] > v);
+      if (pk && x < W - 1) pk = !(s_map[i + 1] > v);
+    }
+    const unsigned bal = __ballot_sync(kFull, pk);
+    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_total;
+    for (int w = 0; w < warp; ++w) before += s_warp_cnt[w];
+    if (pk) {
+      const int slot = before + __popc(bal & ((1u << lane) - 1u));
+      if (slot < MP) s_cell[slot] = i;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = s_total;
+      for (int w = 0; w < kThreads / 32; ++w) t += s_warp_cnt[w];
+      s_total = t;
+    }
+    __syncthreads();
+  }
+  int n = s_total;
+  if (n > MP) {
+    if (tid == 0) atomicOr(o.flags + b, POPNET_FLAG_PEAK_OVERFLOW);
+    n = MP;
+  }
+  if (tid == 0) o.peak_count[(size_t)b * K + k] = n;
+
+  // refinement: one warp per peak
+  float* tmp = s_tmp[warp];
+  for (int pi = warp; pi < n; pi += kThreads / 32) {
+    const int cell = s_cell[pi];
+    const int y = cell / W, x = cell - y * W;
+    const int x0 = max(x - 2, 0), y0 = max(y - 2, 0), x1 = min(x + 2, W - 1), y1 = min(y + 2, H - 1);
+    const int pw = x1 - x0 + 1, ph = y1 - y0 + 1, uw = pw * 8, uh = ph * 8;
+    const float* patch = s_map + y0 * W + x0;
+    // horizontal pass: tmp[r][dx], r < ph, dx < uw
+    for (int i = lane; i < ph * uw; i += 32) {
+      const int r = i / uw, dx = i - r * uw;
+      const int rx = dx & 7, bx = (dx >> 3) + c_ofs[rx];
+      const float* row = patch + r * W;
+      tmp[r * 40 + dx] = ((row[clampi(bx - 1, 0, pw - 1)] * c_coef[rx][0] + row[clampi(bx, 0, pw - 1)] * c_coef[rx][1]) +
+                          row[clampi(bx + 1, 0, pw - 1)] * c_coef[rx][2]) + row[clampi(bx + 2, 0, pw - 1)] * c_coef[rx][3];
+    }
+    __syncwarp();
+    float best = -CUDART_INF_F;
+    int bidx = 0x7fffffff;
+    for (int i = lane; i < uh * uw; i += 32) {
+      const int dy = i / uw, dx = i - dy * uw;
+      const int ry = dy & 7, by = (dy >> 3) + c_ofs[ry];
+      const float v = tmp[clampi(by - 1, 0, ph - 1) * 40 + dx] * c_coef[ry][0] +
+                      (tmp[clampi(by, 0, ph - 1) * 40 + dx] * c_coef[ry][1] +
+                       (tmp[clampi(by + 1, 0, ph - 1) * 40 + dx] * c_coef[ry][2] +
+                        tmp[clampi(by + 2, 0, ph - 1) * 40 + dx] * c_coef[ry][3]));
+      if (v > best) { best = v; bidx = i; }          // ascending i per lane: first maximum
+    }
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+      const float ov = __shfl_xor_sync(kFull, best, ofs);
+      const int oi = __shfl_xor_sync(kFull, bidx, ofs);
+      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    if (lane == 0) {
+      const int ay = bidx / uw, ax = bidx - ay * uw;
+      const size_t slot = ((size_t)b * K + k) * MP + pi;
+      o.peak_xy[slot * 2] = (int16_t)(8 * x0 + ax);
+      o.peak_xy[slot * 2 + 1] = (int16_t)(8 * y0 + ay);
+      o.peak_score[slot] = best;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// D4: limb scoring + greedy matching
+// ------------------------------------------------------------------------------------------------
+// round(linspace(a, b, n))[i] for integer a, b (paf_to_pose.py:214-217)
+__device__ __forceinline__ int line_point(int a, int b, int i, int n) {
+  if (n == 10) {
+    const int num = 2 * (9 * a + i * (b - a)) + 9;
+    int q = num / 18;
+    if (num % 18 != 0 && num < 0) --q;
+    return q;
+  }
+  if (n == 1) return a;
+  const double step = ((double)b - (double)a) / (double)(n - 1);
+  const double v = (i == n - 1) ? (double)b : (double)a + (double)i * step;
+  return (int)rint(v);
+}
+
+struct Best { double v; int idx; };
+
+__global__ void __launch_bounds__(kThreads) limbs_kernel(const float* __restrict__ paf, PopnetDecodeParams p,
+                                                         PopnetDecodeOut o) {
+  extern __shared__ unsigned char s_raw[];
+  const int l = blockIdx.x, b = blockIdx.y;
+  const int H = p.grid_h, W = p.grid_w, cells = H * W;
+  const int K = p.num_joints, L = p.num_limbs, MP = p.max_peaks, NP = p.num_intermed_pts;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ta = p.limbs[l][0], tb = p.limbs[l][1];
+  const int na = o.peak_count[(size_t)b * K + ta], nb = o.peak_count[(size_t)b * K + tb];
+  if (na == 0 || nb == 0) {
+    if (tid == 0) o.conn_count[(size_t)b * L + l] = 0;
+    return;
+  }
+  double* s_score = reinterpret_cast<double*>(s_raw);                       // [na][nb]
+  float* s_px = reinterpret_cast<float*>(s_raw + sizeof(double) * MP * MP); // [cells]
+  float* s_py = s_px + cells;
+  __shared__ int16_t s_ax[POPNET_MAX_PEAKS], s_ay[POPNET_MAX_PEAKS], s_bx[POPNET_MAX_PEAKS], s_by[POPNET_MAX_PEAKS];
+  __shared__ unsigned char s_used_a[POPNET_MAX_PEAKS], s_used_b[POPNET_MAX_PEAKS];
+  __shared__ Best s_best[kThreads / 32];
+
+  const float* mx = paf + ((size_t)b * 2 * L + 2 * l) * cells;
+  for (int i = tid; i < cells; i += kThreads) { s_px[i] = mx[i]; s_py[i] = mx[cells + i]; }
+  for (int i = tid; i < na; i += kThreads) {
+    const int16_t* q = o.peak_xy + (((size_t)b * K + ta) * MP + i) * 2;
+    s_ax[i] = q[0]; s_ay[i] = q[1]; s_used_a[i] = 0;
+  }
+  for (int i = tid; i < nb; i += kThreads) {
+    const int16_t* q = o.peak_xy + (((size_t)b * K + tb) * MP + i) * 2;
+    s_bx[i] = q[0]; s_by[i] = q[1]; s_used_b[i] = 0;
+  }
+  __syncthreads();
+
+  const double Hup = (double)(H * p.stride);
+  const int npairs = na * nb;
+  for (int pr = tid; pr < npairs; pr += kThreads) {
+    const int i = pr / nb, j = pr - i * nb;
+    const int ax = s_ax[i], ay = s_ay[i], bx = s_bx[j], by = s_by[j];
+    const double dx = (double)bx - (double)ax, dy = (double)by - (double)ay;
+    const double dist = sqrt(dx * dx + dy * dy) + 1e-8;
+    const double ux = dx / dist, uy = dy / dist;
+    double s[32];                                      // NP <= 32 (checked on the host)
+    int above = 0;
+    const int body = NP & ~3;
+    for (int t = 0; t < NP; ++t) {
+      const int X = line_point(ax, bx, t, NP), Y = line_point(ay, by, t, NP);
+      const double px = (double)bicubic_at(s_px, W, H, W, X, Y), py = (double)bicubic_at(s_py, W, H, W, X, Y);
+      // ndarray.dot -> OpenBLAS dgemv: vector body fma(px,ux,py*uy), scalar tail fma(py,uy,px*ux)
+      s[t] = (t < body) ? fma(px, ux, py * uy) : fma(py, uy, px * ux);
+      above += s[t] > p.thresh_paf;
+    }
+    // np.mean: NumPy pairwise sum (plain loop below 8 elements, else 8 running sums + tail)
+    double sum;
+    if (NP < 8) {
+      sum = 0.0;
+      for (int t = 0; t < NP; ++t) sum += s[t];
+    } else {
+      double r8[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) r8[t] = s[t];
+      int t = 8;
+      for (; t + 8 <= NP; t += 8)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r8[u] += s[t + u];
+      sum = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+      for (; t < NP; ++t) sum += s[t];
+    }
+    double pen = 0.5 * Hup / dist - 1;
+    if (!(pen < 0)) pen = 0;
+    const double sc = sum / (double)NP + pen;
+    s_score[i * MP + j] = ((double)above > 0.8 * (double)NP && sc > 0) ? sc : -CUDART_INF;
+  }
+  __syncthreads();
+
+  // Stable descending sort + greedy (paf_to_pose.py:241-261) == repeatedly take the best remaining
+  // pair whose ends are both free, ties to the smallest (i, j).
+  const int maxc = min(na, nb);
+  int nconn = 0;
+  while (nconn < maxc) {
+    double bv = -CUDART_INF;
+    int bi = 0x7fffffff;
+    for (int pr = tid; pr < npairs; pr += kThreads) {
+      const int i = pr / nb, j = pr - i * nb;
+      if (s_used_a[i] || s_used_b[j]) continue;
+      const double v = s_score[i * MP + j];
+      if (v > bv) { bv = v; bi = pr; }
+    }
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+      const double ov = __shfl_xor_sync(kFull, bv, ofs);
+      const int oi = __shfl_xor_sync(kFull, bi, ofs);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_best[warp].v = bv; s_best[warp].idx = bi; }
+    __syncthreads();
+    bv = s_best[0].v; bi = s_best[0].idx;
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; ++w) {
+      const double ov = s_best[w].v;
+      const int oi = s_best[w].idx;
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (bi == 0x7fffffff) break;                       // uniform: nothing admissible is left
+    const int i = bi / nb, j = bi - i * nb;
+    if (tid == 0) {
+      s_used_a[i] = 1; s_used_b[j] = 1;
+      const size_t slot = ((size_t)b * L + l) * MP + nconn;
+      o.conn_ij[slot * 2] = (int16_t)i;
+      o.conn_ij[slot * 2 + 1] = (int16_t)j;
+      o.conn_score[slot] = bv;
+    }
+    ++nconn;
+    __syncthreads();
+  }
+  if (tid == 0) o.conn_count[(size_t)b * L + l] = nconn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// D5 + D7..D9: assembly, pruning, lift (one warp per frame)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sum_pairwise_f32(const float* a, int n) {
+  if (n < 8) {
+    float r = 0.f;
+    for (int i = 0; i < n; ++i) r += a[i];
+    return r;
+  }
+  float r = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  for (int i = 8; i < n; ++i) r += a[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(32) assemble_kernel(const float* __restrict__ heat, const float* __restrict__ depth,
+                                                      PopnetDecodeParams p, PopnetDecodeOut o) {
+  __shared__ int16_t s_pj[POPNET_MAX_PERSONS][POPNET_MAX_JOINTS];
+  __shared__ double s_ps[POPNET_MAX_PERSONS];
+  __shared__ int s_pc[POPNET_MAX_PERSONS];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int K = p.num_joints, L = p.num_limbs, MP = p.max_peaks, MM = p.max_persons;
+  const int H = p.grid_h, W = p.grid_w, cells = H * W;
+  int np_ = 0;
+  unsigned flags = 0;
+
+  for (int l = 0; l < L; ++l) {
+    const int ta = p.limbs[l][0], tb = p.limbs[l][1];
+    const int nc = o.conn_count[(size_t)b * L + l];
+    for (int c = 0; c < nc; ++c) {
+      const size_t slot = ((size_t)b * L + l) * MP + c;
+      const int ia = o.conn_ij[slot * 2], ib = o.conn_ij[slot * 2 + 1];
+      const double ls = o.conn_score[slot];
+      // persons whose src or dst slot already holds this joint (paf_to_pose.py:285-287)
+      unsigned long long hits = 0;
+      for (int q0 = 0; q0 < np_; q0 += 32) {
+        const int q = q0 + lane;
+        const bool h = q < np_ && (s_pj[q][ta] == ia || s_pj[q][tb] == ib);
+        hits |= (unsigned long long)__ballot_sync(kFull, h) << q0;
+      }
+      const int nh = __popcll(hits);
+      const double sb = (double)o.peak_score[((size_t)b * K + tb) * MP + ib];
+      if (nh == 1) {
+        const int q = __ffsll((long long)hits) - 1;
+        if (lane == 0 && s_pj[q][tb] != ib) {
+          s_pj[q][tb] = (int16_t)ib;
+          s_pc[q] += 1;
+          s_ps[q] += sb + ls;
+        }
+      } else if (nh == 2) {
+        const int q1 = __ffsll((long long)hits) - 1;
+        const int q2 = __ffsll((long long)(hits & (hits - 1))) - 1;
+        const bool ov = lane < K && s_pj[q1][lane] >= 0 && s_pj[q2][lane] >= 0;
+        if (!__any_sync(kFull, ov)) {
+          if (lane < K) s_pj[q1][lane] = (int16_t)(s_pj[q1][lane] + s_pj[q2][lane] + 1);
+          if (lane == 0) {
+            s_ps[q1] += s_ps[q2];
+            s_pc[q1] += s_pc[q2];
+            s_ps[q1] += ls;
+          }
+          __syncwarp();
+          for (int q = q2; q + 1 < np_; ++q) {        // list.pop(q2): later persons move up
+            if (lane < K) s_pj[q][lane] = s_pj[q + 1][lane];
+            if (lane == 0) { s_ps[q] = s_ps[q + 1]; s_pc[q] = s_pc[q + 1]; }
+            __syncwarp();
+          }
+          --np_;
+        } else if (lane == 0) {
+          s_pj[q1][tb] = (int16_t)ib;
+          s_pc[q1] += 1;
+          s_ps[q1] += sb + ls;
+        }
+      } else {                                          // 0 or >= 3 matches: a new person
+        if (np_ >= MM) flags |= POPNET_FLAG_PERSON_OVERFLOW;
+        else {
+          if (lane < POPNET_MAX_JOINTS) s_pj[np_][lane] = (lane == ta) ? (int16_t)ia : (lane == tb) ? (int16_t)ib : (int16_t)-1;
+          if (lane == 0) {
+            const double sa = (double)o.peak_score[((size_t)b * K + ta) * MP + ia];
+            s_pc[np_] = 2;
+            s_ps[np_] = ((0 + sa) + sb) + ls;
+          }
+          ++np_;
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  int nout = 0;
+  for (int q = 0; q < np_; ++q) {
+    const double cnt = (double)s_pc[q], sc = s_ps[q];
+    if (cnt < 3 || sc / cnt < 0.2) continue;            // paf_to_pose.py:338-346
+    const size_t row = (size_t)b * MM + nout;
+    if (lane == 0) {
+      if (o.person_score) o.person_score[row] = sc;
+      if (o.person_njoint) o.person_njoint[row] = s_pc[q];
+    }
+    if (lane < K) {
+      const int k = lane, idx = s_pj[q][k];
+      if (o.person_peak) o.person_peak[row * K + k] = (int16_t)idx;
+      double x2 = -1, y2 = -1, Z = -1, conf = 0;
+      if (idx >= 0) {
+        const size_t ps = ((size_t)b * K + k) * MP + idx;
+        const int X = o.peak_xy[ps * 2], Y = o.peak_xy[ps * 2 + 1];
+        conf = (double)o.peak_score[ps];
+        if (depth) {                                     // common.py:272-293, fp32, NumPy pairwise order
+          const int cx = X / p.stride, cy = Y / p.stride;
+          const int x0 = clampi(cx - 1, 0, W - 1), x1 = clampi(cx + 1, 0, W - 1);
+          const int y0 = clampi(cy - 1, 0, H - 1), y1 = clampi(cy + 1, 0, H - 1);
+          const float* hm = heat + ((size_t)b * (K + 1) + k) * cells;
+          const float* dm = depth + ((size_t)b * K + k) * cells;
+          float wv[9], dv[9];
+          int n = 0;
+          for (int yy = y0; yy <= y1; ++yy)
+            for (int xx = x0; xx <= x1; ++xx) {
+              float hv = hm[yy * W + xx];
+              if (hv < 0) hv = 0;
+              const float w = hv + 0.000000001f;
+              float d = dm[yy * W + xx] * p.depth_std;
+              d = d + p.depth_mean;
+              wv[n] = w; dv[n] = d * w; ++n;
+            }
+          Z = (double)(sum_pairwise_f32(dv, n) / sum_pairwise_f32(wv, n));
+        }
+        x2 = (double)X / p.input_size * p.w_org;
+        y2 = (double)Y / p.input_size * p.h_org;
+      }
+      if (o.pose2d) { o.pose2d[(row * K + k) * 2] = x2; o.pose2d[(row * K + k) * 2 + 1] = y2; }
+      if (o.pose_conf) o.pose_conf[row * K + k] = conf;
+      if (o.pose3d && depth) {
+        double X3 = (x2 - p.cx) * Z / p.fx, Y3 = (y2 - p.cy) * Z / p.fy;
+        if (p.flip_y) Y3 = -Y3;
+        double* d3 = o.pose3d + (row * K + k) * 3;
+        d3[0] = X3; d3[1] = Y3; d3[2] = Z;
+      }
+    }
+    ++nout;
+  }
+  if (lane == 0) {
+    o.n_person[b] = nout;
+    if (flags) atomicOr(o.flags + b, flags);
+  }
+}
+
+bool g_tables_uploaded = false;
+
+int upload_tables() {
+  // OpenCV interpolateCubic in fp32 (exact: all operands are small dyadic rationals)
+  int ofs[8];
+  float coef[8][4];
+  for (int r = 0; r < 8; ++r) {
+    const float fx = (float)((r + 0.5) * 0.125 - 0.5);
+    const int s = (int)floorf(fx);
+    const float x = fx - (float)s, A = -0.75f;
+    ofs[r] = s;
+    coef[r][0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+    coef[r][1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+    coef[r][2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+    coef[r][3] = 1.f - coef[r][0] - coef[r][1] - coef[r][2];
+  }
+  POPNET_CUDA_TRY(cudaMemcpyToSymbol(c_ofs, ofs, sizeof(ofs)));
+  POPNET_CUDA_TRY(cudaMemcpyToSymbol(c_coef, coef, sizeof(coef)));
+  return POPNET_OK;
+}
+
+}  // namespace
+
+extern "C" int popnet_decode(const float* heat, const float* paf, const float* depth, int batch,
+                             const PopnetDecodeParams* p, const PopnetDecodeOut* o, void* stream) {
+  if (!heat || !paf || !p || !o || batch < 0) return POPNET_ERR_INVALID_ARG;
+  // peak_* and conn_* double as the stage-to-stage storage and are therefore mandatory
+  if (!o->peak_count || !o->peak_xy || !o->peak_score || !o->conn_count || !o->conn_ij || !o->conn_score ||
+      !o->n_person || !o->flags)
+    return POPNET_ERR_INVALID_ARG;
+  if (p->num_joints < 1 || p->num_joints > POPNET_MAX_JOINTS || p->num_limbs < 1 || p->num_limbs > POPNET_MAX_LIMBS ||
+      p->stride != 8 || p->max_peaks < 1 || p->max_peaks > POPNET_MAX_PEAKS || p->max_persons < 1 ||
+      p->max_persons > POPNET_MAX_PERSONS || p->grid_h < 1 || p->grid_w < 1 || p->grid_h * p->grid_w > kMaxCells ||
+      p->num_intermed_pts < 1 || p->num_intermed_pts > 32 || p->num_joints > 32)
+    return POPNET_ERR_UNSUPPORTED;
+  for (int l = 0; l < p->num_limbs; ++l)
+    if (p->limbs[l][0] < 0 || p->limbs[l][0] >= p->num_joints || p->limbs[l][1] < 0 || p->limbs[l][1] >= p->num_joints)
+      return POPNET_ERR_INVALID_ARG;
+  if (batch == 0) return POPNET_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!g_tables_uploaded) {      // idempotent constant upload (same bytes every time)
+    int rc = upload_tables();
+    if (rc != POPNET_OK) return rc;
+    g_tables_uploaded = true;
+  }
+  POPNET_CUDA_TRY(cudaMemsetAsync(o->flags, 0, sizeof(uint32_t) * batch, st));
+  const int cells = p->grid_h * p->grid_w;
+  const size_t smem_peaks = sizeof(float) * cells;
+  const size_t smem_limbs = sizeof(double) * p->max_peaks * p->max_peaks + 2 * sizeof(float) * cells;
+  if (smem_limbs > 48 * 1024)
+    POPNET_CUDA_TRY(cudaFuncSetAttribute(limbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limbs));
+  peaks_kernel<<<dim3(p->num_joints, batch), kThreads, smem_peaks, st>>>(heat, *p, *o);
+  POPNET_AFTER_LAUNCH();
+  limbs_kernel<<<dim3(p->num_limbs, batch), kThreads, smem_limbs, st>>>(paf, *p, *o);
+  POPNET_AFTER_LAUNCH();
+  assemble_kernel<<<batch, 32, 0, st>>>(heat, depth, *p, *o);
+  POPNET_AFTER_LAUNCH();
+  return POPNET_OK;
+}

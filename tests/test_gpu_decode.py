@@ -1,0 +1,77 @@
+"""GPU parity: CUDA decode + lift (through the C ABI) against the C oracle and the reference's golden outputs."""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import DECODE_CASES, golden
+from popnet_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", DECODE_CASES, ids=[c[0] for c in DECODE_CASES])
+def test_decode_bitwise_vs_oracle_and_reference(case, cuda_backend, oracle_lib):
+    g = golden("decode_golden")
+    heat, paf, depth = helpers.decode_case_inputs(case)
+    params = helpers.params_for(case[5])
+    dev = cuda_backend.decode(heat, paf, depth, params)
+    ora = oracle_lib.decode(heat, paf, depth, params)
+    assert helpers.records_equal(dev, ora) == []
+    for f in range(heat.shape[0]):
+        ok, why = helpers.compare_to_golden(dev, f, g, "%s/native/%d/" % (case[0], f), exact=True)
+        assert ok, "frame %d vs reference (OpenCV C++ path): %s" % (f, why)
+        ok, why = helpers.compare_to_golden(dev, f, g, "%s/ipp/%d/" % (case[0], f), exact=False)
+        assert ok, "frame %d vs reference (IPP path): %s" % (f, why)
+
+
+@pytest.mark.parametrize("batch,persons,seed", [(64, (1, 6), 1234), (256, (12, 16), 4242), (512, (1, 6), 77)],
+                         ids=["C2-b64", "C5-crowd-b256", "C4-b512"])
+def test_decode_full_size_vs_oracle(batch, persons, seed, cuda_backend, oracle_lib):
+    """BASELINE.json configs C2 / C5 / C4 at their full batch sizes, byte-for-byte against the oracle."""
+    heat, paf, depth, _ = synth.map_batch(batch, seed=seed, persons=persons, noise=0.01)
+    params = helpers.params_for("MP3DHP")
+    dev = cuda_backend.decode(heat, paf, depth, params)
+    ora = oracle_lib.decode(heat, paf, depth, params)
+    assert helpers.records_equal(dev, ora) == []
+    assert int(dev["n_person"].sum()) > batch * persons[0] * 0.5
+
+
+def test_decode_shard_invariance(cuda_backend):
+    """Frames are independent: decoding a batch in shards gives the same records (the multi-GPU contract)."""
+    heat, paf, depth, _ = synth.map_batch(48, seed=9, persons=(1, 6), noise=0.01)
+    params = helpers.params_for("MP3DHP")
+    full = cuda_backend.decode(heat, paf, depth, params)
+    parts = [cuda_backend.decode(heat[s], paf[s], depth[s], params) for s in (slice(0, 16), slice(16, 17), slice(17, 48))]
+    cat = {k: np.concatenate([p[k] for p in parts], 0) for k in full}
+    assert helpers.records_equal(full, cat) == []
+
+
+def test_decode_degenerate_overflow_flags(cuda_backend, oracle_lib):
+    """Untrained-network-like maps (heat ~ 0.5 everywhere): hundreds of plateau peaks per joint
+    type.  Capacities overflow; flags and the truncated records must match the oracle's."""
+    rng = np.random.default_rng(0)
+    heat = (0.5 + 0.01 * rng.standard_normal((3, 16, 28, 28))).astype(np.float32)
+    heat[2] = 0.5                                         # one giant plateau: every cell is a peak
+    paf = (0.05 * rng.standard_normal((3, 28, 28, 28))).astype(np.float32)
+    depth = rng.standard_normal((3, 15, 28, 28)).astype(np.float32)
+    params = helpers.params_for("MP3DHP")
+    dev = cuda_backend.decode(heat, paf, depth, params)
+    ora = oracle_lib.decode(heat, paf, depth, params)
+    assert (dev["flags"] & 1).all()
+    assert helpers.records_equal(dev, ora) == []
+
+
+def test_paf_to_pose_signature(cuda_backend):
+    """The reference-facing call: HWC maps of one frame in, (joint_list, person_to_joint_assoc) out."""
+    from types import SimpleNamespace as NS
+    from popnet_b200.decode import paf_to_pose, paf_to_human_list
+    g = golden("decode_golden")
+    heat, paf, depth = helpers.decode_case_inputs(DECODE_CASES[0])
+    cfg = NS(MODEL=NS(NUM_KEYPOINTS=15, NUM_LIMBS=14, DOWNSAMPLE=8),
+             TEST=NS(THRESH_HEATMAP=0.1, THRESH_PAF=0.05, NUM_INTERMED_PTS_BETWEEN_KEYPOINTS=10))
+    for f in (0, 1, 5):
+        jl, assoc = paf_to_pose(heat[f].transpose(1, 2, 0), paf[f].transpose(1, 2, 0), cfg)
+        assert np.array_equal(jl, g["mp/native/%d/joint_list" % f])
+        assert np.array_equal(np.asarray(assoc).reshape(-1, 17), g["mp/native/%d/assoc" % f])
+        humans, vis, conf = paf_to_human_list(jl, assoc)
+        assert len(humans) == len(g["mp/native/%d/assoc" % f])

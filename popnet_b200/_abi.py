@@ -90,14 +90,9 @@ PROTOTYPES = {
 }
 
 
-_PENDING = {'popnet_num_conv_layers','popnet_packed_weight_bytes','popnet_workspace_bytes','popnet_pack_weights','popnet_forward'}
-
-
 def bind(lib):
     """Attach restype/argtypes to every declared symbol; raises AttributeError on a missing export."""
     for name, (res, args) in PROTOTYPES.items():
-        if not hasattr(lib, name) and name in _PENDING:
-            continue
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -1,0 +1,492 @@
+// Convolution kernels of the rtpose_light3d forward (reference: third_party_methods/lib/network/
+// rtpose_light3d.py:24-32, 56-72, 145-158, 222-246 -- nn.Conv2d + eval-mode BatchNorm2d + ReLU /
+// LeakyReLU(0.1) + residual add + AvgPool2d(3,2,1), which the reference runs through cuDNN/ATen).
+//
+//   conv_tc_kernel   the product path: implicit GEMM on the 5th-generation tensor cores.
+//                    D[128 positions x NT channels] (fp32, TMEM) += A[positions x 16 cin] * B[NT x 16 cin]
+//                    issued as tcgen05.mma.cta_group::1.kind::f16 by one thread; operands are staged in
+//                    shared memory by bulk-async copies (cp.async.bulk + mbarrier complete_tx) in the
+//                    canonical no-swizzle K-major core-matrix layout, which is exactly the C8P activation
+//                    layout (conv.cuh), so a 3x3 tap is a descriptor start-address shift and every input
+//                    tile is fetched once per 64 input channels instead of once per tap.
+//                    Warp roles: 0 = copy producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue
+//                    (tcgen05.ld -> +shift, residual, activation -> bf16 C8P store and/or fp32 NCHW head).
+//   conv_simt_kernel a plain CUDA-core evaluation of the same packed operands, used by tests / bring-up
+//                    to localise tensor-core descriptor mistakes (POPNET_FWD_IMPL_SIMT); not a product path.
+//   stem_kernel      model0.conv1 (7x7, stride 2, C_in = 1): direct fp32 evaluation, 0.6 % of the FLOPs.
+//   pool_kernel      AvgPool2d(3, 2, 1) with count_include_pad (always / 9) on C8P planes.
+//
+// Roofline: tensor pipe for conv_tc_kernel (13.34 GFLOP per frame in total); HBM for the
+// stem and the pools.
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "conv.cuh"
+
+namespace popnet {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0, 16 B aligned)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_NONE, K-major: 8 rows x 16 B core matrices, rows 16 B apart inside
+// a core matrix; SBO = byte distance between 8-row groups (M/N direction), LBO = byte distance between the
+// two core matrices one K=16 instruction consumes (cute/atom/mma_traits_sm100.hpp, "INTERLEAVE" K-major).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor for kind::f16: D = F32, A = B = BF16, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue shared by the tensor-core and the SIMT kernels
+// ------------------------------------------------------------------------------------------------
+struct PosInfo {
+  bool in_range, interior;
+  int n, h, w;
+};
+
+__device__ __forceinline__ PosInfo locate(int pos, const ConvArgs& a) {
+  PosInfo r;
+  r.in_range = pos < a.P;
+  const int per = a.Hp * a.Wp;
+  const int n = pos / per, rem = pos - n * per;
+  const int hp = rem / a.Wp, wp = rem - hp * a.Wp;
+  r.interior = r.in_range && hp >= 1 && hp <= a.Hp - 2 && wp >= 1 && wp <= a.Wp - 2;
+  r.n = n; r.h = hp - 1; r.w = wp - 1;
+  return r;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// v: raw accumulators of channels ch0 .. ch0+7 at `pos`
+__device__ __forceinline__ void finish8(const ConvArgs& a, int pos, const PosInfo& pi, int ch0, const float (&v)[8]) {
+  if (!pi.in_range) return;
+  __align__(16) __nv_bfloat16 ob[8];
+  if (pi.interior) {
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = 0.f;
+    if (a.res) {
+      const uint4 q = *reinterpret_cast<const uint4*>(a.res + (long long)(ch0 >> 3) * a.res_plane_stride + (long long)pos * 8);
+      const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = __bfloat162float(rb[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float x = v[i] + __ldg(a.shift + ch0 + i) + r[i];
+      switch (a.act) {
+        case kActRelu: x = fmaxf(x, 0.f); break;
+        case kActLeaky: x = x > 0.f ? x : 0.1f * x; break;
+        case kActHeadPaf: x = (sigmoidf_(x) - 0.5f) * 4.f; break;      // rtpose_light3d.py:335,337
+        case kActHeadHeat: x = sigmoidf_(x); break;                    // rtpose_light3d.py:336
+        default: break;
+      }
+      if (a.head_out && ch0 + i < a.cout) {
+        const int H = a.Hp - 2, W = a.Wp - 2;
+        a.head_out[(((long long)pi.n * a.cout + ch0 + i) * H + pi.h) * W + pi.w] = x;
+      }
+      if (ch0 + i >= a.cout) x = 0.f;                                  // padded channels stay zero
+      ob[i] = __float2bfloat16(x);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ob[i] = __float2bfloat16(0.f);
+  }
+  if (a.out)
+    *reinterpret_cast<uint4*>(a.out + (long long)(ch0 >> 3) * a.out_plane_stride + (long long)pos * 8) =
+        *reinterpret_cast<const uint4*>(ob);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core implicit GEMM
+// ------------------------------------------------------------------------------------------------
+constexpr int kTcThreads = 256;
+
+template <int NT, int NACC, int TAPS, int BST>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int MT = NACC * 128;
+  constexpr uint32_t kBStageBytes = 8u * NT * 16u;          // 64 input channels x NT output channels
+  constexpr uint32_t kCols = (NACC * NT <= 32) ? 32 : (NACC * NT <= 64) ? 64 : (NACC * NT <= 128) ? 128
+                             : (NACC * NT <= 256) ? 256 : 512;
+  static_assert(NACC * NT <= 512, "accumulators exceed TMEM");
+  const int halo = (TAPS == 9) ? a.Wp + 1 : 0;
+  const int apos = MT + 2 * halo;                            // positions per staged plane
+  const uint32_t a_plane_bytes = (uint32_t)apos * 16u;
+  const uint32_t a_stage_bytes = 8u * a_plane_bytes;
+  const int ast = a.a_stages;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (((size_t)ast * a_stage_bytes + 127) & ~(size_t)127);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)BST * kBStageBytes);
+  // bars: [0,2) a_full, [2,4) a_empty, [4,4+BST) b_full, [4+BST,4+2BST) b_empty, [4+2BST] acc_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * BST + 1);
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (4 + BST + s); };
+  const uint32_t acc_full = bar0 + 8u * (4 + 2 * BST);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * MT;
+  const int ntile = blockIdx.y;
+  const int chunks = a.chunks;
+  const int k8_total = chunks * 8;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4 + 2 * BST + 1; ++i) mbar_init(bar0 + 8u * i, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), kCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- producer ----------------
+      const __nv_bfloat16* wbase = a.w + (long long)ntile * TAPS * k8_total * NT * 8;
+      for (int c = 0; c < chunks; ++c) {
+        const int as = c % ast;
+        if (c >= ast) mbar_wait(a_empty(as), ((c / ast) - 1) & 1);
+        mbar_expect_tx(a_full(as), a_stage_bytes);
+        for (int g = 0; g < 8; ++g)
+          bulk_g2s(smem_u32(sA + (size_t)as * a_stage_bytes + (size_t)g * a_plane_bytes),
+                   a.in + (long long)(c * 8 + g) * a.in_plane_stride + (long long)(t0 - halo) * 8, a_plane_bytes,
+                   a_full(as));
+        for (int t = 0; t < TAPS; ++t) {
+          const int it = c * TAPS + t, bs = it % BST;
+          if (it >= BST) mbar_wait(b_empty(bs), ((it / BST) - 1) & 1);
+          mbar_expect_tx(b_full(bs), kBStageBytes);
+          bulk_g2s(smem_u32(sB + (size_t)bs * kBStageBytes), wbase + ((long long)t * k8_total + c * 8) * NT * 8,
+                   kBStageBytes, b_full(bs));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = umma_idesc(NT);
+      const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
+      const uint32_t a_lbo = a.lbo_sbo_swapped ? 128u : a_plane_bytes, a_sbo = a.lbo_sbo_swapped ? a_plane_bytes : 128u;
+      const uint32_t b_lbo = a.lbo_sbo_swapped ? 128u : (uint32_t)NT * 16u, b_sbo = a.lbo_sbo_swapped ? (uint32_t)NT * 16u : 128u;
+      for (int c = 0; c < chunks; ++c) {
+        const int as = c % ast;
+        mbar_wait(a_full(as), (c / ast) & 1);
+        tc_fence_after();
+        for (int t = 0; t < TAPS; ++t) {
+          const int it = c * TAPS + t, bs = it % BST;
+          mbar_wait(b_full(bs), (it / BST) & 1);
+          tc_fence_after();
+          const int shift = (TAPS == 9) ? ((t / 3 - 1) * a.Wp + (t % 3 - 1) + halo) : 0;
+#pragma unroll
+          for (int acc = 0; acc < NACC; ++acc) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t da = umma_desc(sA0 + as * a_stage_bytes + (2 * kk) * a_plane_bytes + (uint32_t)(shift + acc * 128) * 16u,
+                                            a_lbo, a_sbo);
+              const uint64_t db = umma_desc(sB0 + bs * kBStageBytes + (2 * kk) * NT * 16u, b_lbo, b_sbo);
+              umma_bf16(tmem_base + acc * NT, da, db, idesc, (c | t | kk) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(b_empty(bs));       // B stage reusable once these MMAs retire
+        }
+        umma_commit(a_empty(as));
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue: TMEM lane quarter q, thread = one output position ----------------
+    const int q = warp & 3;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int acc = 0; acc < NACC; ++acc) {
+      const int pos = t0 + acc * 128 + q * 32 + lane;
+      const PosInfo pi = locate(pos, a);
+#pragma unroll 1
+      for (int j = 0; j < NT / 16; ++j) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + j * 16), r);
+        tmem_ld_wait();
+        float v[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h * 8 + i]);
+          finish8(a, pos, pi, ntile * NT + j * 16 + h * 8, v);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core check kernel: one thread = one position x 8 output channels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) conv_simt_kernel(const ConvArgs a) {
+  const int pos = blockIdx.x * 128 + threadIdx.x;
+  const int ch0 = blockIdx.y * 8;
+  const PosInfo pi = locate(pos, a);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (pi.interior) {
+    const int k8_total = a.chunks * 8;
+    const int nti = ch0 / a.nt, nn = ch0 - nti * a.nt;
+    for (int t = 0; t < a.taps; ++t) {
+      const int shift = (a.taps == 9) ? ((t / 3 - 1) * a.Wp + (t % 3 - 1)) : 0;
+      for (int g = 0; g < k8_total; ++g) {
+        const uint4 xa = *reinterpret_cast<const uint4*>(a.in + (long long)g * a.in_plane_stride + (long long)(pos + shift) * 8);
+        const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(&xa);
+        const __nv_bfloat16* wrow = a.w + ((((long long)nti * a.taps + t) * k8_total + g) * a.nt + nn) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 wa = *reinterpret_cast<const uint4*>(wrow + i * 8);
+          const __nv_bfloat16* wb = reinterpret_cast<const __nv_bfloat16*>(&wa);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i] = fmaf(__bfloat162float(xb[j]), __bfloat162float(wb[j]), acc[i]);
+        }
+      }
+    }
+  }
+  finish8(a, pos, pi, ch0, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem: 7x7 stride 2 pad 3, one input channel, + folded BN + ReLU -> C8P bf16 (64 channels)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) stem_kernel(const StemArgs a) {
+  __shared__ float s_w[49 * 64];
+  __shared__ float s_shift[64];
+  for (int i = threadIdx.x; i < 49 * 64; i += 128) s_w[i] = a.w[i];
+  if (threadIdx.x < 64) s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  __syncthreads();
+  const int Ho = a.H / 2, Wo = a.W / 2, Hp = Ho + 2, Wp = Wo + 2;
+  const int P = a.N * Hp * Wp;
+  const int pos = blockIdx.x * 128 + threadIdx.x;
+  if (pos >= P) return;
+  const int g = blockIdx.y;                         // output plane (8 channels)
+  const int n = pos / (Hp * Wp), rem = pos - n * Hp * Wp;
+  const int hp = rem / Wp, wp = rem - hp * Wp;
+  __align__(16) __nv_bfloat16 ob[8];
+  if (hp >= 1 && hp <= Ho && wp >= 1 && wp <= Wo) {
+    const int oy = hp - 1, ox = wp - 1;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const float* img = a.x + (long long)n * a.H * a.W;
+    for (int ky = 0; ky < 7; ++ky) {
+      const int iy = oy * 2 - 3 + ky;
+      if (iy < 0 || iy >= a.H) continue;
+      for (int kx = 0; kx < 7; ++kx) {
+        const int ix = ox * 2 - 3 + kx;
+        if (ix < 0 || ix >= a.W) continue;
+        const float xv = __ldg(img + iy * a.W + ix);
+        const float* wr = s_w + (ky * 7 + kx) * 64 + g * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, wr[i], acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ob[i] = __float2bfloat16(fmaxf(acc[i] + s_shift[g * 8 + i], 0.f));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ob[i] = __float2bfloat16(0.f);
+  }
+  *reinterpret_cast<uint4*>(a.out + (long long)g * a.out_plane_stride + (long long)pos * 8) = *reinterpret_cast<const uint4*>(ob);
+}
+
+// ------------------------------------------------------------------------------------------------
+// AvgPool2d(3, stride 2, pad 1), divisor always 9; the zero ring of the input IS the padding
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pool_kernel(const PoolArgs a) {
+  const int Ho = a.H / 2, Wo = a.W / 2, Hpo = Ho + 2, Wpo = Wo + 2, Wpi = a.W + 2, Hpi = a.H + 2;
+  const int P = a.N * Hpo * Wpo;
+  const int pos = blockIdx.x * 128 + threadIdx.x;
+  if (pos >= P) return;
+  const int g = blockIdx.y;
+  const int n = pos / (Hpo * Wpo), rem = pos - n * Hpo * Wpo;
+  const int hp = rem / Wpo, wp = rem - hp * Wpo;
+  __align__(16) __nv_bfloat16 ob[8];
+  if (hp >= 1 && hp <= Ho && wp >= 1 && wp <= Wo) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    // output (oy, ox) covers input rows 2oy-1 .. 2oy+1 -> padded rows 2oy .. 2oy+2
+    const __nv_bfloat16* src = a.in + (long long)g * a.in_plane_stride + ((long long)n * Hpi * Wpi) * 8;
+    const int py = 2 * (hp - 1), px = 2 * (wp - 1);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const uint4 q = *reinterpret_cast<const uint4*>(src + ((long long)(py + dy) * Wpi + px + dx) * 8);
+        const __nv_bfloat16* qb = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += __bfloat162float(qb[i]);
+      }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ob[i] = __float2bfloat16(acc[i] * (1.f / 9.f));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ob[i] = __float2bfloat16(0.f);
+  }
+  *reinterpret_cast<uint4*>(a.out + (long long)g * a.out_plane_stride + (long long)pos * 8) = *reinterpret_cast<const uint4*>(ob);
+}
+
+template <int NT, int NACC, int TAPS, int BST>
+int launch_tc_inst(const ConvArgs& a, size_t smem, cudaStream_t st) {
+  auto kern = conv_tc_kernel<NT, NACC, TAPS, BST>;
+  POPNET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int MT = NACC * 128;
+  dim3 grid((a.P + MT - 1) / MT, a.cout_pad / NT);
+  kern<<<grid, kTcThreads, smem, st>>>(a);
+  POPNET_AFTER_LAUNCH();
+  return POPNET_OK;
+}
+
+template <int NT, int NACC, int TAPS>
+int launch_tc_bst(const ConvArgs& a, int bst, size_t smem, cudaStream_t st) {
+  switch (bst) {
+    case 2: return launch_tc_inst<NT, NACC, TAPS, 2>(a, smem, st);
+    case 3: return launch_tc_inst<NT, NACC, TAPS, 3>(a, smem, st);
+    default: return launch_tc_inst<NT, NACC, TAPS, 4>(a, smem, st);
+  }
+}
+
+}  // namespace
+
+constexpr size_t kSmemLimit = 227 * 1024;
+
+size_t conv_tc_smem_bytes(int nt, int nacc, int taps, int a_stages, int Wp, int* b_stages_out) {
+  const int halo = taps == 9 ? Wp + 1 : 0;
+  const size_t a_bytes = (((size_t)a_stages * 8 * (nacc * 128 + 2 * halo) * 16) + 127) & ~(size_t)127;
+  const size_t b_stage = (size_t)8 * nt * 16;
+  int bst = 4;
+  while (bst > 2 && a_bytes + bst * b_stage + 256 > kSmemLimit) --bst;
+  if (b_stages_out) *b_stages_out = bst;
+  return a_bytes + bst * b_stage + 256;
+}
+
+int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st) {
+  int bst = 0;
+  const size_t smem = conv_tc_smem_bytes(a.nt, nacc, a.taps, a.a_stages, a.Wp, &bst);
+  if (smem > kSmemLimit) return POPNET_ERR_UNSUPPORTED;
+#define POPNET_TC_CASE(NT_, NACC_, TAPS_) \
+  if (a.nt == NT_ && nacc == NACC_ && a.taps == TAPS_) return launch_tc_bst<NT_, NACC_, TAPS_>(a, bst, smem, st);
+  POPNET_TC_CASE(64, 2, 9)
+  POPNET_TC_CASE(64, 4, 9)
+  POPNET_TC_CASE(128, 2, 9)
+  POPNET_TC_CASE(128, 4, 9)
+  POPNET_TC_CASE(128, 4, 1)
+  POPNET_TC_CASE(256, 2, 9)
+  POPNET_TC_CASE(32, 4, 1)
+  POPNET_TC_CASE(16, 4, 9)
+#undef POPNET_TC_CASE
+  return POPNET_ERR_UNSUPPORTED;
+}
+
+int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
+  dim3 grid((a.P + 127) / 128, a.cout_pad / 8);
+  conv_simt_kernel<<<grid, 128, 0, st>>>(a);
+  POPNET_AFTER_LAUNCH();
+  return POPNET_OK;
+}
+
+int launch_stem(const StemArgs& a, cudaStream_t st) {
+  const int P = a.N * (a.H / 2 + 2) * (a.W / 2 + 2);
+  dim3 grid((P + 127) / 128, 8);
+  stem_kernel<<<grid, 128, 0, st>>>(a);
+  POPNET_AFTER_LAUNCH();
+  return POPNET_OK;
+}
+
+int launch_pool(const PoolArgs& a, cudaStream_t st) {
+  const int P = a.N * (a.H / 2 + 2) * (a.W / 2 + 2);
+  dim3 grid((P + 127) / 128, a.planes);
+  pool_kernel<<<grid, 128, 0, st>>>(a);
+  POPNET_AFTER_LAUNCH();
+  return POPNET_OK;
+}
+
+}  // namespace popnet

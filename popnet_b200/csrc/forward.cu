@@ -1,0 +1,318 @@
+// rtpose_light3d forward: layer plan, weight packing and launch schedule.
+//
+// Mirrors third_party_methods/lib/network/rtpose_light3d.py of the reference:
+//   ResPreprocessNet._forward_impl :201-216, BasicBlock.forward :56-72, make_stages :222-246,
+//   rtpose_light3d.__init__ :249-324 (channel tables) and forward :326-356.
+// Canonical conv-layer order (what popnet_pack_weights expects, 39 layers for num_stages = 2):
+//   0 model0.conv1 | 1-4 model0.layer1.{0,1}.conv{1,2} | 5 layer2.0.conv1 | 6 layer2.0.conv2 |
+//   7 layer2.0.downsample.0 | 8 model0.conv2 | 9 + 5*(3*(stage-1) + (branch-1)) + i : model{stage}_{branch}.{3i}
+//
+// Stage-2 input (reference: torch.cat([paf, heat, depth, feat], 1), 187 channels) is one 192-channel C8P
+// buffer laid out [paf 28 + 4 zero | heat 16 | depth 15 + 1 zero | feat 128]; the heads and the second
+// average pool write straight into their slices, so the concatenation never happens.
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "conv.cuh"
+
+namespace popnet {
+namespace {
+
+struct Buf {
+  int C, H, W;
+  size_t off;             // bf16 elements from the workspace start
+  long long plane_stride; // bf16 elements
+  int P;                  // N * (H+2) * (W+2)
+};
+
+enum BufId { A112, B112, C112, D56, E56, F56, G56, S2IN, LA, LB, LC, SA, SB_, DA, DB, DC, kNumBufs };
+
+struct Layer {
+  int cin, cout, k;          // logical
+  int cin_pad, cout_pad;
+  int nt, nacc;
+  int act;
+  int in_buf, in_plane0, out_buf, out_plane0, res_buf;
+  int head;                  // 0 none, 1 paf, 2 heat, 3 depth
+  int stage;                 // 0 block0, 1, 2
+  int remap_s2;              // input channels follow the S2IN layout
+  size_t w_off, shift_off;   // bytes in the packed blob
+};
+
+struct Plan {
+  Buf bufs[kNumBufs];
+  std::vector<Layer> layers;
+  size_t blob_bytes = 0, ws_bytes = 0;
+  int K, L, pl, ph, pd;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
+  if (cfg.input_dim != 1 || cfg.height % 8 || cfg.width % 8 || cfg.height < 16 || cfg.width < 16) return false;
+  if (cfg.num_parts < 1 || cfg.num_parts > 15 || cfg.num_limbs < 1 || cfg.num_limbs > 15) return false;
+  if (cfg.width / 2 + 3 > kGuard) return false;
+  p.K = cfg.num_parts; p.L = cfg.num_limbs;
+  p.pl = 32; p.ph = 16; p.pd = 16;
+  const int H2 = cfg.height / 2, W2 = cfg.width / 2, H4 = H2 / 2, W4 = W2 / 2, H8 = H4 / 2, W8 = W4 / 2;
+  auto setb = [&](int id, int C, int H, int W) { p.bufs[id].C = C; p.bufs[id].H = H; p.bufs[id].W = W; };
+  setb(A112, 64, H2, W2); setb(B112, 64, H2, W2); setb(C112, 64, H2, W2);
+  setb(D56, 64, H4, W4); setb(E56, 128, H4, W4); setb(F56, 128, H4, W4); setb(G56, 128, H4, W4);
+  setb(S2IN, 192, H8, W8);
+  setb(LA, 256, H8, W8); setb(LB, 256, H8, W8); setb(LC, 128, H8, W8);
+  setb(SA, 128, H8, W8); setb(SB_, 128, H8, W8);
+  setb(DA, 128, H8, W8); setb(DB, 64, H8, W8); setb(DC, 64, H8, W8);
+  size_t off = 0;
+  for (int i = 0; i < kNumBufs; ++i) {
+    Buf& b = p.bufs[i];
+    b.P = batch * (b.H + 2) * (b.W + 2);
+    b.plane_stride = (long long)(kGuard + align_up((size_t)(batch > 0 ? b.P : 0), kPosRound) + kGuard) * 8;
+    b.off = off;
+    off += (size_t)(b.C / 8) * b.plane_stride;
+    off = align_up(off, 128);
+  }
+  p.ws_bytes = off * sizeof(__nv_bfloat16);
+
+  auto add = [&](int cin, int cout, int k, int nt, int nacc, int act, int in_buf, int in_plane0, int out_buf,
+                 int out_plane0, int res_buf, int head, int stage, int remap) {
+    Layer l{};
+    l.cin = cin; l.cout = cout; l.k = k;
+    l.cin_pad = (k == 7) ? cin : (int)align_up(cin, 64);
+    l.cout_pad = (int)align_up(cout, nt);
+    l.nt = nt; l.nacc = nacc; l.act = act;
+    l.in_buf = in_buf; l.in_plane0 = in_plane0; l.out_buf = out_buf; l.out_plane0 = out_plane0; l.res_buf = res_buf;
+    l.head = head; l.stage = stage; l.remap_s2 = remap;
+    p.layers.push_back(l);
+  };
+  p.layers.clear();
+  // block0
+  add(1, 64, 7, 64, 0, kActRelu, -1, 0, A112, 0, -1, 0, 0, 0);              // 0 conv1 (stem kernel)
+  add(64, 64, 3, 64, 2, kActRelu, A112, 0, B112, 0, -1, 0, 0, 0);           // 1 layer1.0.conv1
+  add(64, 64, 3, 64, 2, kActRelu, B112, 0, C112, 0, A112, 0, 0, 0);         // 2 layer1.0.conv2 (+x)
+  add(64, 64, 3, 64, 2, kActRelu, C112, 0, B112, 0, -1, 0, 0, 0);           // 3 layer1.1.conv1
+  add(64, 64, 3, 64, 2, kActRelu, B112, 0, A112, 0, C112, 0, 0, 0);         // 4 layer1.1.conv2 (+x)
+  add(64, 128, 3, 128, 2, kActRelu, D56, 0, E56, 0, -1, 0, 0, 0);           // 5 layer2.0.conv1
+  add(128, 128, 3, 128, 4, kActRelu, E56, 0, G56, 0, F56, 0, 0, 0);         // 6 layer2.0.conv2 (+downsample)
+  add(64, 128, 1, 128, 4, kActNone, D56, 0, F56, 0, -1, 0, 0, 0);           // 7 layer2.0.downsample
+  add(128, 128, 1, 128, 4, kActRelu, G56, 0, E56, 0, -1, 0, 0, 0);          // 8 conv2
+  const int K1 = p.K + 1, L2 = 2 * p.L, L1 = p.L + 1;
+  for (int s = 1; s <= 2; ++s) {
+    const int in0 = (s == 1) ? (p.pl + p.ph + p.pd) / 8 : 0;     // stage 1 reads only the feature planes
+    const int cin = (s == 1) ? 128 : 128 + L2 + K1 + L1;
+    const int remap = (s == 2);
+    // paf branch: 3x3 -> 256, 256, 256, 1x1 -> 128, 1x1 -> 2L
+    add(cin, 256, 3, 256, 2, kActLeaky, S2IN, in0, LA, 0, -1, 0, s, remap);
+    add(256, 256, 3, 256, 2, kActLeaky, LA, 0, LB, 0, -1, 0, s, 0);
+    add(256, 256, 3, 256, 2, kActLeaky, LB, 0, LA, 0, -1, 0, s, 0);
+    add(256, 128, 1, 128, 4, kActLeaky, LA, 0, LC, 0, -1, 0, s, 0);
+    add(128, L2, 1, 32, 4, kActHeadPaf, LC, 0, (s == 1) ? S2IN : -1, 0, -1, 1, s, 0);
+    // heat-map branch: 3x3 -> 128 x4, 3x3 -> K+1
+    add(cin, 128, 3, 128, 4, kActLeaky, S2IN, in0, SA, 0, -1, 0, s, remap);
+    add(128, 128, 3, 128, 4, kActLeaky, SA, 0, SB_, 0, -1, 0, s, 0);
+    add(128, 128, 3, 128, 4, kActLeaky, SB_, 0, SA, 0, -1, 0, s, 0);
+    add(128, 128, 3, 128, 4, kActLeaky, SA, 0, SB_, 0, -1, 0, s, 0);
+    add(128, K1, 3, 16, 4, kActHeadHeat, SB_, 0, (s == 1) ? S2IN : -1, p.pl / 8, -1, 2, s, 0);
+    // depth branch: 3x3 -> 128, 64, 64, 64, 3x3 -> L+1
+    add(cin, 128, 3, 128, 4, kActLeaky, S2IN, in0, DA, 0, -1, 0, s, remap);
+    add(128, 64, 3, 64, 4, kActLeaky, DA, 0, DB, 0, -1, 0, s, 0);
+    add(64, 64, 3, 64, 4, kActLeaky, DB, 0, DC, 0, -1, 0, s, 0);
+    add(64, 64, 3, 64, 4, kActLeaky, DC, 0, DB, 0, -1, 0, s, 0);
+    add(64, L1, 3, 16, 4, kActHeadPaf, DB, 0, (s == 1) ? S2IN : -1, (p.pl + p.ph) / 8, -1, 3, s, 0);
+  }
+  size_t boff = 0;
+  for (Layer& l : p.layers) {
+    const size_t wbytes = (l.k == 7) ? (size_t)49 * 64 * sizeof(float)
+                                     : (size_t)l.k * l.k * l.cin_pad * l.cout_pad * sizeof(__nv_bfloat16);
+    l.w_off = boff; boff = align_up(boff + wbytes, 256);
+    l.shift_off = boff; boff = align_up(boff + (size_t)l.cout_pad * sizeof(float), 256);
+  }
+  p.blob_bytes = boff;
+  return true;
+}
+
+// S2IN channel -> channel of the reference's torch.cat([paf, heat, depth, feat]) or -1 for padding
+int s2_to_ref(const Plan& p, int c) {
+  const int L2 = 2 * p.L, K1 = p.K + 1, L1 = p.L + 1;
+  if (c < p.pl) return c < L2 ? c : -1;
+  c -= p.pl;
+  if (c < p.ph) return c < K1 ? L2 + c : -1;
+  c -= p.ph;
+  if (c < p.pd) return c < L1 ? L2 + K1 + c : -1;
+  c -= p.pd;
+  return L2 + K1 + L1 + c;
+}
+
+__nv_bfloat16* buf_ptr(void* ws, const Buf& b, int plane0) {
+  return static_cast<__nv_bfloat16*>(ws) + b.off + (size_t)plane0 * b.plane_stride + (size_t)kGuard * 8;
+}
+
+}  // namespace
+}  // namespace popnet
+
+using namespace popnet;
+
+extern "C" int popnet_num_conv_layers(const PopnetNetConfig* cfg) {
+  Plan p;
+  if (!cfg || !make_plan(*cfg, 1, p)) return POPNET_ERR_UNSUPPORTED;
+  return (int)p.layers.size();
+}
+
+extern "C" size_t popnet_packed_weight_bytes(const PopnetNetConfig* cfg) {
+  Plan p;
+  if (!cfg || !make_plan(*cfg, 1, p)) return 0;
+  return p.blob_bytes;
+}
+
+extern "C" size_t popnet_workspace_bytes(const PopnetNetConfig* cfg, int batch) {
+  Plan p;
+  if (!cfg || batch < 1 || !make_plan(*cfg, batch, p)) return 0;
+  return p.ws_bytes;
+}
+
+extern "C" int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvHost* layers, int num_layers,
+                                   void* packed_dev, size_t packed_bytes, void* stream) {
+  Plan p;
+  if (!cfg || !layers || !packed_dev) return POPNET_ERR_INVALID_ARG;
+  if (!make_plan(*cfg, 1, p)) return POPNET_ERR_UNSUPPORTED;
+  if (num_layers != (int)p.layers.size() || packed_bytes < p.blob_bytes) return POPNET_ERR_INVALID_ARG;
+  std::vector<unsigned char> blob(p.blob_bytes, 0);
+  for (size_t li = 0; li < p.layers.size(); ++li) {
+    const Layer& l = p.layers[li];
+    const PopnetConvHost& h = layers[li];
+    if (h.cout != l.cout || h.cin != l.cin || h.ksize != l.k || !h.weight_host || !h.scale_host || !h.shift_host)
+      return POPNET_ERR_INVALID_ARG;
+    float* shift = reinterpret_cast<float*>(blob.data() + l.shift_off);
+    for (int n = 0; n < l.cout; ++n) shift[n] = h.shift_host[n];
+    if (l.k == 7) {                                      // stem: fp32 [tap][cout]
+      float* w = reinterpret_cast<float*>(blob.data() + l.w_off);
+      for (int n = 0; n < 64; ++n)
+        for (int t = 0; t < 49; ++t) w[t * 64 + n] = h.weight_host[(size_t)n * 49 + t] * h.scale_host[n];
+      continue;
+    }
+    __nv_bfloat16* w = reinterpret_cast<__nv_bfloat16*>(blob.data() + l.w_off);
+    const int taps = l.k * l.k, k8 = l.cin_pad / 8, ntiles = l.cout_pad / l.nt;
+    for (int ti = 0; ti < ntiles; ++ti)
+      for (int t = 0; t < taps; ++t)
+        for (int g = 0; g < k8; ++g)
+          for (int nn = 0; nn < l.nt; ++nn)
+            for (int j = 0; j < 8; ++j) {
+              const int n = ti * l.nt + nn, ci = g * 8 + j;
+              const int cref = l.remap_s2 ? s2_to_ref(p, ci) : (ci < l.cin ? ci : -1);
+              float v = 0.f;
+              if (n < l.cout && cref >= 0) v = h.weight_host[((size_t)n * l.cin + cref) * taps + t] * h.scale_host[n];
+              w[((((size_t)ti * taps + t) * k8 + g) * l.nt + nn) * 8 + j] = __float2bfloat16(v);
+            }
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  POPNET_CUDA_TRY(cudaMemcpyAsync(packed_dev, blob.data(), p.blob_bytes, cudaMemcpyHostToDevice, st));
+  POPNET_CUDA_TRY(cudaStreamSynchronize(st));            // `blob` is freed on return
+  return POPNET_OK;
+}
+
+namespace {
+std::atomic<int> g_dbg_swap{0};
+}
+// bring-up switch (not part of the public header): exchange LBO and SBO in the UMMA descriptors
+extern "C" __attribute__((visibility("default"))) void popnet_debug_set_desc_swap(int v) { g_dbg_swap.store(v); }
+
+extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev, const float* x, int batch,
+                              float* paf, float* heat, float* depth, float* s1_paf, float* s1_heat, float* s1_depth,
+                              void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  if (!cfg || !packed_dev || !x || !paf || !heat || !depth || !workspace || batch < 1) return POPNET_ERR_INVALID_ARG;
+  if (impl != POPNET_FWD_IMPL_TCGEN05 && impl != POPNET_FWD_IMPL_SIMT) return POPNET_ERR_INVALID_ARG;
+  Plan p;
+  if (!make_plan(*cfg, batch, p)) return POPNET_ERR_UNSUPPORTED;
+  if (workspace_bytes < p.ws_bytes) return POPNET_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned char* blob = static_cast<const unsigned char*>(packed_dev);
+
+  auto run_conv = [&](int li) -> int {
+    const Layer& l = p.layers[li];
+    const Buf& bi = p.bufs[l.in_buf];
+    ConvArgs a{};
+    a.in = buf_ptr(workspace, bi, l.in_plane0);
+    a.in_plane_stride = bi.plane_stride;
+    a.w = reinterpret_cast<const __nv_bfloat16*>(blob + l.w_off);
+    a.shift = reinterpret_cast<const float*>(blob + l.shift_off);
+    if (l.out_buf >= 0) {
+      a.out = buf_ptr(workspace, p.bufs[l.out_buf], l.out_plane0);
+      a.out_plane_stride = p.bufs[l.out_buf].plane_stride;
+    }
+    if (l.res_buf >= 0) {
+      a.res = buf_ptr(workspace, p.bufs[l.res_buf], 0);
+      a.res_plane_stride = p.bufs[l.res_buf].plane_stride;
+    }
+    if (l.head) {
+      float* s1[4] = {nullptr, s1_paf, s1_heat, s1_depth};
+      float* s2[4] = {nullptr, paf, heat, depth};
+      a.head_out = (l.stage == 1) ? s1[l.head] : s2[l.head];
+    }
+    a.P = bi.P; a.Hp = bi.H + 2; a.Wp = bi.W + 2;
+    a.chunks = l.cin_pad / 64;
+    a.a_stages = a.chunks > 1 ? 2 : 1;
+    a.act = l.act; a.cout = l.cout; a.cout_pad = l.cout_pad; a.nt = l.nt; a.taps = l.k * l.k;
+    a.lbo_sbo_swapped = g_dbg_swap.load();
+    if (impl == POPNET_FWD_IMPL_SIMT) return launch_conv_simt(a, st);
+    // shrink the A staging if the tile does not fit next to two B stages
+    int bst = 0;
+    if (conv_tc_smem_bytes(a.nt, l.nacc, a.taps, a.a_stages, a.Wp, &bst) > 227 * 1024) a.a_stages = 1;
+    return launch_conv_tc(a, l.nacc, st);
+  };
+  auto run_pool = [&](int in_buf, int out_buf, int out_plane0) -> int {
+    const Buf& bi = p.bufs[in_buf];
+    PoolArgs a{};
+    a.in = buf_ptr(workspace, bi, 0); a.in_plane_stride = bi.plane_stride;
+    a.out = buf_ptr(workspace, p.bufs[out_buf], out_plane0); a.out_plane_stride = p.bufs[out_buf].plane_stride;
+    a.planes = bi.C / 8; a.N = batch; a.H = bi.H; a.W = bi.W;
+    return launch_pool(a, st);
+  };
+#define POPNET_TRY(expr) do { int _rc = (expr); if (_rc != POPNET_OK) return _rc; } while (0)
+  {
+    const Layer& l = p.layers[0];
+    StemArgs a{};
+    a.x = x; a.w = reinterpret_cast<const float*>(blob + l.w_off); a.shift = reinterpret_cast<const float*>(blob + l.shift_off);
+    a.out = buf_ptr(workspace, p.bufs[A112], 0); a.out_plane_stride = p.bufs[A112].plane_stride;
+    a.N = batch; a.H = cfg->height; a.W = cfg->width;
+    POPNET_TRY(launch_stem(a, st));
+  }
+  for (int li = 1; li <= 4; ++li) POPNET_TRY(run_conv(li));
+  POPNET_TRY(run_pool(A112, D56, 0));
+  POPNET_TRY(run_conv(5));
+  POPNET_TRY(run_conv(7));
+  POPNET_TRY(run_conv(6));
+  POPNET_TRY(run_conv(8));
+  POPNET_TRY(run_pool(E56, S2IN, (p.pl + p.ph + p.pd) / 8));
+  for (int li = 9; li < (int)p.layers.size(); ++li) POPNET_TRY(run_conv(li));
+#undef POPNET_TRY
+  return POPNET_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bring-up / unit-test hook (not in the public header): run ONE convolution on caller-provided C8P
+// buffers, through either kernel.  tests/test_gpu_conv_unit.py drives every instantiated tile shape.
+// ------------------------------------------------------------------------------------------------
+struct PopnetDebugConv {
+  const void* in; long long in_plane_stride;
+  const void* w; const float* shift;
+  void* out; long long out_plane_stride;
+  const void* res; long long res_plane_stride;
+  float* head_out;
+  int P, Hp, Wp, chunks, a_stages, act, cout, cout_pad, nt, nacc, taps, impl, swap;
+};
+
+extern "C" __attribute__((visibility("default"))) int popnet_debug_conv(const PopnetDebugConv* d, void* stream) {
+  if (!d) return POPNET_ERR_INVALID_ARG;
+  ConvArgs a{};
+  a.in = static_cast<const __nv_bfloat16*>(d->in); a.in_plane_stride = d->in_plane_stride;
+  a.w = static_cast<const __nv_bfloat16*>(d->w); a.shift = d->shift;
+  a.out = static_cast<__nv_bfloat16*>(d->out); a.out_plane_stride = d->out_plane_stride;
+  a.res = static_cast<const __nv_bfloat16*>(d->res); a.res_plane_stride = d->res_plane_stride;
+  a.head_out = d->head_out;
+  a.P = d->P; a.Hp = d->Hp; a.Wp = d->Wp; a.chunks = d->chunks; a.a_stages = d->a_stages; a.act = d->act;
+  a.cout = d->cout; a.cout_pad = d->cout_pad; a.nt = d->nt; a.taps = d->taps; a.lbo_sbo_swapped = d->swap;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return d->impl == POPNET_FWD_IMPL_SIMT ? launch_conv_simt(a, st) : launch_conv_tc(a, d->nacc, st);
+}

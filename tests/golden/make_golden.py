@@ -136,38 +136,31 @@ def make_eval():
 
 
 def make_forward():
+    """Reference module (its own forward, fp32, CPU) on the C1 frame and two synthetic frames, for two
+    seeded checkpoints built by popnet_b200.network.synth_state_dict (no trained weights ship)."""
+    import cv2
     import torch
     from popnet_b200 import network
     ref = refshim.load()
     out = {}
     # C1 input: bundled ITOP frame through the ITOP eval-time recipe
-    # (datasets_itop_rtpose.py:213-223, data_augmentation_2d3d.py:510)
-    import cv2
+    # (datasets_itop_rtpose.py:213-223: resize 224 bilinear, clamp [0, 5], (x-3)/2)
     raw = np.load(os.path.join(refshim.REFERENCE_ROOT, "third_party_methods", "00_02254.npy")).astype(np.float32)
     img = cv2.resize(raw, (224, 224), interpolation=cv2.INTER_LINEAR)
     img = np.clip(img, 0, 5.0)
-    x1 = ((img - 3.0) / 2.0).astype(np.float32)[None, None]
-    out["c1/x"] = x1
-    frames = synth.depth_frames(3, seed=4321)
-    out["syn/x"] = frames
+    x = np.concatenate([((img - 3.0) / 2.0).astype(np.float32)[None, None], synth.depth_frames(2, seed=4321)], 0)
+    out["x"] = x.astype(np.float16)          # stored as fp16; the test feeds exactly these (rounded) frames
+    x = out["x"].astype(np.float32)
     torch.set_num_threads(8)
     for style in ("reference", "trained_like"):
-        torch.manual_seed(0)
+        sd = network.synth_state_dict(seed=11, style=style)
+        out[style + "/state_sha"] = np.array(sha(*[sd[k] for k in sorted(sd)]))
         model = ref.rtpose_light3d(15, 14, 2, input_dim=1).float().eval()
-        if style == "trained_like":
-            sd = network.synth_state_dict(seed=11, style="trained_like")
-            model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
-        else:
-            sd = {k: v.detach().numpy() for k, v in model.state_dict().items()}
-        for tag, x in (("c1", x1), ("syn", frames)):
-            with torch.no_grad():
-                (paf, heat, depth), saved = model(torch.from_numpy(x))
-            key = "%s/%s/" % (style, tag)
-            out[key + "paf"], out[key + "heat"], out[key + "depth"] = paf.numpy(), heat.numpy(), depth.numpy()
-            out[key + "paf1"], out[key + "heat1"], out[key + "depth1"] = (s.numpy() for s in saved[:3])
-        if style == "reference":
-            # the seed-0 reference-init weights themselves (bf16-rounded would not be the reference): keep fp16-compressible fp32
-            np.savez_compressed(os.path.join(HERE, "forward_weights_reference_seed0.npz"), **sd)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        with torch.no_grad():
+            (paf, heat, depth), saved = model(torch.from_numpy(x))
+        out[style + "/paf"], out[style + "/heat"], out[style + "/depth"] = paf.numpy(), heat.numpy(), depth.numpy()
+        out[style + "/paf1"], out[style + "/heat1"], out[style + "/depth1"] = (t.numpy() for t in saved[:3])
         print("forward style", style)
     np.savez_compressed(os.path.join(HERE, "forward_golden.npz"), **out)
 

@@ -1,0 +1,95 @@
+"""Forward parity.
+
+CPU part: the fp32 torch oracle (oracle/forward_torch.py) against the reference module's own outputs
+(golden fixture), and the state-dict contract of the host mirror.
+GPU part: the CUDA forward (tcgen05 path and the CUDA-core check path, both through popnet_forward)
+against the oracle; tolerance max-abs <= 1e-2 on the three output maps (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from helpers import golden
+from popnet_b200 import network
+
+TOL = 1e-2
+
+
+def _state(style):
+    sd = network.synth_state_dict(seed=11, style=style)
+    g = golden("forward_golden")
+    assert helpers.sha(*[sd[k] for k in sorted(sd)]) == str(g[style + "/state_sha"]), "synthetic checkpoint drifted"
+    return sd
+
+
+@pytest.mark.parametrize("style", ["reference", "trained_like"])
+def test_torch_oracle_matches_reference_module(style):
+    from oracle import forward_torch
+    g = golden("forward_golden")
+    x = g["x"].astype(np.float32)
+    (paf, heat, depth), saved = forward_torch.forward(_state(style), x)
+    for name, t in (("paf", paf), ("heat", heat), ("depth", depth), ("paf1", saved[0]), ("heat1", saved[1]), ("depth1", saved[2])):
+        err = np.abs(t.numpy() - g["%s/%s" % (style, name)]).max()
+        assert err < 2e-5, (name, err)      # same fp32 ops; thread-count dependent summation order only
+
+
+def test_state_dict_contract():
+    """234 reference keys, DataParallel prefix accepted, canonical conv order has 39 layers."""
+    m = network.rtpose_light3d(15, 14, 2, input_dim=1)
+    sd = m.state_dict()
+    assert len(sd) == 234
+    assert "model0.layer2.0.downsample.1.running_var" in sd and "model2_3.12.bias" in sd and "model1_1.1.num_batches_tracked" in sd
+    m.load_state_dict({"module." + k: v for k, v in sd.items()})
+    assert len(m.conv_layers()) == 39
+    assert sum(p.numel() for p in m.parameters()) == 5525814
+    with pytest.raises(ValueError):
+        network.rtpose_light3d(15, 14, 3, input_dim=1)
+
+
+def test_forward_requires_cuda_tensor():
+    from popnet_b200._lib import PopnetError
+    m = network.rtpose_light3d(15, 14, 2, input_dim=1)
+    with pytest.raises(PopnetError):
+        m(torch.zeros(1, 1, 224, 224))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("style", ["reference", "trained_like"])
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+def test_cuda_forward_vs_oracle(style, impl, cuda_backend):
+    from oracle import forward_torch
+    from popnet_b200 import _abi
+    g = golden("forward_golden")
+    x = g["x"].astype(np.float32)
+    sd = _state(style)
+    m = network.rtpose_light3d(15, 14, 2, input_dim=1)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m.impl = _abi.FWD_IMPL_SIMT if impl == "simt" else _abi.FWD_IMPL_TCGEN05
+    (paf, heat, depth), saved = m(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    (opaf, oheat, odepth), osaved = forward_torch.forward(sd, x)
+    errs = {}
+    for name, a, b in (("paf", paf, opaf), ("heat", heat, oheat), ("depth", depth, odepth),
+                       ("paf1", saved[0], osaved[0]), ("heat1", saved[1], osaved[1]), ("depth1", saved[2], osaved[2])):
+        errs[name] = float((a.cpu() - b).abs().max())
+        # and against the reference module's own numbers
+        errs[name + "_vs_ref"] = float(np.abs(a.cpu().numpy() - g["%s/%s" % (style, name)]).max())
+    print("max-abs errors (%s, %s):" % (style, impl), errs)
+    assert all(np.isfinite(v) and v <= TOL for v in errs.values()), errs
+
+
+@pytest.mark.gpu
+def test_cuda_forward_batch_invariance(cuda_backend):
+    """Frames are independent: a frame's maps do not depend on its position in the batch or on batch size."""
+    from popnet_b200 import synth
+    sd = network.synth_state_dict(seed=11, style="trained_like")
+    m = network.rtpose_light3d(15, 14, 2, input_dim=1)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    x = torch.from_numpy(synth.depth_frames(9, seed=99)).cuda()
+    (p9, h9, d9), _ = m(x)
+    (p1, h1, d1), _ = m(x[4:5])
+    (p3, h3, d3), _ = m(x[3:6])
+    torch.cuda.synchronize()
+    assert torch.equal(p9[4:5], p1) and torch.equal(h9[4:5], h1) and torch.equal(d9[4:5], d1)
+    assert torch.equal(p9[3:6], p3) and torch.equal(h9[3:6], h3) and torch.equal(d9[3:6], d3)

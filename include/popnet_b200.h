@@ -184,7 +184,13 @@ typedef struct PopnetNetConfig {
   int32_t num_limbs;           /* 14                                                               */
   int32_t input_dim;           /* 1 (depth); the only compiled value                               */
   int32_t height, width;       /* 224 x 224; must be multiples of 8                                */
+  int32_t operand_dtype;       /* POPNET_OPERAND_BF16 (default) or POPNET_OPERAND_FP16: storage format of
+                                  weights and inter-layer activations; accumulation is always fp32 and
+                                  the six output maps are always fp32                                 */
 } PopnetNetConfig;
+
+#define POPNET_OPERAND_BF16 0
+#define POPNET_OPERAND_FP16 1
 
 /* number of conv layers (39) and, per layer l, the element counts the packer expects */
 POPNET_API int popnet_num_conv_layers(const PopnetNetConfig* cfg);

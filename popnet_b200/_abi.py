@@ -17,6 +17,8 @@ FLAG_PEAK_OVERFLOW = 1
 FLAG_PERSON_OVERFLOW = 2
 FWD_IMPL_TCGEN05 = 0
 FWD_IMPL_SIMT = 1
+OPERAND_BF16 = 0
+OPERAND_FP16 = 1
 
 vp = C.c_void_p
 
@@ -63,7 +65,7 @@ class MapArgs(C.Structure):
 
 class NetConfig(C.Structure):
     _fields_ = [("num_parts", C.c_int32), ("num_limbs", C.c_int32), ("input_dim", C.c_int32),
-                ("height", C.c_int32), ("width", C.c_int32)]
+                ("height", C.c_int32), ("width", C.c_int32), ("operand_dtype", C.c_int32)]
 
 
 class ConvHost(C.Structure):

@@ -4,7 +4,7 @@
 // stored as C/8 planes; plane g holds, for every position of the zero-padded images, the 8 channels
 // 8g .. 8g+7 as one 16-byte vector:
 //
-//     plane[g][ guard | N * (H+2) * (W+2) positions, rounded up to 512 | guard ][8]   bf16
+//     plane[g][ guard | N * (H+2) * (W+2) positions, rounded up to 512 | guard ][8]   bf16 / fp16
 //
 // Positions are linear over (n, h_pad, w_pad).  The one-pixel ring around every image is ZERO (every
 // producer writes it), which makes a 3x3 tap a pure shift by dh*(W+2)+dw positions: the A operand of
@@ -14,6 +14,8 @@
 // MMA are independent, so whatever they hold only reaches ring / slack outputs.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
 
 #include "common.cuh"
 
@@ -22,16 +24,28 @@ namespace popnet {
 constexpr int kGuard = 128;        // positions in front of / behind every plane (>= W + 3)
 constexpr int kPosRound = 512;     // planes hold a multiple of the largest CTA tile
 
+// 16-bit operand storage: bf16 (fmt 0, the north-star default) or fp16 (fmt 1).  Both run at the same
+// tensor-core rate and byte count; fp16 carries 3 more mantissa bits ("operand format").
+typedef uint16_t h16;
+__host__ __device__ inline h16 f2h16(float x, int fmt) {
+  if (fmt == 0) return __bfloat16_as_ushort(__float2bfloat16(x));
+  return __half_as_ushort(__float2half(x));
+}
+__host__ __device__ inline float h162f(h16 v, int fmt) {
+  if (fmt == 0) return __bfloat162float(__ushort_as_bfloat16(v));
+  return __half2float(__ushort_as_half(v));
+}
+
 enum Act : int { kActNone = 0, kActRelu = 1, kActLeaky = 2, kActHeadPaf = 3, kActHeadHeat = 4 };
 
 struct ConvArgs {
-  const __nv_bfloat16* in;      // position 0 of the first input plane
-  long long in_plane_stride;    // bf16 elements between planes
-  const __nv_bfloat16* w;       // packed [n_tile][tap][cin_pad/8][NT][8], BN scale folded in
+  const h16* in;                // position 0 of the first input plane
+  long long in_plane_stride;    // 16-bit elements between planes
+  const h16* w;                 // packed [n_tile][tap][cin_pad/8][NT][8], BN scale folded in
   const float* shift;           // [cout_pad] folded BN shift + conv bias
-  __nv_bfloat16* out;           // position 0 of the first output plane, or nullptr
+  h16* out;                     // position 0 of the first output plane, or nullptr
   long long out_plane_stride;
-  const __nv_bfloat16* res;     // residual (same geometry as out) or nullptr
+  const h16* res;               // residual (same geometry as out) or nullptr
   long long res_plane_stride;
   float* head_out;              // fp32 [N][cout][H][W] or nullptr
   int P;                        // N * Hp * Wp
@@ -43,25 +57,29 @@ struct ConvArgs {
   int cout_pad;
   int nt;                       // N tile (template argument of the launched kernel)
   int taps;                     // 1 or 9
-  int lbo_sbo_swapped;          // bring-up switch: exchange LBO / SBO in the UMMA descriptors
+  int fmt;                      // 0 = bf16, 1 = fp16 operands
+  long long* probe;             // optional [gridDim.x][16] clock64 stamps (bring-up / tuning), else nullptr
+  int dbg;                      // bring-up switches: 1 = skip MMA issue, 2 = skip epilogue stores
 };
 
 struct StemArgs {
   const float* x;               // [N][H][W] fp32
-  const float* w;               // [49][64] fp32, scale folded
+  const h16* w;                 // [8 k8][64 cout][8]: K = ky*7+kx (49 taps, zero padded to 64), scale folded
   const float* shift;           // [64]
-  __nv_bfloat16* out;           // C8P, 64 channels at (H/2, W/2)
+  h16* out;                     // C8P, 64 channels at (H/2, W/2)
   long long out_plane_stride;
   int N, H, W;                  // input size
+  int fmt;
 };
 
 struct PoolArgs {
-  const __nv_bfloat16* in;
+  const h16* in;
   long long in_plane_stride;
-  __nv_bfloat16* out;
+  h16* out;
   long long out_plane_stride;
   int planes;
   int N, H, W;                  // input spatial size (output is H/2 x W/2)
+  int fmt;
 };
 
 int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st);

@@ -10,7 +10,8 @@
 //                    layout (conv.cuh), so a 3x3 tap is a descriptor start-address shift and every input
 //                    tile is fetched once per 64 input channels instead of once per tap.
 //                    Warp roles: 0 = copy producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue
-//                    (tcgen05.ld -> +shift, residual, activation -> bf16 C8P store and/or fp32 NCHW head).
+//                    (tcgen05.ld -> +shift, residual, activation -> 16-bit C8P store and/or fp32 NCHW head).
+//                    Operands are bf16 (default) or fp16 -- a runtime field of the instruction descriptor.
 //   conv_simt_kernel a plain CUDA-core evaluation of the same packed operands, used by tests / bring-up
 //                    to localise tensor-core descriptor mistakes (POPNET_FWD_IMPL_SIMT); not a product path.
 //   stem_kernel      model0.conv1 (7x7, stride 2, C_in = 1): direct fp32 evaluation, 0.6 % of the FLOPs.
@@ -94,7 +95,31 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// two fp32 -> one packed pair of 16-bit operands (single cvt.rn instruction per pair)
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, int fmt) {
+  if (fmt == 0) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+  }
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
+  if (fmt == 0) return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
 
 // UMMA shared-memory descriptor, SWIZZLE_NONE, K-major: 8 rows x 16 B core matrices, rows 16 B apart inside
 // a core matrix; SBO = byte distance between 8-row groups (M/N direction), LBO = byte distance between the
@@ -103,9 +128,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-// instruction descriptor for kind::f16: D = F32, A = B = BF16, both K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t umma_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor for kind::f16: D = F32, A = B = BF16 (fmt 0) or F16 (fmt 1), both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t umma_idesc(int n, int fmt) {
+  return (1u << 4) | ((fmt == 0 ? 1u : 0u) << 7) | ((fmt == 0 ? 1u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -132,16 +158,16 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // v: raw accumulators of channels ch0 .. ch0+7 at `pos`
 __device__ __forceinline__ void finish8(const ConvArgs& a, int pos, const PosInfo& pi, int ch0, const float (&v)[8]) {
   if (!pi.in_range) return;
-  __align__(16) __nv_bfloat16 ob[8];
+  __align__(16) h16 ob[8];
   if (pi.interior) {
     float r[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) r[i] = 0.f;
     if (a.res) {
       const uint4 q = *reinterpret_cast<const uint4*>(a.res + (long long)(ch0 >> 3) * a.res_plane_stride + (long long)pos * 8);
-      const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(&q);
+      const h16* rb = reinterpret_cast<const h16*>(&q);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] = __bfloat162float(rb[i]);
+      for (int i = 0; i < 8; ++i) r[i] = h162f(rb[i], a.fmt);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -158,24 +184,55 @@ __device__ __forceinline__ void finish8(const ConvArgs& a, int pos, const PosInf
         a.head_out[(((long long)pi.n * a.cout + ch0 + i) * H + pi.h) * W + pi.w] = x;
       }
       if (ch0 + i >= a.cout) x = 0.f;                                  // padded channels stay zero
-      ob[i] = __float2bfloat16(x);
+      ob[i] = f2h16(x, a.fmt);
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ob[i] = __float2bfloat16(0.f);
+    for (int i = 0; i < 8; ++i) ob[i] = 0;
   }
   if (a.out)
     *reinterpret_cast<uint4*>(a.out + (long long)(ch0 >> 3) * a.out_plane_stride + (long long)pos * 8) =
         *reinterpret_cast<const uint4*>(ob);
 }
 
+// hot-path epilogue of the hidden layers: 8 channels (one C8P vector) of one interior position.
+// activation as a slope: ReLU = 0, LeakyReLU = 0.1, none = 1
+__device__ __forceinline__ uint4 finish8_fast(const uint32_t* acc, const float* s_shift8, bool has_res, uint4 res,
+                                              float slope, bool interior, int fmt) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[i]) + s_shift8[i];
+  if (has_res) {
+    const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack2(rw[i], fmt);
+      x[2 * i] += f.x;
+      x[2 * i + 1] += f.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float y = fmaxf(x[i], 0.f) + slope * fminf(x[i], 0.f);     // ReLU / LeakyReLU / identity by slope
+    x[i] = interior ? y : 0.f;
+  }
+  uint4 o;
+  o.x = pack2(x[0], x[1], fmt); o.y = pack2(x[2], x[3], fmt); o.z = pack2(x[4], x[5], fmt); o.w = pack2(x[6], x[7], fmt);
+  return o;
+}
+
 // ------------------------------------------------------------------------------------------------
 // tensor-core implicit GEMM
 // ------------------------------------------------------------------------------------------------
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 384;       // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarp0 = 4;
+
+// two CTAs per SM (register cap 85) for the tile shapes whose shared memory allows it
+template <int NT, int NACC>
+constexpr int min_ctas() { return (NACC == 2 && NT <= 128) ? 2 : 1; }
 
 template <int NT, int NACC, int TAPS, int BST>
-__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a) {
+__global__ void __launch_bounds__(kTcThreads, min_ctas<NT, NACC>()) conv_tc_kernel(const ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int MT = NACC * 128;
   constexpr uint32_t kBStageBytes = 8u * NT * 16u;          // 64 input channels x NT output channels
@@ -192,6 +249,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)BST * kBStageBytes);
   // bars: [0,2) a_full, [2,4) a_empty, [4,4+BST) b_full, [4+BST,4+2BST) b_empty, [4+2BST] acc_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * BST + 1);
+  float* s_shift = reinterpret_cast<float*>(bars + 4 + 2 * BST + 2);      // [NT]
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8u * s; };
   auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -202,6 +260,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * MT;
   const int ntile = blockIdx.y;
+  long long* probe = (a.probe && blockIdx.y == 0) ? a.probe + (long long)blockIdx.x * 16 : nullptr;
+  if (probe && threadIdx.x == 0) probe[0] = clock64();
   const int chunks = a.chunks;
   const int k8_total = chunks * 8;
 
@@ -209,6 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
     for (int i = 0; i < 4 + 2 * BST + 1; ++i) mbar_init(bar0 + 8u * i, 1);
     fence_mbar_init();
   }
+  for (int i = threadIdx.x; i < NT; i += kTcThreads) s_shift[i] = a.shift[ntile * NT + i];
   if (warp == 2) {
     tmem_alloc(smem_u32(tmem_slot), kCols);
     tmem_relinquish();
@@ -217,11 +278,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (probe && threadIdx.x == 0) probe[1] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- producer ----------------
-      const __nv_bfloat16* wbase = a.w + (long long)ntile * TAPS * k8_total * NT * 8;
+      const h16* wbase = a.w + (long long)ntile * TAPS * k8_total * NT * 8;
       for (int c = 0; c < chunks; ++c) {
         const int as = c % ast;
         if (c >= ast) mbar_wait(a_empty(as), ((c / ast) - 1) & 1);
@@ -238,21 +300,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
                    kBStageBytes, b_full(bs));
         }
       }
+      if (probe) probe[2] = clock64();
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = umma_idesc(NT);
+      const uint32_t idesc = umma_idesc(NT, a.fmt);
       const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
-      const uint32_t a_lbo = a.lbo_sbo_swapped ? 128u : a_plane_bytes, a_sbo = a.lbo_sbo_swapped ? a_plane_bytes : 128u;
-      const uint32_t b_lbo = a.lbo_sbo_swapped ? 128u : (uint32_t)NT * 16u, b_sbo = a.lbo_sbo_swapped ? (uint32_t)NT * 16u : 128u;
+      const uint32_t a_lbo = a_plane_bytes, a_sbo = 128u;      // K-direction / 8-row-group strides
+      const uint32_t b_lbo = (uint32_t)NT * 16u, b_sbo = 128u;
+      long long wait_a = 0, wait_b = 0;
       for (int c = 0; c < chunks; ++c) {
         const int as = c % ast;
+        long long tw = probe ? clock64() : 0;
         mbar_wait(a_full(as), (c / ast) & 1);
+        if (probe) wait_a += clock64() - tw;
         tc_fence_after();
         for (int t = 0; t < TAPS; ++t) {
           const int it = c * TAPS + t, bs = it % BST;
+          tw = probe ? clock64() : 0;
           mbar_wait(b_full(bs), (it / BST) & 1);
+          if (probe) wait_b += clock64() - tw;
           tc_fence_after();
           const int shift = (TAPS == 9) ? ((t / 3 - 1) * a.Wp + (t % 3 - 1) + halo) : 0;
 #pragma unroll
@@ -262,7 +330,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
               const uint64_t da = umma_desc(sA0 + as * a_stage_bytes + (2 * kk) * a_plane_bytes + (uint32_t)(shift + acc * 128) * 16u,
                                             a_lbo, a_sbo);
               const uint64_t db = umma_desc(sB0 + bs * kBStageBytes + (2 * kk) * NT * 16u, b_lbo, b_sbo);
-              umma_bf16(tmem_base + acc * NT, da, db, idesc, (c | t | kk) != 0 ? 1u : 0u);
+              if (!(a.dbg & 1)) umma_bf16(tmem_base + acc * NT, da, db, idesc, (c | t | kk) != 0 ? 1u : 0u);
             }
           }
           umma_commit(b_empty(bs));       // B stage reusable once these MMAs retire
@@ -270,33 +338,72 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
         umma_commit(a_empty(as));
       }
       umma_commit(acc_full);
+      if (probe) { probe[3] = wait_a; probe[4] = wait_b; probe[5] = clock64(); }
     }
-  } else if (warp >= 4) {
-    // ---------------- epilogue: TMEM lane quarter q, thread = one output position ----------------
+  } else if (warp >= kEpiWarp0) {
+    // ---------------- epilogue: TMEM lane quarter q, thread = one output position; the two warps of a
+    // quarter split the column chunks between them (a lone warp per scheduler is issue-latency bound) ----
     const int q = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (probe && threadIdx.x == kEpiWarp0 * 32) probe[6] = clock64();
+    const bool head = a.act == kActHeadPaf || a.act == kActHeadHeat;
+    const float slope = a.act == kActRelu ? 0.f : (a.act == kActLeaky ? 0.1f : 1.f);
 #pragma unroll 1
     for (int acc = 0; acc < NACC; ++acc) {
       const int pos = t0 + acc * 128 + q * 32 + lane;
       const PosInfo pi = locate(pos, a);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
+      if (head) {
+        // output heads (NT = 16 / 32): fp32 NCHW maps with the sigmoid scaling, optional 16-bit copy
 #pragma unroll 1
-      for (int j = 0; j < NT / 16; ++j) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + j * 16), r);
-        tmem_ld_wait();
-        float v[8];
+        for (int j = half; j < NT / 16; j += 2) {
+          uint32_t r[16];
+          tmem_ld16(trow + (uint32_t)(j * 16), r);
+          tmem_ld_wait();
+          float v[8];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < 2; ++h) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h * 8 + i]);
-          finish8(a, pos, pi, ntile * NT + j * 16 + h * 8, v);
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h * 8 + i]);
+            if (!(a.dbg & 2)) finish8(a, pos, pi, ntile * NT + j * 16 + h * 8, v);
+          }
+        }
+      } else if constexpr (NT >= 32) {
+#pragma unroll 1
+        for (int j = half; j < NT / 32; j += 2) {
+          uint32_t r[32];
+          if (!(a.dbg & 8)) tmem_ld32(trow + (uint32_t)(j * 32), r);
+          else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = 0x3f800000u + i + lane;
+          }
+          const int plane = (ntile * NT + j * 32) >> 3;
+          uint4 rs[4];
+          const bool has_res = a.res != nullptr && pi.interior;
+          if (has_res) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              rs[g] = *reinterpret_cast<const uint4*>(a.res + (long long)(plane + g) * a.res_plane_stride + (long long)pos * 8);
+          }
+          if (!(a.dbg & 8)) tmem_ld_wait();
+          if (pi.in_range && !(a.dbg & 2)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 o = finish8_fast(r + g * 8, s_shift + j * 32 + g * 8, has_res, rs[g], slope, pi.interior, a.fmt);
+              if (!(a.dbg & 4) || o.x == 0x12345678u)
+                *reinterpret_cast<uint4*>(a.out + (long long)(plane + g) * a.out_plane_stride + (long long)pos * 8) = o;
+            }
+          }
         }
       }
     }
+    if (probe && threadIdx.x == kEpiWarp0 * 32) probe[7] = clock64();
     tc_fence_before();
   }
   __syncthreads();
+  if (probe && threadIdx.x == 0) probe[8] = clock64();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kCols);
@@ -318,14 +425,14 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvArgs a) {
       const int shift = (a.taps == 9) ? ((t / 3 - 1) * a.Wp + (t % 3 - 1)) : 0;
       for (int g = 0; g < k8_total; ++g) {
         const uint4 xa = *reinterpret_cast<const uint4*>(a.in + (long long)g * a.in_plane_stride + (long long)(pos + shift) * 8);
-        const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(&xa);
-        const __nv_bfloat16* wrow = a.w + ((((long long)nti * a.taps + t) * k8_total + g) * a.nt + nn) * 8;
+        const h16* xb = reinterpret_cast<const h16*>(&xa);
+        const h16* wrow = a.w + ((((long long)nti * a.taps + t) * k8_total + g) * a.nt + nn) * 8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint4 wa = *reinterpret_cast<const uint4*>(wrow + i * 8);
-          const __nv_bfloat16* wb = reinterpret_cast<const __nv_bfloat16*>(&wa);
+          const h16* wb = reinterpret_cast<const h16*>(&wa);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i] = fmaf(__bfloat162float(xb[j]), __bfloat162float(wb[j]), acc[i]);
+          for (int j = 0; j < 8; ++j) acc[i] = fmaf(h162f(xb[j], a.fmt), h162f(wb[j], a.fmt), acc[i]);
         }
       }
     }
@@ -334,47 +441,106 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem: 7x7 stride 2 pad 3, one input channel, + folded BN + ReLU -> C8P bf16 (64 channels)
+// stem: model0.conv1 (7x7, stride 2, pad 3, one input channel) + folded BN + ReLU -> C8P (64 channels).
+// Also on the tensor cores: each CTA im2col's 128 output positions into the K-major core-matrix layout
+// (K = 49 taps padded to 64), issues four M128 x N64 x K16 MMAs against the resident weights and runs the
+// same TMEM epilogue; the input image is read through L1 (every pixel feeds ~12 taps).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) stem_kernel(const StemArgs a) {
-  __shared__ float s_w[49 * 64];
+constexpr int kStemThreads = 128;
+
+__global__ void __launch_bounds__(kStemThreads) stem_kernel(const StemArgs a) {
+  __shared__ __align__(128) h16 sA[8 * 128 * 8];          // [k8][row][8]
+  __shared__ __align__(128) h16 sB[8 * 64 * 8];           // [k8][cout][8]
   __shared__ float s_shift[64];
-  for (int i = threadIdx.x; i < 49 * 64; i += 128) s_w[i] = a.w[i];
-  if (threadIdx.x < 64) s_shift[threadIdx.x] = a.shift[threadIdx.x];
-  __syncthreads();
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Ho = a.H / 2, Wo = a.W / 2, Hp = Ho + 2, Wp = Wo + 2;
   const int P = a.N * Hp * Wp;
-  const int pos = blockIdx.x * 128 + threadIdx.x;
-  if (pos >= P) return;
-  const int g = blockIdx.y;                         // output plane (8 channels)
-  const int n = pos / (Hp * Wp), rem = pos - n * Hp * Wp;
-  const int hp = rem / Wp, wp = rem - hp * Wp;
-  __align__(16) __nv_bfloat16 ob[8];
-  if (hp >= 1 && hp <= Ho && wp >= 1 && wp <= Wo) {
-    const int oy = hp - 1, ox = wp - 1;
-    float acc[8];
+  const int tiles = (P + 127) / 128;
+  for (int i = tid; i < 8 * 64; i += kStemThreads)
+    reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(a.w)[i];
+  if (tid < 64) s_shift[tid] = a.shift[tid];
+  const uint32_t bar = smem_u32(&s_bar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&s_tmem), 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  const uint32_t idesc = umma_idesc(64, a.fmt);
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int pos = tile * 128 + tid;
+    const int n = pos / (Hp * Wp), rem = pos - n * Hp * Wp;
+    const int hp = rem / Wp, wp = rem - hp * Wp;
+    const bool interior = pos < P && hp >= 1 && hp <= Ho && wp >= 1 && wp <= Wo;
+    // ---- im2col: this thread's 49 taps -> 8 vectors of 8 K-values
+    {
+      const float* img = a.x + (long long)n * a.H * a.W;
+      const int iy0 = (hp - 1) * 2 - 3, ix0 = (wp - 1) * 2 - 3;
+      uint32_t pk[32];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    const float* img = a.x + (long long)n * a.H * a.W;
-    for (int ky = 0; ky < 7; ++ky) {
-      const int iy = oy * 2 - 3 + ky;
-      if (iy < 0 || iy >= a.H) continue;
-      for (int kx = 0; kx < 7; ++kx) {
-        const int ix = ox * 2 - 3 + kx;
-        if (ix < 0 || ix >= a.W) continue;
-        const float xv = __ldg(img + iy * a.W + ix);
-        const float* wr = s_w + (ky * 7 + kx) * 64 + g * 8;
+      for (int k2 = 0; k2 < 32; ++k2) {
+        float v[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, wr[i], acc[i]);
+        for (int e = 0; e < 2; ++e) {
+          const int k = 2 * k2 + e;
+          float x = 0.f;
+          if (k < 49 && interior) {
+            const int iy = iy0 + k / 7, ix = ix0 + k % 7;
+            if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) x = __ldg(img + iy * a.W + ix);
+          }
+          v[e] = x;
+        }
+        pk[k2] = pack2(v[0], v[1], a.fmt);
+      }
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        reinterpret_cast<uint4*>(sA)[g * 128 + tid] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+    }
+    // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_bf16(tmem_base, umma_desc(a0 + (2 * kk) * 128 * 16, 128 * 16, 128), umma_desc(b0 + (2 * kk) * 64 * 16, 64 * 16, 128),
+                  idesc, kk != 0 ? 1u : 0u);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: thread = position (TMEM lane), 64 channels
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), r);
+      tmem_ld_wait();
+      if (pos < P) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 o = finish8_fast(r + g * 8, s_shift + j * 32 + g * 8, false, make_uint4(0, 0, 0, 0), 0.f, interior, a.fmt);
+          *reinterpret_cast<uint4*>(a.out + (long long)(j * 4 + g) * a.out_plane_stride + (long long)pos * 8) = o;
+        }
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ob[i] = __float2bfloat16(fmaxf(acc[i] + s_shift[g * 8 + i], 0.f));
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ob[i] = __float2bfloat16(0.f);
+    tc_fence_before();
+    __syncthreads();          // TMEM and sA are reused by the next tile
+    tc_fence_after();
   }
-  *reinterpret_cast<uint4*>(a.out + (long long)g * a.out_plane_stride + (long long)pos * 8) = *reinterpret_cast<const uint4*>(ob);
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -388,28 +554,28 @@ __global__ void __launch_bounds__(128) pool_kernel(const PoolArgs a) {
   const int g = blockIdx.y;
   const int n = pos / (Hpo * Wpo), rem = pos - n * Hpo * Wpo;
   const int hp = rem / Wpo, wp = rem - hp * Wpo;
-  __align__(16) __nv_bfloat16 ob[8];
+  __align__(16) h16 ob[8];
   if (hp >= 1 && hp <= Ho && wp >= 1 && wp <= Wo) {
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     // output (oy, ox) covers input rows 2oy-1 .. 2oy+1 -> padded rows 2oy .. 2oy+2
-    const __nv_bfloat16* src = a.in + (long long)g * a.in_plane_stride + ((long long)n * Hpi * Wpi) * 8;
+    const h16* src = a.in + (long long)g * a.in_plane_stride + ((long long)n * Hpi * Wpi) * 8;
     const int py = 2 * (hp - 1), px = 2 * (wp - 1);
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
         const uint4 q = *reinterpret_cast<const uint4*>(src + ((long long)(py + dy) * Wpi + px + dx) * 8);
-        const __nv_bfloat16* qb = reinterpret_cast<const __nv_bfloat16*>(&q);
+        const h16* qb = reinterpret_cast<const h16*>(&q);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += __bfloat162float(qb[i]);
+        for (int i = 0; i < 8; ++i) acc[i] += h162f(qb[i], a.fmt);
       }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ob[i] = __float2bfloat16(acc[i] * (1.f / 9.f));
+    for (int i = 0; i < 8; ++i) ob[i] = f2h16(acc[i] * (1.f / 9.f), a.fmt);
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ob[i] = __float2bfloat16(0.f);
+    for (int i = 0; i < 8; ++i) ob[i] = 0;
   }
   *reinterpret_cast<uint4*>(a.out + (long long)g * a.out_plane_stride + (long long)pos * 8) = *reinterpret_cast<const uint4*>(ob);
 }
@@ -443,9 +609,9 @@ size_t conv_tc_smem_bytes(int nt, int nacc, int taps, int a_stages, int Wp, int*
   const size_t a_bytes = (((size_t)a_stages * 8 * (nacc * 128 + 2 * halo) * 16) + 127) & ~(size_t)127;
   const size_t b_stage = (size_t)8 * nt * 16;
   int bst = 4;
-  while (bst > 2 && a_bytes + bst * b_stage + 256 > kSmemLimit) --bst;
+  while (bst > 2 && a_bytes + bst * b_stage + 256 + (size_t)nt * 4 > kSmemLimit) --bst;
   if (b_stages_out) *b_stages_out = bst;
-  return a_bytes + bst * b_stage + 256;
+  return a_bytes + bst * b_stage + 256 + (size_t)nt * 4;
 }
 
 int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st) {
@@ -475,8 +641,9 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
 
 int launch_stem(const StemArgs& a, cudaStream_t st) {
   const int P = a.N * (a.H / 2 + 2) * (a.W / 2 + 2);
-  dim3 grid((P + 127) / 128, 8);
-  stem_kernel<<<grid, 128, 0, st>>>(a);
+  const int tiles = (P + 127) / 128;
+  const int grid = tiles < 148 * 6 ? tiles : 148 * 6;      // persistent: six CTAs per SM walk the tiles
+  stem_kernel<<<grid, kStemThreads, 0, st>>>(a);
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }

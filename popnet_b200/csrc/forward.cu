@@ -52,6 +52,7 @@ struct Plan {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
+  if (cfg.operand_dtype != 0 && cfg.operand_dtype != 1) return false;
   if (cfg.input_dim != 1 || cfg.height % 8 || cfg.width % 8 || cfg.height < 16 || cfg.width < 16) return false;
   if (cfg.num_parts < 1 || cfg.num_parts > 15 || cfg.num_limbs < 1 || cfg.num_limbs > 15) return false;
   if (cfg.width / 2 + 3 > kGuard) return false;
@@ -74,7 +75,7 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
     off += (size_t)(b.C / 8) * b.plane_stride;
     off = align_up(off, 128);
   }
-  p.ws_bytes = off * sizeof(__nv_bfloat16);
+  p.ws_bytes = off * sizeof(h16);
 
   auto add = [&](int cin, int cout, int k, int nt, int nacc, int act, int in_buf, int in_plane0, int out_buf,
                  int out_plane0, int res_buf, int head, int stage, int remap) {
@@ -124,8 +125,8 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   }
   size_t boff = 0;
   for (Layer& l : p.layers) {
-    const size_t wbytes = (l.k == 7) ? (size_t)49 * 64 * sizeof(float)
-                                     : (size_t)l.k * l.k * l.cin_pad * l.cout_pad * sizeof(__nv_bfloat16);
+    const size_t wbytes = (l.k == 7) ? (size_t)64 * 64 * sizeof(h16)
+                                     : (size_t)l.k * l.k * l.cin_pad * l.cout_pad * sizeof(h16);
     l.w_off = boff; boff = align_up(boff + wbytes, 256);
     l.shift_off = boff; boff = align_up(boff + (size_t)l.cout_pad * sizeof(float), 256);
   }
@@ -145,8 +146,8 @@ int s2_to_ref(const Plan& p, int c) {
   return L2 + K1 + L1 + c;
 }
 
-__nv_bfloat16* buf_ptr(void* ws, const Buf& b, int plane0) {
-  return static_cast<__nv_bfloat16*>(ws) + b.off + (size_t)plane0 * b.plane_stride + (size_t)kGuard * 8;
+h16* buf_ptr(void* ws, const Buf& b, int plane0) {
+  return static_cast<h16*>(ws) + b.off + (size_t)plane0 * b.plane_stride + (size_t)kGuard * 8;
 }
 
 }  // namespace
@@ -186,13 +187,15 @@ extern "C" int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvH
       return POPNET_ERR_INVALID_ARG;
     float* shift = reinterpret_cast<float*>(blob.data() + l.shift_off);
     for (int n = 0; n < l.cout; ++n) shift[n] = h.shift_host[n];
-    if (l.k == 7) {                                      // stem: fp32 [tap][cout]
-      float* w = reinterpret_cast<float*>(blob.data() + l.w_off);
+    if (l.k == 7) {                                      // stem: [k8][cout][8] with K = tap index, padded to 64
+      h16* w = reinterpret_cast<h16*>(blob.data() + l.w_off);
       for (int n = 0; n < 64; ++n)
-        for (int t = 0; t < 49; ++t) w[t * 64 + n] = h.weight_host[(size_t)n * 49 + t] * h.scale_host[n];
+        for (int t = 0; t < 64; ++t)
+          w[((t >> 3) * 64 + n) * 8 + (t & 7)] =
+              f2h16(t < 49 ? h.weight_host[(size_t)n * 49 + t] * h.scale_host[n] : 0.f, cfg->operand_dtype);
       continue;
     }
-    __nv_bfloat16* w = reinterpret_cast<__nv_bfloat16*>(blob.data() + l.w_off);
+    h16* w = reinterpret_cast<h16*>(blob.data() + l.w_off);
     const int taps = l.k * l.k, k8 = l.cin_pad / 8, ntiles = l.cout_pad / l.nt;
     for (int ti = 0; ti < ntiles; ++ti)
       for (int t = 0; t < taps; ++t)
@@ -203,7 +206,7 @@ extern "C" int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvH
               const int cref = l.remap_s2 ? s2_to_ref(p, ci) : (ci < l.cin ? ci : -1);
               float v = 0.f;
               if (n < l.cout && cref >= 0) v = h.weight_host[((size_t)n * l.cin + cref) * taps + t] * h.scale_host[n];
-              w[((((size_t)ti * taps + t) * k8 + g) * l.nt + nn) * 8 + j] = __float2bfloat16(v);
+              w[((((size_t)ti * taps + t) * k8 + g) * l.nt + nn) * 8 + j] = f2h16(v, cfg->operand_dtype);
             }
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -213,10 +216,28 @@ extern "C" int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvH
 }
 
 namespace {
-std::atomic<int> g_dbg_swap{0};
+// Two auxiliary streams + fork/join events, created once per process (diagnostic-free plumbing state;
+// no results live here).  Guarded for concurrent first use.
+struct AuxStreams {
+  cudaStream_t s[2];
+  cudaEvent_t fork, join[2];
+};
+AuxStreams* aux_streams() {
+  static AuxStreams aux;
+  static std::atomic<int> state{0};     // 0 = uninitialised, 1 = initialising, 2 = ready, 3 = failed
+  int expected = 0;
+  if (state.compare_exchange_strong(expected, 1)) {
+    bool ok = true;
+    for (int i = 0; i < 2; ++i) ok &= cudaStreamCreateWithFlags(&aux.s[i], cudaStreamNonBlocking) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&aux.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2; ++i) ok &= cudaEventCreateWithFlags(&aux.join[i], cudaEventDisableTiming) == cudaSuccess;
+    state.store(ok ? 2 : 3);
+  }
+  while (state.load() == 1) {
+  }
+  return state.load() == 2 ? &aux : nullptr;
 }
-// bring-up switch (not part of the public header): exchange LBO and SBO in the UMMA descriptors
-extern "C" __attribute__((visibility("default"))) void popnet_debug_set_desc_swap(int v) { g_dbg_swap.store(v); }
+}  // namespace
 
 extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev, const float* x, int batch,
                               float* paf, float* heat, float* depth, float* s1_paf, float* s1_heat, float* s1_depth,
@@ -235,7 +256,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     ConvArgs a{};
     a.in = buf_ptr(workspace, bi, l.in_plane0);
     a.in_plane_stride = bi.plane_stride;
-    a.w = reinterpret_cast<const __nv_bfloat16*>(blob + l.w_off);
+    a.w = reinterpret_cast<const h16*>(blob + l.w_off);
     a.shift = reinterpret_cast<const float*>(blob + l.shift_off);
     if (l.out_buf >= 0) {
       a.out = buf_ptr(workspace, p.bufs[l.out_buf], l.out_plane0);
@@ -254,7 +275,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     a.chunks = l.cin_pad / 64;
     a.a_stages = a.chunks > 1 ? 2 : 1;
     a.act = l.act; a.cout = l.cout; a.cout_pad = l.cout_pad; a.nt = l.nt; a.taps = l.k * l.k;
-    a.lbo_sbo_swapped = g_dbg_swap.load();
+    a.fmt = cfg->operand_dtype;
     if (impl == POPNET_FWD_IMPL_SIMT) return launch_conv_simt(a, st);
     // shrink the A staging if the tile does not fit next to two B stages
     int bst = 0;
@@ -266,16 +287,16 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     PoolArgs a{};
     a.in = buf_ptr(workspace, bi, 0); a.in_plane_stride = bi.plane_stride;
     a.out = buf_ptr(workspace, p.bufs[out_buf], out_plane0); a.out_plane_stride = p.bufs[out_buf].plane_stride;
-    a.planes = bi.C / 8; a.N = batch; a.H = bi.H; a.W = bi.W;
+    a.planes = bi.C / 8; a.N = batch; a.H = bi.H; a.W = bi.W; a.fmt = cfg->operand_dtype;
     return launch_pool(a, st);
   };
 #define POPNET_TRY(expr) do { int _rc = (expr); if (_rc != POPNET_OK) return _rc; } while (0)
   {
     const Layer& l = p.layers[0];
     StemArgs a{};
-    a.x = x; a.w = reinterpret_cast<const float*>(blob + l.w_off); a.shift = reinterpret_cast<const float*>(blob + l.shift_off);
+    a.x = x; a.w = reinterpret_cast<const h16*>(blob + l.w_off); a.shift = reinterpret_cast<const float*>(blob + l.shift_off);
     a.out = buf_ptr(workspace, p.bufs[A112], 0); a.out_plane_stride = p.bufs[A112].plane_stride;
-    a.N = batch; a.H = cfg->height; a.W = cfg->width;
+    a.N = batch; a.H = cfg->height; a.W = cfg->width; a.fmt = cfg->operand_dtype;
     POPNET_TRY(launch_stem(a, st));
   }
   for (int li = 1; li <= 4; ++li) POPNET_TRY(run_conv(li));
@@ -285,7 +306,26 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
   POPNET_TRY(run_conv(6));
   POPNET_TRY(run_conv(8));
   POPNET_TRY(run_pool(E56, S2IN, (p.pl + p.ph + p.pd) / 8));
-  for (int li = 9; li < (int)p.layers.size(); ++li) POPNET_TRY(run_conv(li));
+  // The three branches of a stage are independent 5-conv chains on the same input: run the heat-map and
+  // depth branches on two auxiliary streams so that their CTAs fill the SMs the (two-wave) PAF branch
+  // leaves idle.  Fork/join through events keeps the whole forward capturable in a CUDA graph.
+  AuxStreams* aux = aux_streams();
+  if (!aux) return POPNET_ERR_CUDA;
+  for (int s = 1; s <= 2; ++s) {
+    const int base = 9 + 15 * (s - 1);
+    POPNET_CUDA_TRY(cudaEventRecord(aux->fork, st));
+    for (int b = 0; b < 2; ++b) POPNET_CUDA_TRY(cudaStreamWaitEvent(aux->s[b], aux->fork, 0));
+    cudaStream_t main_st = st;
+    for (int b = 0; b < 3; ++b) {
+      st = (b == 0) ? main_st : aux->s[b - 1];
+      for (int i = 0; i < 5; ++i) POPNET_TRY(run_conv(base + 5 * b + i));
+    }
+    st = main_st;
+    for (int b = 0; b < 2; ++b) {
+      POPNET_CUDA_TRY(cudaEventRecord(aux->join[b], aux->s[b]));
+      POPNET_CUDA_TRY(cudaStreamWaitEvent(st, aux->join[b], 0));
+    }
+  }
 #undef POPNET_TRY
   return POPNET_OK;
 }
@@ -300,19 +340,20 @@ struct PopnetDebugConv {
   void* out; long long out_plane_stride;
   const void* res; long long res_plane_stride;
   float* head_out;
-  int P, Hp, Wp, chunks, a_stages, act, cout, cout_pad, nt, nacc, taps, impl, swap;
+  int P, Hp, Wp, chunks, a_stages, act, cout, cout_pad, nt, nacc, taps, impl, fmt, dbg;
+  long long* probe;
 };
 
 extern "C" __attribute__((visibility("default"))) int popnet_debug_conv(const PopnetDebugConv* d, void* stream) {
   if (!d) return POPNET_ERR_INVALID_ARG;
   ConvArgs a{};
-  a.in = static_cast<const __nv_bfloat16*>(d->in); a.in_plane_stride = d->in_plane_stride;
-  a.w = static_cast<const __nv_bfloat16*>(d->w); a.shift = d->shift;
-  a.out = static_cast<__nv_bfloat16*>(d->out); a.out_plane_stride = d->out_plane_stride;
-  a.res = static_cast<const __nv_bfloat16*>(d->res); a.res_plane_stride = d->res_plane_stride;
+  a.in = static_cast<const h16*>(d->in); a.in_plane_stride = d->in_plane_stride;
+  a.w = static_cast<const h16*>(d->w); a.shift = d->shift;
+  a.out = static_cast<h16*>(d->out); a.out_plane_stride = d->out_plane_stride;
+  a.res = static_cast<const h16*>(d->res); a.res_plane_stride = d->res_plane_stride;
   a.head_out = d->head_out;
   a.P = d->P; a.Hp = d->Hp; a.Wp = d->Wp; a.chunks = d->chunks; a.a_stages = d->a_stages; a.act = d->act;
-  a.cout = d->cout; a.cout_pad = d->cout_pad; a.nt = d->nt; a.taps = d->taps; a.lbo_sbo_swapped = d->swap;
+  a.cout = d->cout; a.cout_pad = d->cout_pad; a.nt = d->nt; a.taps = d->taps; a.fmt = d->fmt; a.dbg = d->dbg; a.probe = d->probe;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return d->impl == POPNET_FWD_IMPL_SIMT ? launch_conv_simt(a, st) : launch_conv_tc(a, d->nacc, st);
 }

@@ -87,6 +87,7 @@ class rtpose_light3d(nn.Module):
                 setattr(self, "model%d_%d" % (s, b), _stage(spec))
         self._initialize_weights_norm()
         self.impl = _abi.FWD_IMPL_TCGEN05
+        self.operand_dtype = _abi.OPERAND_BF16     # or _abi.OPERAND_FP16; call pack() again after changing
         self._packed = None        # (device blob, config key)
         self._workspace = None
         for p in self.parameters():
@@ -137,7 +138,7 @@ class rtpose_light3d(nn.Module):
 
     def _net_config(self, h, w):
         return _abi.NetConfig(num_parts=self.num_parts, num_limbs=self.num_limbs, input_dim=self.input_dim,
-                              height=h, width=w)
+                              height=h, width=w, operand_dtype=int(self.operand_dtype))
 
     def pack(self, h=224, w=224):
         """Fold + pack the current parameters into the device blob (idempotent until load_state_dict)."""
@@ -167,6 +168,7 @@ class rtpose_light3d(nn.Module):
                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, "popnet_pack_weights")
         self._packed = blob
+        self._packed_dtype = int(self.operand_dtype)
         return blob
 
     def forward(self, x):
@@ -178,7 +180,7 @@ class rtpose_light3d(nn.Module):
             raise ValueError("expected [B, %d, H, W], got %s" % (self.input_dim, tuple(x.shape)))
         x = x.contiguous().float()
         B, _, H, W = x.shape
-        if self._packed is None:
+        if self._packed is None or self._packed_dtype != int(self.operand_dtype):
             self.pack(H, W)
         cfg = self._net_config(H, W)
         ws_bytes = lib.popnet_workspace_bytes(C.byref(cfg), B)

@@ -17,7 +17,10 @@ class DebugConv(C.Structure):
                 ("out", C.c_void_p), ("out_plane_stride", C.c_longlong), ("res", C.c_void_p),
                 ("res_plane_stride", C.c_longlong), ("head_out", C.c_void_p)] + \
                [(n, C.c_int) for n in ("P", "Hp", "Wp", "chunks", "a_stages", "act", "cout", "cout_pad", "nt", "nacc",
-                                       "taps", "impl", "swap")]
+                                       "taps", "impl", "fmt", "dbg")] + [("probe", C.c_void_p)]
+
+
+DT = torch.bfloat16
 
 
 def to_c8p(x):
@@ -27,9 +30,9 @@ def to_c8p(x):
     plen = GUARD + (P + ROUND - 1) // ROUND * ROUND + GUARD
     xp = torch.zeros((N, Cc, H + 2, W + 2), device=x.device)
     xp[:, :, 1:-1, 1:-1] = x
-    planes = torch.full((Cc // 8, plen, 8), float("nan"), device=x.device, dtype=torch.bfloat16)
+    planes = torch.full((Cc // 8, plen, 8), float("nan"), device=x.device, dtype=DT)
     v = xp.permute(1, 0, 2, 3).reshape(Cc // 8, 8, P).permute(0, 2, 1)
-    planes[:, GUARD:GUARD + P] = v.to(torch.bfloat16)
+    planes[:, GUARD:GUARD + P] = v.to(DT)
     return planes, P, plen
 
 
@@ -45,7 +48,7 @@ def pack_w(w, nt, cin_pad, cout_pad):
     wp = torch.zeros((cout_pad, cin_pad, k * k), device=w.device)
     wp[:cout, :cin] = w.reshape(cout, cin, k * k)
     v = wp.reshape(cout_pad // nt, nt, cin_pad // 8, 8, k * k).permute(0, 4, 2, 1, 3).contiguous()
-    return v.to(torch.bfloat16)
+    return v.to(DT)
 
 
 CASES = [  # nt, nacc, taps, cin, cout, H, W, N, act, residual, head
@@ -63,9 +66,12 @@ CASES = [  # nt, nacc, taps, cin, cout, H, W, N, act, residual, head
 ]
 
 
+@pytest.mark.parametrize("fmt", [0, 1], ids=["bf16", "fp16"])
 @pytest.mark.parametrize("case", CASES, ids=["nt%d-acc%d-t%d-cin%d-cout%d" % c[:5] for c in CASES])
-def test_conv_tc_vs_simt_vs_torch(case, cuda_backend):
+def test_conv_tc_vs_simt_vs_torch(case, fmt, cuda_backend):
     nt, nacc, taps, cin, cout, H, W, N, act, use_res, head = case
+    global DT
+    DT = torch.bfloat16 if fmt == 0 else torch.float16
     lib = cuda_backend.lib
     lib.popnet_debug_conv.restype = C.c_int
     lib.popnet_debug_conv.argtypes = [C.POINTER(DebugConv), C.c_void_p]
@@ -81,23 +87,23 @@ def test_conv_tc_vs_simt_vs_torch(case, cuda_backend):
     wpk = pack_w(w, nt, cin_pad, cout_pad)
     rin = to_c8p(res)[0] if use_res else None
     # fp32 reference on the bf16-rounded operands
-    xr = x[:, :cin].to(torch.bfloat16).float()
-    wr = w.to(torch.bfloat16).float()
+    xr = x[:, :cin].to(DT).float()
+    wr = w.to(DT).float()
     ref = torch.nn.functional.conv2d(xr, wr, None, 1, k // 2) + shift[:cout].view(1, -1, 1, 1)
     if use_res:
-        ref = ref + res[:, :cout].to(torch.bfloat16).float()
+        ref = ref + res[:, :cout].to(DT).float()
     ref = {0: ref, 1: ref.relu(), 2: torch.nn.functional.leaky_relu(ref, 0.1), 3: (ref.sigmoid() - 0.5) * 4,
            4: ref.sigmoid()}[act]
     results = {}
-    for name, impl, swap in (("simt", 1, 0), ("tc", 0, 0)):
-        out = torch.full((cout_pad // 8, plen, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
+    for name, impl in (("simt", 1), ("tc", 0)):
+        out = torch.full((cout_pad // 8, plen, 8), float("nan"), device="cuda", dtype=DT)
         hout = torch.full((N, cout, H, W), float("nan"), device="cuda") if head else None
         d = DebugConv(inp=xin[:, GUARD:].data_ptr(), in_plane_stride=plen * 8, w=wpk.data_ptr(), shift=shift.data_ptr(),
                       out=out[:, GUARD:].data_ptr(), out_plane_stride=plen * 8,
                       res=(rin[:, GUARD:].data_ptr() if use_res else None), res_plane_stride=plen * 8,
                       head_out=(hout.data_ptr() if head else None), P=P, Hp=H + 2, Wp=W + 2, chunks=cin_pad // 64,
                       a_stages=2 if cin_pad > 64 else 1, act=act, cout=cout, cout_pad=cout_pad, nt=nt, nacc=nacc,
-                      taps=taps, impl=impl, swap=swap)
+                      taps=taps, impl=impl, fmt=fmt)
         rc = lib.popnet_debug_conv(C.byref(d), None)
         assert rc == 0, rc
         torch.cuda.synchronize()

@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -119,10 +119,11 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     sample = 16
-    fps, ts = cpu_path(sample, args.steps, args.warmup, cores)
+    steps = min(args.steps, 40)          # bounded: the whole run ends within a few minutes
+    fps, ts = cpu_path(sample, steps, min(args.warmup, 3), cores)
     desc = "%d frames per step: fp32 torch forward (%d threads) + C-oracle decode/lift over %d threads" % (sample, cores, cores)
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(ts)) * 1e3,
+            "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": float(np.mean(ts)) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU port of the reference path (oracle/); the Python reference "
                        "cannot travel to the GPU box"},
@@ -270,9 +271,9 @@ def run_ours(args, rank, local_rank, world):
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        fps, ts = cpu_path(16, 3, 1, cores)
+        fps, ts = cpu_path(64, 12, 1, cores)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": "16 frames x 3 repeats: fp32 torch forward (%d threads) + C-oracle decode/lift "
+                                "sample": "64 frames x 12 repeats: fp32 torch forward (%d threads) + C-oracle decode/lift "
                                           "over %d threads (%.1f s)" % (cores, cores, sum(ts))}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -282,8 +283,8 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])

@@ -84,6 +84,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same instruction with the two descriptors given as (lo, hi) 32-bit halves: only `lo` (start address) changes
+// between the MMAs of a tile, so the issuing thread does one integer add per operand per instruction
+__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrive when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -224,21 +240,33 @@ __device__ __forceinline__ uint4 finish8_fast(const uint32_t* acc, const float* 
 // ------------------------------------------------------------------------------------------------
 // tensor-core implicit GEMM
 // ------------------------------------------------------------------------------------------------
+constexpr int kNumSMs = 148;           // B200
 constexpr int kTcThreads = 384;       // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;
 
-// two CTAs per SM (register cap 85) for the tile shapes whose shared memory allows it
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent kernel: one CTA per SM walks the output tiles (tile = MT = NACC*128 positions x NT channels).
+// Three pipelines, all mbarrier-based:
+//   A ring  (a_full / a_empty, `ast` stages)  : one 64-input-channel slab of the tile + halo, all 9 taps read it
+//   B ring  (b_full / b_empty, BST stages)    : one (tap, 64-channel) weight slab
+//   accumulators (acc_full / acc_empty, AS)   : AS = 2 lets the epilogue of tile i run under the MMAs of tile i+1
 template <int NT, int NACC>
-constexpr int min_ctas() { return (NACC == 2 && NT <= 128) ? 2 : 1; }
+constexpr int acc_stages() { return (2 * NACC * NT <= 512) ? 2 : 1; }
 
 template <int NT, int NACC, int TAPS, int BST>
-__global__ void __launch_bounds__(kTcThreads, min_ctas<NT, NACC>()) conv_tc_kernel(const ConvArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int MT = NACC * 128;
+  constexpr int AS = acc_stages<NT, NACC>();
   constexpr uint32_t kBStageBytes = 8u * NT * 16u;          // 64 input channels x NT output channels
-  constexpr uint32_t kCols = (NACC * NT <= 32) ? 32 : (NACC * NT <= 64) ? 64 : (NACC * NT <= 128) ? 128
-                             : (NACC * NT <= 256) ? 256 : 512;
-  static_assert(NACC * NT <= 512, "accumulators exceed TMEM");
+  constexpr uint32_t kAccCols = NACC * NT;
+  constexpr uint32_t kCols = (AS * kAccCols <= 32) ? 32 : (AS * kAccCols <= 64) ? 64 : (AS * kAccCols <= 128) ? 128
+                             : (AS * kAccCols <= 256) ? 256 : 512;
+  static_assert(AS * kAccCols <= 512, "accumulators exceed TMEM");
+  constexpr int kNumBars = 4 + 2 * BST + 2 * AS;
   const int halo = (TAPS == 9) ? a.Wp + 1 : 0;
   const int apos = MT + 2 * halo;                            // positions per staged plane
   const uint32_t a_plane_bytes = (uint32_t)apos * 16u;
@@ -247,29 +275,28 @@ __global__ void __launch_bounds__(kTcThreads, min_ctas<NT, NACC>()) conv_tc_kern
   uint8_t* sA = smem;
   uint8_t* sB = smem + (((size_t)ast * a_stage_bytes + 127) & ~(size_t)127);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)BST * kBStageBytes);
-  // bars: [0,2) a_full, [2,4) a_empty, [4,4+BST) b_full, [4+BST,4+2BST) b_empty, [4+2BST] acc_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * BST + 1);
-  float* s_shift = reinterpret_cast<float*>(bars + 4 + 2 * BST + 2);      // [NT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  float* s_shift = reinterpret_cast<float*>(bars + kNumBars + 1);         // [NT]
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8u * s; };
   auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
   auto b_full = [&](int s) { return bar0 + 8u * (4 + s); };
   auto b_empty = [&](int s) { return bar0 + 8u * (4 + BST + s); };
-  const uint32_t acc_full = bar0 + 8u * (4 + 2 * BST);
+  auto acc_full = [&](int s) { return bar0 + 8u * (4 + 2 * BST + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (4 + 2 * BST + AS + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t0 = blockIdx.x * MT;
-  const int ntile = blockIdx.y;
-  long long* probe = (a.probe && blockIdx.y == 0) ? a.probe + (long long)blockIdx.x * 16 : nullptr;
+  const int num_tiles = (a.P + MT - 1) / MT;
+  long long* probe = a.probe ? a.probe + (long long)blockIdx.x * 16 : nullptr;
   if (probe && threadIdx.x == 0) probe[0] = clock64();
   const int chunks = a.chunks;
   const int k8_total = chunks * 8;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4 + 2 * BST + 1; ++i) mbar_init(bar0 + 8u * i, 1);
+    for (int i = 0; i < kNumBars; ++i) mbar_init(bar0 + 8u * i, (i >= 4 + 2 * BST + AS) ? 8u : 1u);   // acc_empty: 8 epilogue warps
     fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < NT; i += kTcThreads) s_shift[i] = a.shift[ntile * NT + i];
+  for (int i = threadIdx.x; i < NT; i += kTcThreads) s_shift[i] = a.shift[i];
   if (warp == 2) {
     tmem_alloc(smem_u32(tmem_slot), kCols);
     tmem_relinquish();
@@ -283,125 +310,156 @@ __global__ void __launch_bounds__(kTcThreads, min_ctas<NT, NACC>()) conv_tc_kern
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- producer ----------------
-      const h16* wbase = a.w + (long long)ntile * TAPS * k8_total * NT * 8;
-      for (int c = 0; c < chunks; ++c) {
-        const int as = c % ast;
-        if (c >= ast) mbar_wait(a_empty(as), ((c / ast) - 1) & 1);
-        mbar_expect_tx(a_full(as), a_stage_bytes);
-        for (int g = 0; g < 8; ++g)
-          bulk_g2s(smem_u32(sA + (size_t)as * a_stage_bytes + (size_t)g * a_plane_bytes),
-                   a.in + (long long)(c * 8 + g) * a.in_plane_stride + (long long)(t0 - halo) * 8, a_plane_bytes,
-                   a_full(as));
-        for (int t = 0; t < TAPS; ++t) {
-          const int it = c * TAPS + t, bs = it % BST;
-          if (it >= BST) mbar_wait(b_empty(bs), ((it / BST) - 1) & 1);
-          mbar_expect_tx(b_full(bs), kBStageBytes);
-          bulk_g2s(smem_u32(sB + (size_t)bs * kBStageBytes), wbase + ((long long)t * k8_total + c * 8) * NT * 8,
-                   kBStageBytes, b_full(bs));
+      int ia = 0, ib = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int t0 = tile * MT;
+        for (int c = 0; c < chunks; ++c, ++ia) {
+          const int as = ia % ast;
+          if (ia >= ast) mbar_wait(a_empty(as), ((ia / ast) - 1) & 1);
+          mbar_expect_tx(a_full(as), a_stage_bytes);
+          for (int g = 0; g < 8; ++g)
+            bulk_g2s(smem_u32(sA + (size_t)as * a_stage_bytes + (size_t)g * a_plane_bytes),
+                     a.in + (long long)(c * 8 + g) * a.in_plane_stride + (long long)(t0 - halo) * 8, a_plane_bytes,
+                     a_full(as));
+          for (int t = 0; t < TAPS; ++t, ++ib) {
+            const int bs = ib % BST;
+            if (ib >= BST) mbar_wait(b_empty(bs), ((ib / BST) - 1) & 1);
+            mbar_expect_tx(b_full(bs), kBStageBytes);
+            bulk_g2s(smem_u32(sB + (size_t)bs * kBStageBytes), a.w + ((long long)t * k8_total + c * 8) * NT * 8,
+                     kBStageBytes, b_full(bs));
+          }
         }
       }
-      if (probe) probe[2] = clock64();
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = umma_idesc(NT, a.fmt);
       const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
-      const uint32_t a_lbo = a_plane_bytes, a_sbo = 128u;      // K-direction / 8-row-group strides
-      const uint32_t b_lbo = (uint32_t)NT * 16u, b_sbo = 128u;
-      long long wait_a = 0, wait_b = 0;
-      for (int c = 0; c < chunks; ++c) {
-        const int as = c % ast;
-        long long tw = probe ? clock64() : 0;
-        mbar_wait(a_full(as), (c / ast) & 1);
-        if (probe) wait_a += clock64() - tw;
-        tc_fence_after();
-        for (int t = 0; t < TAPS; ++t) {
-          const int it = c * TAPS + t, bs = it % BST;
-          tw = probe ? clock64() : 0;
-          mbar_wait(b_full(bs), (it / BST) & 1);
-          if (probe) wait_b += clock64() - tw;
+      // descriptor halves: hi = SBO (128 B between 8-row groups) | version 1; lo = start address | LBO << 16
+      // (LBO = byte distance between the two K core matrices of one K=16 instruction), all in 16-byte units
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+      const uint32_t a_lo0 = ((sA0 >> 4) & 0x3FFFu) | (((a_plane_bytes >> 4) & 0x3FFFu) << 16);
+      const uint32_t b_lo0 = ((sB0 >> 4) & 0x3FFFu) | ((((uint32_t)NT * 16u >> 4) & 0x3FFFu) << 16);
+      const uint32_t a_kstep = (2u * a_plane_bytes) >> 4;       // two K core matrices per instruction
+      constexpr uint32_t b_kstep = (2u * NT * 16u) >> 4;
+      long long wait_a = 0, wait_b = 0, wait_acc = 0;
+      int ia = 0, ib = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        const int s = ti % AS;
+        if (ti >= AS) {
+          long long tw = probe ? clock64() : 0;
+          mbar_wait(acc_empty(s), ((ti / AS) - 1) & 1);
+          if (probe) wait_acc += clock64() - tw;
           tc_fence_after();
-          const int shift = (TAPS == 9) ? ((t / 3 - 1) * a.Wp + (t % 3 - 1) + halo) : 0;
-#pragma unroll
-          for (int acc = 0; acc < NACC; ++acc) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t da = umma_desc(sA0 + as * a_stage_bytes + (2 * kk) * a_plane_bytes + (uint32_t)(shift + acc * 128) * 16u,
-                                            a_lbo, a_sbo);
-              const uint64_t db = umma_desc(sB0 + bs * kBStageBytes + (2 * kk) * NT * 16u, b_lbo, b_sbo);
-              if (!(a.dbg & 1)) umma_bf16(tmem_base + acc * NT, da, db, idesc, (c | t | kk) != 0 ? 1u : 0u);
-            }
-          }
-          umma_commit(b_empty(bs));       // B stage reusable once these MMAs retire
         }
-        umma_commit(a_empty(as));
+        const uint32_t tmem_acc = tmem_base + (uint32_t)s * kAccCols;
+        uint32_t accumulate = 0;
+        for (int c = 0; c < chunks; ++c, ++ia) {
+          const int as = ia % ast;
+          long long tw = probe ? clock64() : 0;
+          mbar_wait(a_full(as), (ia / ast) & 1);
+          if (probe) wait_a += clock64() - tw;
+          tc_fence_after();
+          const uint32_t a_lo_stage = a_lo0 + ((as * a_stage_bytes) >> 4);
+#pragma unroll 1
+          for (int t = 0; t < TAPS; ++t, ++ib) {
+            const int bs = ib % BST;
+            tw = probe ? clock64() : 0;
+            mbar_wait(b_full(bs), (ib / BST) & 1);
+            if (probe) wait_b += clock64() - tw;
+            tc_fence_after();
+            const int shift = (TAPS == 9) ? ((t / 3 - 1) * a.Wp + (t % 3 - 1) + halo) : 0;
+            const uint32_t a_lo_tap = a_lo_stage + (uint32_t)shift;          // one position = one 16-byte unit
+            const uint32_t b_lo_tap = b_lo0 + ((bs * kBStageBytes) >> 4);
+            if (!(a.dbg & 1)) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                for (int acc = 0; acc < NACC; ++acc)
+                  umma_lohi(tmem_acc + acc * NT, a_lo_tap + kk * a_kstep + acc * 128, desc_hi, b_lo_tap + kk * b_kstep, desc_hi,
+                            idesc, (kk == 0) ? accumulate : 1u);
+              }
+            }
+            accumulate = 1u;
+            umma_commit(b_empty(bs));       // B stage reusable once these MMAs retire
+          }
+          umma_commit(a_empty(as));
+        }
+        umma_commit(acc_full(s));
       }
-      umma_commit(acc_full);
-      if (probe) { probe[3] = wait_a; probe[4] = wait_b; probe[5] = clock64(); }
+      if (probe) { probe[3] = wait_a; probe[4] = wait_b; probe[5] = clock64(); probe[10] = wait_acc; probe[9] = ti; }
     }
   } else if (warp >= kEpiWarp0) {
     // ---------------- epilogue: TMEM lane quarter q, thread = one output position; the two warps of a
     // quarter split the column chunks between them (a lone warp per scheduler is issue-latency bound) ----
     const int q = warp & 3;
     const int half = (warp - kEpiWarp0) >> 2;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    if (probe && threadIdx.x == kEpiWarp0 * 32) probe[6] = clock64();
     const bool head = a.act == kActHeadPaf || a.act == kActHeadHeat;
     const float slope = a.act == kActRelu ? 0.f : (a.act == kActLeaky ? 0.1f : 1.f);
+    long long wait_full = 0, busy = 0;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      const int s = ti % AS;
+      const int t0 = tile * MT;
+      long long tw = probe ? clock64() : 0;
+      mbar_wait(acc_full(s), (ti / AS) & 1);
+      tc_fence_after();
+      long long tb = probe ? clock64() : 0;
+      if (probe) wait_full += tb - tw;
 #pragma unroll 1
-    for (int acc = 0; acc < NACC; ++acc) {
-      const int pos = t0 + acc * 128 + q * 32 + lane;
-      const PosInfo pi = locate(pos, a);
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
-      if (head) {
-        // output heads (NT = 16 / 32): fp32 NCHW maps with the sigmoid scaling, optional 16-bit copy
+      for (int acc = 0; acc < NACC; ++acc) {
+        const int pos = t0 + acc * 128 + q * 32 + lane;
+        const PosInfo pi = locate(pos, a);
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + acc * NT);
+        if (head) {
+          // output heads (NT = 16 / 32): fp32 NCHW maps with the sigmoid scaling, optional 16-bit copy
 #pragma unroll 1
-        for (int j = half; j < NT / 16; j += 2) {
-          uint32_t r[16];
-          tmem_ld16(trow + (uint32_t)(j * 16), r);
-          tmem_ld_wait();
-          float v[8];
+          for (int j = half; j < NT / 16; j += 2) {
+            uint32_t r[16];
+            tmem_ld16(trow + (uint32_t)(j * 16), r);
+            tmem_ld_wait();
+            float v[8];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h * 8 + i]);
-            if (!(a.dbg & 2)) finish8(a, pos, pi, ntile * NT + j * 16 + h * 8, v);
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h * 8 + i]);
+              if (!(a.dbg & 2)) finish8(a, pos, pi, j * 16 + h * 8, v);
+            }
           }
-        }
-      } else if constexpr (NT >= 32) {
+        } else if constexpr (NT >= 32) {
 #pragma unroll 1
-        for (int j = half; j < NT / 32; j += 2) {
-          uint32_t r[32];
-          if (!(a.dbg & 8)) tmem_ld32(trow + (uint32_t)(j * 32), r);
-          else {
+          for (int j = half; j < NT / 32; j += 2) {
+            uint32_t r[32];
+            tmem_ld32(trow + (uint32_t)(j * 32), r);
+            const int plane = (j * 32) >> 3;
+            uint4 rs[4];
+            const bool has_res = a.res != nullptr && pi.interior;
+            if (has_res) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = 0x3f800000u + i + lane;
-          }
-          const int plane = (ntile * NT + j * 32) >> 3;
-          uint4 rs[4];
-          const bool has_res = a.res != nullptr && pi.interior;
-          if (has_res) {
+              for (int g = 0; g < 4; ++g)
+                rs[g] = *reinterpret_cast<const uint4*>(a.res + (long long)(plane + g) * a.res_plane_stride + (long long)pos * 8);
+            }
+            tmem_ld_wait();
+            if (pi.in_range && !(a.dbg & 2)) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              rs[g] = *reinterpret_cast<const uint4*>(a.res + (long long)(plane + g) * a.res_plane_stride + (long long)pos * 8);
-          }
-          if (!(a.dbg & 8)) tmem_ld_wait();
-          if (pi.in_range && !(a.dbg & 2)) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint4 o = finish8_fast(r + g * 8, s_shift + j * 32 + g * 8, has_res, rs[g], slope, pi.interior, a.fmt);
-              if (!(a.dbg & 4) || o.x == 0x12345678u)
+              for (int g = 0; g < 4; ++g) {
+                const uint4 o = finish8_fast(r + g * 8, s_shift + j * 32 + g * 8, has_res, rs[g], slope, pi.interior, a.fmt);
                 *reinterpret_cast<uint4*>(a.out + (long long)(plane + g) * a.out_plane_stride + (long long)pos * 8) = o;
+              }
             }
           }
         }
       }
+      // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(s));
+      if (probe) busy += clock64() - tb;
     }
-    if (probe && threadIdx.x == kEpiWarp0 * 32) probe[7] = clock64();
-    tc_fence_before();
+    if (probe && threadIdx.x == kEpiWarp0 * 32) { probe[6] = wait_full; probe[7] = busy; }
   }
+  tc_fence_before();
   __syncthreads();
   if (probe && threadIdx.x == 0) probe[8] = clock64();
   if (warp == 2) {
@@ -584,8 +642,12 @@ template <int NT, int NACC, int TAPS, int BST>
 int launch_tc_inst(const ConvArgs& a, size_t smem, cudaStream_t st) {
   auto kern = conv_tc_kernel<NT, NACC, TAPS, BST>;
   POPNET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // ask for the full shared-memory carveout so that two CTAs can be co-resident where their tiles allow it
+  POPNET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int MT = NACC * 128;
-  dim3 grid((a.P + MT - 1) / MT, a.cout_pad / NT);
+  if (a.cout_pad != NT) return POPNET_ERR_UNSUPPORTED;     // one N tile per layer (true for every rtpose layer)
+  const int tiles = (a.P + MT - 1) / MT;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;        // persistent: one CTA per SM walks the tiles
   kern<<<grid, kTcThreads, smem, st>>>(a);
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;

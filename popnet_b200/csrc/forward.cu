@@ -91,10 +91,10 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   p.layers.clear();
   // block0
   add(1, 64, 7, 64, 0, kActRelu, -1, 0, A112, 0, -1, 0, 0, 0);              // 0 conv1 (stem kernel)
-  add(64, 64, 3, 64, 2, kActRelu, A112, 0, B112, 0, -1, 0, 0, 0);           // 1 layer1.0.conv1
-  add(64, 64, 3, 64, 2, kActRelu, B112, 0, C112, 0, A112, 0, 0, 0);         // 2 layer1.0.conv2 (+x)
-  add(64, 64, 3, 64, 2, kActRelu, C112, 0, B112, 0, -1, 0, 0, 0);           // 3 layer1.1.conv1
-  add(64, 64, 3, 64, 2, kActRelu, B112, 0, A112, 0, C112, 0, 0, 0);         // 4 layer1.1.conv2 (+x)
+  add(64, 64, 3, 64, 4, kActRelu, A112, 0, B112, 0, -1, 0, 0, 0);           // 1 layer1.0.conv1
+  add(64, 64, 3, 64, 4, kActRelu, B112, 0, C112, 0, A112, 0, 0, 0);         // 2 layer1.0.conv2 (+x)
+  add(64, 64, 3, 64, 4, kActRelu, C112, 0, B112, 0, -1, 0, 0, 0);           // 3 layer1.1.conv1
+  add(64, 64, 3, 64, 4, kActRelu, B112, 0, A112, 0, C112, 0, 0, 0);         // 4 layer1.1.conv2 (+x)
   add(64, 128, 3, 128, 2, kActRelu, D56, 0, E56, 0, -1, 0, 0, 0);           // 5 layer2.0.conv1
   add(128, 128, 3, 128, 4, kActRelu, E56, 0, G56, 0, F56, 0, 0, 0);         // 6 layer2.0.conv2 (+downsample)
   add(64, 128, 1, 128, 4, kActNone, D56, 0, F56, 0, -1, 0, 0, 0);           // 7 layer2.0.downsample
@@ -273,7 +273,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     }
     a.P = bi.P; a.Hp = bi.H + 2; a.Wp = bi.W + 2;
     a.chunks = l.cin_pad / 64;
-    a.a_stages = a.chunks > 1 ? 2 : 1;
+    a.a_stages = 2;                       // double-buffered across chunks AND across tiles (persistent kernel)
     a.act = l.act; a.cout = l.cout; a.cout_pad = l.cout_pad; a.nt = l.nt; a.taps = l.k * l.k;
     a.fmt = cfg->operand_dtype;
     if (impl == POPNET_FWD_IMPL_SIMT) return launch_conv_simt(a, st);

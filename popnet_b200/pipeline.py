@@ -85,19 +85,30 @@ class PoseEstimator:
 # ---------------------------------------------------------------------------------------------
 def gather_records(records, group=None):
     """All-gather fixed-size pose records of equal-sized batch shards; rank r's frames land at
-    [r*B, (r+1)*B).  Works on CUDA tensors (NCCL) and CPU tensors (gloo).  Returns a dict of tensors."""
+    [r*B, (r+1)*B).  Works on CUDA tensors (NCCL) and CPU tensors (gloo).  The eight record arrays of a
+    frame are packed into one byte row so that the step issues ONE collective (int16 fields are not a
+    collective dtype in either backend anyway).  Returns a dict of tensors."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    out = {}
+    parts, meta = [], []
+    B = None
     for k in RECORD_KEYS:
         t = records[k]
         t = t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t))
         if t.dtype == torch.uint32:
             t = t.view(torch.int32)
         t = t.contiguous()
-        full = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(full, t, group=group)
-        out[k] = full
+        B = t.shape[0]
+        row = t.reshape(B, -1).view(torch.uint8)
+        parts.append(row)
+        meta.append((k, t.dtype, tuple(t.shape[1:]), row.shape[1]))
+    packed = torch.cat(parts, dim=1).contiguous()
+    full = torch.empty((world * B, packed.shape[1]), dtype=torch.uint8, device=packed.device)
+    dist.all_gather_into_tensor(full, packed, group=group)
+    out, off = {}, 0
+    for k, dt, shape, nbytes in meta:
+        out[k] = full[:, off:off + nbytes].contiguous().view(dt).reshape((world * B,) + shape)
+        off += nbytes
     return out
 
 

@@ -102,7 +102,7 @@ def test_conv_tc_vs_simt_vs_torch(case, fmt, cuda_backend):
                       out=out[:, GUARD:].data_ptr(), out_plane_stride=plen * 8,
                       res=(rin[:, GUARD:].data_ptr() if use_res else None), res_plane_stride=plen * 8,
                       head_out=(hout.data_ptr() if head else None), P=P, Hp=H + 2, Wp=W + 2, chunks=cin_pad // 64,
-                      a_stages=2 if cin_pad > 64 else 1, act=act, cout=cout, cout_pad=cout_pad, nt=nt, nacc=nacc,
+                      a_stages=2, act=act, cout=cout, cout_pad=cout_pad, nt=nt, nacc=nacc,
                       taps=taps, impl=impl, fmt=fmt)
         rc = lib.popnet_debug_conv(C.byref(d), None)
         assert rc == 0, rc

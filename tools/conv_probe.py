@@ -21,11 +21,13 @@ lib.popnet_debug_conv.restype = C.c_int
 lib.popnet_debug_conv.argtypes = [C.POINTER(DebugConv), C.c_void_p]
 
 # name, nt, nacc, taps, cin, cout, H
-LAYERS_ALL = [("64->64@112", 64, 2, 9, 64, 64, 112), ("64->128@56", 128, 2, 9, 64, 128, 56),
+LAYERS_ALL = [("64->64@112", 64, 2, 9, 64, 64, 112), ("64->64@112 acc4", 64, 4, 9, 64, 64, 112),
+          ("64->128@56", 128, 2, 9, 64, 128, 56), ("64->128@56 acc4", 128, 4, 9, 64, 128, 56),
+          ("128->128@56 acc2", 128, 2, 9, 128, 128, 56), ("128->128@28 acc2", 128, 2, 9, 128, 128, 28),
           ("128->128@56", 128, 4, 9, 128, 128, 56), ("1x1 128->128@56", 128, 4, 1, 128, 128, 56),
           ("256->256@28", 256, 2, 9, 256, 256, 28), ("128->128@28", 128, 4, 9, 128, 128, 28),
           ("64->64@28", 64, 4, 9, 64, 64, 28)]
-LAYERS = [l for l in LAYERS_ALL if l[0] in ("64->64@112", "256->256@28", "128->128@28")]
+LAYERS = LAYERS_ALL
 for name, nt, nacc, taps, cin, cout, H in LAYERS:
     N = a.batch
     P = N * (H + 2) * (H + 2)
@@ -39,10 +41,10 @@ for name, nt, nacc, taps, cin, cout, H in LAYERS:
     ncta = (P + mt - 1) // mt
     probe = torch.zeros((ncta, 16), device="cuda", dtype=torch.int64)
     flops = 2.0 * N * H * H * cin * cout * taps
-    for dbg, label in ((0, "full"), (1, "no-mma"), (2, "no-epilogue"), (4, "epilogue w/o STG"), (8, "epilogue w/o LDTM"), (12, "w/o STG+LDTM")):
+    for dbg, label in ((0, "full"), (1, "no-mma"), (2, "no-epilogue")):
         d = DebugConv(inp=xin[:, GUARD:].data_ptr(), in_plane_stride=plen * 8, w=w.data_ptr(), shift=shift.data_ptr(),
                       out=out[:, GUARD:].data_ptr(), out_plane_stride=plen * 8, res=None, res_plane_stride=0,
-                      head_out=None, P=P, Hp=H + 2, Wp=H + 2, chunks=cin // 64, a_stages=2 if cin > 64 else 1, act=1,
+                      head_out=None, P=P, Hp=H + 2, Wp=H + 2, chunks=cin // 64, a_stages=2, act=1,
                       cout=cout, cout_pad=cout, nt=nt, nacc=nacc, taps=taps, impl=0, fmt=0, dbg=dbg, probe=None)
         for _ in range(2):
             assert lib.popnet_debug_conv(C.byref(d), None) == 0
@@ -60,10 +62,8 @@ for name, nt, nacc, taps, cin, cout, H in LAYERS:
     lib.popnet_debug_conv(C.byref(d), None)
     torch.cuda.synchronize()
     pr = probe.cpu().numpy()
-    for cta in (0, ncta // 2, ncta - 2):
+    g = min(ncta, 148)
+    for cta in (0, g // 2, g - 1):
         r = pr[cta]
-        print("   cta %5d: setup %6d | producer done +%6d | mma wait_a %6d wait_b %6d issue-end +%6d | acc ready +%6d "
-              "epilogue %6d | total %6d cycles" % (cta, r[1] - r[0], r[2] - r[1], r[3], r[4], r[5] - r[1], r[6] - r[1],
-                                                  r[7] - r[6], r[8] - r[0]))
-    tot = pr[:, 8] - pr[:, 0]
-    print("   CTA lifetime cycles: median %d  p90 %d" % (np.median(tot), np.percentile(tot, 90)))
+        print("   cta %4d: tiles %3d | mma thread: wait_a %7d wait_b %7d wait_acc %7d end +%7d | epilogue warp: wait %7d busy %7d "
+              "| lifetime %7d cycles" % (cta, r[9], r[3], r[4], r[10], r[5] - r[1], r[6], r[7], r[8] - r[0]))

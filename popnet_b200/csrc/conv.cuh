@@ -22,7 +22,8 @@
 namespace popnet {
 
 constexpr int kGuard = 128;        // positions in front of / behind every plane (>= W + 3)
-constexpr int kPosRound = 512;     // planes hold a multiple of the largest CTA tile
+constexpr int kPosRound = 512;     // planes hold a multiple of 512 positions ...
+constexpr int kPosSlack = 512;     // ... plus slack so that 384-position tiles may overrun the last multiple
 
 // 16-bit operand storage: bf16 (fmt 0, the north-star default) or fp16 (fmt 1).  Both run at the same
 // tensor-core rate and byte count; fp16 carries 3 more mantissa bits ("operand format").
@@ -86,6 +87,6 @@ int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st);
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int launch_stem(const StemArgs& a, cudaStream_t st);
 int launch_pool(const PoolArgs& a, cudaStream_t st);
-size_t conv_tc_smem_bytes(int nt, int nacc, int taps, int a_stages, int Wp, int* b_stages_out);
+size_t conv_tc_smem_bytes(int nt, int nacc, int taps, int a_stages, int Wp, int* b_stages_out, bool b_resident = false);
 
 }  // namespace popnet

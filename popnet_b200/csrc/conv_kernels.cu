@@ -56,6 +56,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for waits that are expected to be long (epilogue warps waiting for a whole tile of MMAs): back off so
+// that the polling does not compete with the tensor core for shared-memory bandwidth
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+}
 // global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0, 16 B aligned)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -228,12 +233,10 @@ __device__ __forceinline__ uint4 finish8_fast(const uint32_t* acc, const float* 
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float y = fmaxf(x[i], 0.f) + slope * fminf(x[i], 0.f);     // ReLU / LeakyReLU / identity by slope
-    x[i] = interior ? y : 0.f;
-  }
+  for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], slope * x[i]);      // slope in [0,1]: ReLU 0, LeakyReLU 0.1, identity 1
   uint4 o;
   o.x = pack2(x[0], x[1], fmt); o.y = pack2(x[2], x[3], fmt); o.z = pack2(x[4], x[5], fmt); o.w = pack2(x[6], x[7], fmt);
+  if (!interior) o = make_uint4(0u, 0u, 0u, 0u);                     // padding ring stays zero
   return o;
 }
 
@@ -241,8 +244,15 @@ __device__ __forceinline__ uint4 finish8_fast(const uint32_t* acc, const float* 
 // tensor-core implicit GEMM
 // ------------------------------------------------------------------------------------------------
 constexpr int kNumSMs = 148;           // B200
-constexpr int kTcThreads = 384;       // 4 control warps + 8 epilogue warps
+constexpr int kTcThreads = 640;       // 4 control warps + 16 epilogue warps
+constexpr int kEpiWarps = 16;
 constexpr int kEpiWarp0 = 4;
+
+// Programmatic dependent launch: every kernel of the forward lets its successor be scheduled early
+// (launch_dependents) and touches global memory only after its predecessor has completed (wait), so the
+// successor's launch latency and prologue (barrier init, TMEM allocation) overlap the predecessor's tail.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -256,11 +266,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 template <int NT, int NACC>
 constexpr int acc_stages() { return (2 * NACC * NT <= 512) ? 2 : 1; }
 
-template <int NT, int NACC, int TAPS, int BST>
+//   BRES: the layer has a single 64-channel chunk and all of its taps' weights stay resident in shared memory
+//         for the whole kernel (loaded once): the MMA thread then never waits on the B ring, which matters
+//         because the tensor core's instruction queue is shallow -- every instruction the issuing thread
+//         spends between two MMAs is exposed (measured: tools/umma_bench.cu).
+//   DBG:  bring-up instantiation with clock64 probes and debug switches; the product path compiles them out.
+template <int NT, int NACC, int TAPS, int BST, bool BRES, bool DBG>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int MT = NACC * 128;
   constexpr int AS = acc_stages<NT, NACC>();
+  constexpr int kBSlots = BRES ? TAPS : BST;                 // B slabs held in shared memory
   constexpr uint32_t kBStageBytes = 8u * NT * 16u;          // 64 input channels x NT output channels
   constexpr uint32_t kAccCols = NACC * NT;
   constexpr uint32_t kCols = (AS * kAccCols <= 32) ? 32 : (AS * kAccCols <= 64) ? 64 : (AS * kAccCols <= 128) ? 128
@@ -274,7 +290,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   const int ast = a.a_stages;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (((size_t)ast * a_stage_bytes + 127) & ~(size_t)127);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)BST * kBStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)kBSlots * kBStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   float* s_shift = reinterpret_cast<float*>(bars + kNumBars + 1);         // [NT]
   const uint32_t bar0 = smem_u32(bars);
@@ -287,13 +303,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (a.P + MT - 1) / MT;
-  long long* probe = a.probe ? a.probe + (long long)blockIdx.x * 16 : nullptr;
+  long long* probe = (DBG && a.probe) ? a.probe + (long long)blockIdx.x * 16 : nullptr;
+  const int dbg = DBG ? a.dbg : 0;
   if (probe && threadIdx.x == 0) probe[0] = clock64();
   const int chunks = a.chunks;
   const int k8_total = chunks * 8;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNumBars; ++i) mbar_init(bar0 + 8u * i, (i >= 4 + 2 * BST + AS) ? 8u : 1u);   // acc_empty: 8 epilogue warps
+    for (int i = 0; i < kNumBars; ++i) mbar_init(bar0 + 8u * i, (i >= 4 + 2 * BST + AS) ? (uint32_t)kEpiWarps : 1u);   // acc_empty: one arrive per epilogue warp
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < NT; i += kTcThreads) s_shift[i] = a.shift[i];
@@ -305,28 +323,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // activations of the previous layer are complete and visible from here on
   if (probe && threadIdx.x == 0) probe[1] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- producer ----------------
       int ia = 0, ib = 0;
+      if (BRES) {                                   // all taps of the (single) chunk, once
+        mbar_expect_tx(b_full(0), (uint32_t)TAPS * kBStageBytes);
+        for (int t = 0; t < TAPS; ++t)
+          bulk_g2s(smem_u32(sB + (size_t)t * kBStageBytes), a.w + (long long)t * k8_total * NT * 8, kBStageBytes, b_full(0));
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int t0 = tile * MT;
         for (int c = 0; c < chunks; ++c, ++ia) {
           const int as = ia % ast;
-          if (ia >= ast) mbar_wait(a_empty(as), ((ia / ast) - 1) & 1);
-          mbar_expect_tx(a_full(as), a_stage_bytes);
-          for (int g = 0; g < 8; ++g)
-            bulk_g2s(smem_u32(sA + (size_t)as * a_stage_bytes + (size_t)g * a_plane_bytes),
-                     a.in + (long long)(c * 8 + g) * a.in_plane_stride + (long long)(t0 - halo) * 8, a_plane_bytes,
-                     a_full(as));
-          for (int t = 0; t < TAPS; ++t, ++ib) {
+          if (ia >= ast) mbar_wait_relaxed(a_empty(as), ((ia / ast) - 1) & 1);
+          if ((dbg & 16) && ia >= ast) mbar_arrive(a_full(as));      // tuning: no copy traffic after the first fill
+          else {
+            mbar_expect_tx(a_full(as), a_stage_bytes);
+            for (int g = 0; g < 8; ++g)
+              bulk_g2s(smem_u32(sA + (size_t)as * a_stage_bytes + (size_t)g * a_plane_bytes),
+                       a.in + (long long)(c * 8 + g) * a.in_plane_stride + (long long)(t0 - halo) * 8, a_plane_bytes,
+                       a_full(as));
+          }
+          for (int t = 0; t < TAPS && !BRES; ++t, ++ib) {
             const int bs = ib % BST;
-            if (ib >= BST) mbar_wait(b_empty(bs), ((ib / BST) - 1) & 1);
-            mbar_expect_tx(b_full(bs), kBStageBytes);
-            bulk_g2s(smem_u32(sB + (size_t)bs * kBStageBytes), a.w + ((long long)t * k8_total + c * 8) * NT * 8,
-                     kBStageBytes, b_full(bs));
+            if (ib >= BST) mbar_wait_relaxed(b_empty(bs), ((ib / BST) - 1) & 1);
+            if ((dbg & 16) && ib >= BST) mbar_arrive(b_full(bs));
+            else {
+              mbar_expect_tx(b_full(bs), kBStageBytes);
+              bulk_g2s(smem_u32(sB + (size_t)bs * kBStageBytes), a.w + ((long long)t * k8_total + c * 8) * NT * 8,
+                       kBStageBytes, b_full(bs));
+            }
           }
         }
       }
@@ -344,14 +374,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
       const uint32_t a_kstep = (2u * a_plane_bytes) >> 4;       // two K core matrices per instruction
       constexpr uint32_t b_kstep = (2u * NT * 16u) >> 4;
       long long wait_a = 0, wait_b = 0, wait_acc = 0;
+      // The tensor core's instruction queue is shallow: whatever this thread does between two MMAs is exposed.
+      // Hence (1) no divisions / 64-bit math in the loop, (2) the B-ring wait of the NEXT tap is taken before the
+      // MMAs of the current tap are issued (always deadlock-free: that slot was released by a tap already issued).
       int ia = 0, ib = 0, ti = 0;
+      bool b_ready = false;                       // b_full of step `ib` already observed
+      if (BRES) { mbar_wait(b_full(0), 0); b_ready = true; }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
         const int s = ti % AS;
         if (ti >= AS) {
           long long tw = probe ? clock64() : 0;
           mbar_wait(acc_empty(s), ((ti / AS) - 1) & 1);
           if (probe) wait_acc += clock64() - tw;
-          tc_fence_after();
         }
         const uint32_t tmem_acc = tmem_base + (uint32_t)s * kAccCols;
         uint32_t accumulate = 0;
@@ -360,19 +394,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
           long long tw = probe ? clock64() : 0;
           mbar_wait(a_full(as), (ia / ast) & 1);
           if (probe) wait_a += clock64() - tw;
-          tc_fence_after();
           const uint32_t a_lo_stage = a_lo0 + ((as * a_stage_bytes) >> 4);
+          int bs = ib % BST;
+          uint32_t bph = (ib / BST) & 1;
+          int dh = -1, dw = -1;                   // tap offsets without div/mod
 #pragma unroll 1
           for (int t = 0; t < TAPS; ++t, ++ib) {
-            const int bs = ib % BST;
-            tw = probe ? clock64() : 0;
-            mbar_wait(b_full(bs), (ib / BST) & 1);
-            if (probe) wait_b += clock64() - tw;
-            tc_fence_after();
-            const int shift = (TAPS == 9) ? ((t / 3 - 1) * a.Wp + (t % 3 - 1) + halo) : 0;
+            int nbs = bs + 1;
+            uint32_t nbph = bph;
+            if (!BRES) {
+              if (!b_ready) {
+                tw = probe ? clock64() : 0;
+                mbar_wait(b_full(bs), bph);
+                if (probe) wait_b += clock64() - tw;
+              }
+              // look ahead: next B stage (also across chunk / tile boundaries)
+              if (nbs == BST) { nbs = 0; nbph ^= 1; }
+              tw = probe ? clock64() : 0;
+              b_ready = mbar_try_wait(b_full(nbs), nbph);     // one probe only; if not there yet, block next time
+              if (probe) wait_b += clock64() - tw;
+              tc_fence_after();
+            } else if (t == 0) {
+              tc_fence_after();
+            }
+            const int shift = (TAPS == 9) ? (dh * a.Wp + dw + halo) : 0;
             const uint32_t a_lo_tap = a_lo_stage + (uint32_t)shift;          // one position = one 16-byte unit
-            const uint32_t b_lo_tap = b_lo0 + ((bs * kBStageBytes) >> 4);
-            if (!(a.dbg & 1)) {
+            const uint32_t b_lo_tap = b_lo0 + (((BRES ? t : bs) * kBStageBytes) >> 4);
+            if (!(dbg & 1)) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
@@ -382,7 +430,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
               }
             }
             accumulate = 1u;
-            umma_commit(b_empty(bs));       // B stage reusable once these MMAs retire
+            if (!BRES) umma_commit(b_empty(bs));       // B stage reusable once these MMAs retire
+            bs = nbs; bph = nbph;
+            if (++dw == 2) { dw = -1; ++dh; }
           }
           umma_commit(a_empty(as));
         }
@@ -394,7 +444,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
     // ---------------- epilogue: TMEM lane quarter q, thread = one output position; the two warps of a
     // quarter split the column chunks between them (a lone warp per scheduler is issue-latency bound) ----
     const int q = warp & 3;
-    const int half = (warp - kEpiWarp0) >> 2;
+    const int sub = (warp - kEpiWarp0) >> 2;            // 0..3: the four warps of a lane quarter split the work items
     const bool head = a.act == kActHeadPaf || a.act == kActHeadHeat;
     const float slope = a.act == kActRelu ? 0.f : (a.act == kActLeaky ? 0.1f : 1.f);
     long long wait_full = 0, busy = 0;
@@ -403,50 +453,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
       const int s = ti % AS;
       const int t0 = tile * MT;
       long long tw = probe ? clock64() : 0;
-      mbar_wait(acc_full(s), (ti / AS) & 1);
+      mbar_wait_relaxed(acc_full(s), (ti / AS) & 1);
       tc_fence_after();
       long long tb = probe ? clock64() : 0;
       if (probe) wait_full += tb - tw;
+      if (head) {
+        // output heads (NT = 16 / 32): fp32 NCHW maps with the sigmoid scaling, optional 16-bit copy
+        constexpr int kItems = NACC * (NT / 16);
 #pragma unroll 1
-      for (int acc = 0; acc < NACC; ++acc) {
-        const int pos = t0 + acc * 128 + q * 32 + lane;
-        const PosInfo pi = locate(pos, a);
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + acc * NT);
-        if (head) {
-          // output heads (NT = 16 / 32): fp32 NCHW maps with the sigmoid scaling, optional 16-bit copy
-#pragma unroll 1
-          for (int j = half; j < NT / 16; j += 2) {
-            uint32_t r[16];
-            tmem_ld16(trow + (uint32_t)(j * 16), r);
-            tmem_ld_wait();
-            float v[8];
+        for (int it = sub; it < kItems; it += 4) {
+          const int acc = it / (NT / 16), j = it - acc * (NT / 16);
+          const int pos = t0 + acc * 128 + q * 32 + lane;
+          const PosInfo pi = locate(pos, a);
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + acc * NT + j * 16), r);
+          tmem_ld_wait();
+          float v[8];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < 2; ++h) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h * 8 + i]);
-              if (!(a.dbg & 2)) finish8(a, pos, pi, j * 16 + h * 8, v);
-            }
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h * 8 + i]);
+            if (!(dbg & 2)) finish8(a, pos, pi, j * 16 + h * 8, v);
           }
-        } else if constexpr (NT >= 32) {
+        }
+      } else if constexpr (NT >= 32) {
+        constexpr int kItems = NACC * (NT / 32);
 #pragma unroll 1
-          for (int j = half; j < NT / 32; j += 2) {
-            uint32_t r[32];
-            tmem_ld32(trow + (uint32_t)(j * 32), r);
-            const int plane = (j * 32) >> 3;
-            uint4 rs[4];
-            const bool has_res = a.res != nullptr && pi.interior;
-            if (has_res) {
+        for (int it = sub; it < kItems; it += 4) {
+          const int acc = it / (NT / 32), j = it - acc * (NT / 32);
+          const int pos = t0 + acc * 128 + q * 32 + lane;
+          const PosInfo pi = locate(pos, a);
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + acc * NT + j * 32), r);
+          const int plane = (j * 32) >> 3;
+          uint4 rs[4];
+          const bool has_res = a.res != nullptr && pi.interior;
+          if (has_res) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g)
-                rs[g] = *reinterpret_cast<const uint4*>(a.res + (long long)(plane + g) * a.res_plane_stride + (long long)pos * 8);
-            }
-            tmem_ld_wait();
-            if (pi.in_range && !(a.dbg & 2)) {
+            for (int g = 0; g < 4; ++g)
+              rs[g] = *reinterpret_cast<const uint4*>(a.res + (long long)(plane + g) * a.res_plane_stride + (long long)pos * 8);
+          }
+          tmem_ld_wait();
+          if (pi.in_range && !(dbg & 2)) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint4 o = finish8_fast(r + g * 8, s_shift + j * 32 + g * 8, has_res, rs[g], slope, pi.interior, a.fmt);
-                *reinterpret_cast<uint4*>(a.out + (long long)(plane + g) * a.out_plane_stride + (long long)pos * 8) = o;
-              }
+            for (int g = 0; g < 4; ++g) {
+              const uint4 o = finish8_fast(r + g * 8, s_shift + j * 32 + g * 8, has_res, rs[g], slope, pi.interior, a.fmt);
+              *reinterpret_cast<uint4*>(a.out + (long long)(plane + g) * a.out_plane_stride + (long long)pos * 8) = o;
             }
           }
         }
@@ -534,6 +586,8 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const StemArgs a) {
   const uint32_t tmem_base = s_tmem;
   const uint32_t idesc = umma_idesc(64, a.fmt);
   uint32_t phase = 0;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int pos = tile * 128 + tid;
     const int n = pos / (Hp * Wp), rem = pos - n * Hp * Wp;
@@ -608,6 +662,8 @@ __global__ void __launch_bounds__(128) pool_kernel(const PoolArgs a) {
   const int Ho = a.H / 2, Wo = a.W / 2, Hpo = Ho + 2, Wpo = Wo + 2, Wpi = a.W + 2, Hpi = a.H + 2;
   const int P = a.N * Hpo * Wpo;
   const int pos = blockIdx.x * 128 + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (pos >= P) return;
   const int g = blockIdx.y;
   const int n = pos / (Hpo * Wpo), rem = pos - n * Hpo * Wpo;
@@ -638,9 +694,20 @@ __global__ void __launch_bounds__(128) pool_kernel(const PoolArgs a) {
   *reinterpret_cast<uint4*>(a.out + (long long)g * a.out_plane_stride + (long long)pos * 8) = *reinterpret_cast<const uint4*>(ob);
 }
 
-template <int NT, int NACC, int TAPS, int BST>
+// launch configuration with programmatic stream serialization (PDL) enabled
+cudaLaunchAttribute g_pdl_attr[1];
+cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  g_pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  g_pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = g_pdl_attr; cfg.numAttrs = 1;
+  return cfg;
+}
+
+template <int NT, int NACC, int TAPS, int BST, bool BRES, bool DBG>
 int launch_tc_inst(const ConvArgs& a, size_t smem, cudaStream_t st) {
-  auto kern = conv_tc_kernel<NT, NACC, TAPS, BST>;
+  auto kern = conv_tc_kernel<NT, NACC, TAPS, BST, BRES, DBG>;
   POPNET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // ask for the full shared-memory carveout so that two CTAs can be co-resident where their tiles allow it
   POPNET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -648,17 +715,24 @@ int launch_tc_inst(const ConvArgs& a, size_t smem, cudaStream_t st) {
   if (a.cout_pad != NT) return POPNET_ERR_UNSUPPORTED;     // one N tile per layer (true for every rtpose layer)
   const int tiles = (a.P + MT - 1) / MT;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;        // persistent: one CTA per SM walks the tiles
-  kern<<<grid, kTcThreads, smem, st>>>(a);
+  cudaLaunchConfig_t cfg = pdl_config(dim3(grid), dim3(kTcThreads), smem, st);
+  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }
 
-template <int NT, int NACC, int TAPS>
+template <int NT, int NACC, int TAPS, bool BRES>
 int launch_tc_bst(const ConvArgs& a, int bst, size_t smem, cudaStream_t st) {
+  const bool dbgk = a.probe != nullptr || a.dbg != 0;
+  if (BRES) {
+    if (a.chunks != 1) return POPNET_ERR_UNSUPPORTED;
+    return dbgk ? launch_tc_inst<NT, NACC, TAPS, 2, BRES, true>(a, smem, st) : launch_tc_inst<NT, NACC, TAPS, 2, BRES, false>(a, smem, st);
+  }
+  if (dbgk) return launch_tc_inst<NT, NACC, TAPS, 4, BRES, true>(a, smem, st);      // bring-up: 4 stages only
   switch (bst) {
-    case 2: return launch_tc_inst<NT, NACC, TAPS, 2>(a, smem, st);
-    case 3: return launch_tc_inst<NT, NACC, TAPS, 3>(a, smem, st);
-    default: return launch_tc_inst<NT, NACC, TAPS, 4>(a, smem, st);
+    case 2: return launch_tc_inst<NT, NACC, TAPS, 2, BRES, false>(a, smem, st);
+    case 3: return launch_tc_inst<NT, NACC, TAPS, 3, BRES, false>(a, smem, st);
+    default: return launch_tc_inst<NT, NACC, TAPS, 4, BRES, false>(a, smem, st);
   }
 }
 
@@ -666,30 +740,42 @@ int launch_tc_bst(const ConvArgs& a, int bst, size_t smem, cudaStream_t st) {
 
 constexpr size_t kSmemLimit = 227 * 1024;
 
-size_t conv_tc_smem_bytes(int nt, int nacc, int taps, int a_stages, int Wp, int* b_stages_out) {
+size_t conv_tc_smem_bytes(int nt, int nacc, int taps, int a_stages, int Wp, int* b_stages_out, bool b_resident) {
   const int halo = taps == 9 ? Wp + 1 : 0;
   const size_t a_bytes = (((size_t)a_stages * 8 * (nacc * 128 + 2 * halo) * 16) + 127) & ~(size_t)127;
   const size_t b_stage = (size_t)8 * nt * 16;
+  const size_t misc = 256 + (size_t)nt * 4;
+  if (b_resident) {
+    if (b_stages_out) *b_stages_out = taps;
+    return a_bytes + taps * b_stage + misc;
+  }
   int bst = 4;
-  while (bst > 2 && a_bytes + bst * b_stage + 256 + (size_t)nt * 4 > kSmemLimit) --bst;
+  while (bst > 2 && a_bytes + bst * b_stage + misc > kSmemLimit) --bst;
   if (b_stages_out) *b_stages_out = bst;
-  return a_bytes + bst * b_stage + 256 + (size_t)nt * 4;
+  return a_bytes + bst * b_stage + misc;
 }
 
 int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st) {
   int bst = 0;
-  const size_t smem = conv_tc_smem_bytes(a.nt, nacc, a.taps, a.a_stages, a.Wp, &bst);
+  // weights resident in shared memory whenever the layer is a single chunk and everything fits
+  const bool bres = a.chunks == 1 && a.taps == 9 && a.nt == 64 &&
+                    conv_tc_smem_bytes(a.nt, nacc, a.taps, a.a_stages, a.Wp, nullptr, true) <= kSmemLimit;
+  const size_t smem = conv_tc_smem_bytes(a.nt, nacc, a.taps, a.a_stages, a.Wp, &bst, bres);
   if (smem > kSmemLimit) return POPNET_ERR_UNSUPPORTED;
-#define POPNET_TC_CASE(NT_, NACC_, TAPS_) \
-  if (a.nt == NT_ && nacc == NACC_ && a.taps == TAPS_) return launch_tc_bst<NT_, NACC_, TAPS_>(a, bst, smem, st);
-  POPNET_TC_CASE(64, 2, 9)
-  POPNET_TC_CASE(64, 4, 9)
-  POPNET_TC_CASE(128, 2, 9)
-  POPNET_TC_CASE(128, 4, 9)
-  POPNET_TC_CASE(128, 4, 1)
-  POPNET_TC_CASE(256, 2, 9)
-  POPNET_TC_CASE(32, 4, 1)
-  POPNET_TC_CASE(16, 4, 9)
+  if ((a.probe != nullptr || a.dbg != 0) && !bres && bst != 4) return POPNET_ERR_UNSUPPORTED;
+#define POPNET_TC_CASE(NT_, NACC_, TAPS_, BRES_) \
+  if (a.nt == NT_ && nacc == NACC_ && a.taps == TAPS_ && bres == BRES_) return launch_tc_bst<NT_, NACC_, TAPS_, BRES_>(a, bst, smem, st);
+  POPNET_TC_CASE(64, 2, 9, true)
+  POPNET_TC_CASE(64, 3, 9, true)
+  POPNET_TC_CASE(64, 4, 9, true)
+  POPNET_TC_CASE(64, 2, 9, false)
+  POPNET_TC_CASE(64, 4, 9, false)
+  POPNET_TC_CASE(128, 2, 9, false)
+  POPNET_TC_CASE(128, 4, 9, false)
+  POPNET_TC_CASE(128, 4, 1, false)
+  POPNET_TC_CASE(256, 2, 9, false)
+  POPNET_TC_CASE(32, 4, 1, false)
+  POPNET_TC_CASE(16, 4, 9, false)
 #undef POPNET_TC_CASE
   return POPNET_ERR_UNSUPPORTED;
 }
@@ -705,7 +791,8 @@ int launch_stem(const StemArgs& a, cudaStream_t st) {
   const int P = a.N * (a.H / 2 + 2) * (a.W / 2 + 2);
   const int tiles = (P + 127) / 128;
   const int grid = tiles < 148 * 6 ? tiles : 148 * 6;      // persistent: six CTAs per SM walk the tiles
-  stem_kernel<<<grid, kStemThreads, 0, st>>>(a);
+  cudaLaunchConfig_t cfg = pdl_config(dim3(grid), dim3(kStemThreads), 0, st);
+  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, stem_kernel, a));
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }
@@ -713,7 +800,8 @@ int launch_stem(const StemArgs& a, cudaStream_t st) {
 int launch_pool(const PoolArgs& a, cudaStream_t st) {
   const int P = a.N * (a.H / 2 + 2) * (a.W / 2 + 2);
   dim3 grid((P + 127) / 128, a.planes);
-  pool_kernel<<<grid, 128, 0, st>>>(a);
+  cudaLaunchConfig_t cfg = pdl_config(grid, dim3(128), 0, st);
+  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, pool_kernel, a));
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }

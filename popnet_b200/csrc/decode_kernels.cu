@@ -309,19 +309,37 @@ __global__ void __launch_bounds__(32) assemble_kernel(const float* __restrict__ 
   __shared__ int16_t s_pj[POPNET_MAX_PERSONS][POPNET_MAX_JOINTS];
   __shared__ double s_ps[POPNET_MAX_PERSONS];
   __shared__ int s_pc[POPNET_MAX_PERSONS];
+  // the frame's connection lists and peak scores, staged once (the assembly itself is a serial chain of
+  // dependent steps; it must not pay a global-memory round trip per step)
+  __shared__ int s_nc[POPNET_MAX_LIMBS], s_npk[POPNET_MAX_JOINTS];
+  __shared__ int16_t s_ci[POPNET_MAX_LIMBS][POPNET_MAX_PEAKS][2];
+  __shared__ double s_cs[POPNET_MAX_LIMBS][POPNET_MAX_PEAKS];
+  __shared__ float s_pk[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS];
   const int b = blockIdx.x, lane = threadIdx.x;
   const int K = p.num_joints, L = p.num_limbs, MP = p.max_peaks, MM = p.max_persons;
   const int H = p.grid_h, W = p.grid_w, cells = H * W;
   int np_ = 0;
   unsigned flags = 0;
+  if (lane < L) s_nc[lane] = o.conn_count[(size_t)b * L + lane];
+  if (lane < K) s_npk[lane] = o.peak_count[(size_t)b * K + lane];
+  __syncwarp();
+  for (int l = 0; l < L; ++l)
+    for (int i = lane; i < s_nc[l]; i += 32) {
+      const size_t slot = ((size_t)b * L + l) * MP + i;
+      s_ci[l][i][0] = o.conn_ij[slot * 2];
+      s_ci[l][i][1] = o.conn_ij[slot * 2 + 1];
+      s_cs[l][i] = o.conn_score[slot];
+    }
+  for (int k = 0; k < K; ++k)
+    for (int i = lane; i < s_npk[k]; i += 32) s_pk[k][i] = o.peak_score[((size_t)b * K + k) * MP + i];
+  __syncwarp();
 
   for (int l = 0; l < L; ++l) {
     const int ta = p.limbs[l][0], tb = p.limbs[l][1];
-    const int nc = o.conn_count[(size_t)b * L + l];
+    const int nc = s_nc[l];
     for (int c = 0; c < nc; ++c) {
-      const size_t slot = ((size_t)b * L + l) * MP + c;
-      const int ia = o.conn_ij[slot * 2], ib = o.conn_ij[slot * 2 + 1];
-      const double ls = o.conn_score[slot];
+      const int ia = s_ci[l][c][0], ib = s_ci[l][c][1];
+      const double ls = s_cs[l][c];
       // persons whose src or dst slot already holds this joint (paf_to_pose.py:285-287)
       unsigned long long hits = 0;
       for (int q0 = 0; q0 < np_; q0 += 32) {
@@ -330,7 +348,7 @@ __global__ void __launch_bounds__(32) assemble_kernel(const float* __restrict__ 
         hits |= (unsigned long long)__ballot_sync(kFull, h) << q0;
       }
       const int nh = __popcll(hits);
-      const double sb = (double)o.peak_score[((size_t)b * K + tb) * MP + ib];
+      const double sb = (double)s_pk[tb][ib];
       if (nh == 1) {
         const int q = __ffsll((long long)hits) - 1;
         if (lane == 0 && s_pj[q][tb] != ib) {
@@ -366,7 +384,7 @@ __global__ void __launch_bounds__(32) assemble_kernel(const float* __restrict__ 
         else {
           if (lane < POPNET_MAX_JOINTS) s_pj[np_][lane] = (lane == ta) ? (int16_t)ia : (lane == tb) ? (int16_t)ib : (int16_t)-1;
           if (lane == 0) {
-            const double sa = (double)o.peak_score[((size_t)b * K + ta) * MP + ia];
+            const double sa = (double)s_pk[ta][ia];
             s_pc[np_] = 2;
             s_ps[np_] = ((0 + sa) + sb) + ls;
           }

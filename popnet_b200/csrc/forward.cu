@@ -70,7 +70,7 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   for (int i = 0; i < kNumBufs; ++i) {
     Buf& b = p.bufs[i];
     b.P = batch * (b.H + 2) * (b.W + 2);
-    b.plane_stride = (long long)(kGuard + align_up((size_t)(batch > 0 ? b.P : 0), kPosRound) + kGuard) * 8;
+    b.plane_stride = (long long)(kGuard + align_up((size_t)(batch > 0 ? b.P : 0), kPosRound) + kPosSlack + kGuard) * 8;
     b.off = off;
     off += (size_t)(b.C / 8) * b.plane_stride;
     off = align_up(off, 128);
@@ -91,10 +91,10 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   p.layers.clear();
   // block0
   add(1, 64, 7, 64, 0, kActRelu, -1, 0, A112, 0, -1, 0, 0, 0);              // 0 conv1 (stem kernel)
-  add(64, 64, 3, 64, 4, kActRelu, A112, 0, B112, 0, -1, 0, 0, 0);           // 1 layer1.0.conv1
-  add(64, 64, 3, 64, 4, kActRelu, B112, 0, C112, 0, A112, 0, 0, 0);         // 2 layer1.0.conv2 (+x)
-  add(64, 64, 3, 64, 4, kActRelu, C112, 0, B112, 0, -1, 0, 0, 0);           // 3 layer1.1.conv1
-  add(64, 64, 3, 64, 4, kActRelu, B112, 0, A112, 0, C112, 0, 0, 0);         // 4 layer1.1.conv2 (+x)
+  add(64, 64, 3, 64, 3, kActRelu, A112, 0, B112, 0, -1, 0, 0, 0);           // 1 layer1.0.conv1
+  add(64, 64, 3, 64, 3, kActRelu, B112, 0, C112, 0, A112, 0, 0, 0);         // 2 layer1.0.conv2 (+x)
+  add(64, 64, 3, 64, 3, kActRelu, C112, 0, B112, 0, -1, 0, 0, 0);           // 3 layer1.1.conv1
+  add(64, 64, 3, 64, 3, kActRelu, B112, 0, A112, 0, C112, 0, 0, 0);         // 4 layer1.1.conv2 (+x)
   add(64, 128, 3, 128, 2, kActRelu, D56, 0, E56, 0, -1, 0, 0, 0);           // 5 layer2.0.conv1
   add(128, 128, 3, 128, 4, kActRelu, E56, 0, G56, 0, F56, 0, 0, 0);         // 6 layer2.0.conv2 (+downsample)
   add(64, 128, 1, 128, 4, kActNone, D56, 0, F56, 0, -1, 0, 0, 0);           // 7 layer2.0.downsample
@@ -279,7 +279,9 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     if (impl == POPNET_FWD_IMPL_SIMT) return launch_conv_simt(a, st);
     // shrink the A staging if the tile does not fit next to two B stages
     int bst = 0;
-    if (conv_tc_smem_bytes(a.nt, l.nacc, a.taps, a.a_stages, a.Wp, &bst) > 227 * 1024) a.a_stages = 1;
+    if (conv_tc_smem_bytes(a.nt, l.nacc, a.taps, a.a_stages, a.Wp, &bst, false) > 227 * 1024 &&
+        conv_tc_smem_bytes(a.nt, l.nacc, a.taps, a.a_stages, a.Wp, &bst, true) > 227 * 1024)
+      a.a_stages = 1;
     return launch_conv_tc(a, l.nacc, st);
   };
   auto run_pool = [&](int in_buf, int out_buf, int out_plane0) -> int {

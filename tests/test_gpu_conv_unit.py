@@ -27,7 +27,7 @@ def to_c8p(x):
     """[N,C,H,W] fp32 -> C8P bf16 planes [C/8, plane_len, 8] with zero ring (guards filled with NaN on purpose)."""
     N, Cc, H, W = x.shape
     P = N * (H + 2) * (W + 2)
-    plen = GUARD + (P + ROUND - 1) // ROUND * ROUND + GUARD
+    plen = GUARD + (P + ROUND - 1) // ROUND * ROUND + 512 + GUARD
     xp = torch.zeros((N, Cc, H + 2, W + 2), device=x.device)
     xp[:, :, 1:-1, 1:-1] = x
     planes = torch.full((Cc // 8, plen, 8), float("nan"), device=x.device, dtype=DT)
@@ -54,6 +54,8 @@ def pack_w(w, nt, cin_pad, cout_pad):
 CASES = [  # nt, nacc, taps, cin, cout, H, W, N, act, residual, head
     (64, 2, 9, 64, 64, 20, 24, 3, 1, True, False),
     (64, 4, 9, 128, 64, 12, 12, 5, 2, False, False),
+    (64, 3, 9, 64, 64, 20, 24, 7, 1, True, False),
+    (64, 4, 9, 64, 64, 12, 12, 9, 2, False, False),
     (128, 2, 9, 64, 128, 14, 10, 4, 1, False, False),
     (128, 4, 9, 192, 128, 12, 12, 5, 2, False, False),
     (128, 4, 1, 256, 128, 12, 12, 5, 2, False, False),

@@ -21,17 +21,17 @@ lib.popnet_debug_conv.restype = C.c_int
 lib.popnet_debug_conv.argtypes = [C.POINTER(DebugConv), C.c_void_p]
 
 # name, nt, nacc, taps, cin, cout, H
-LAYERS_ALL = [("64->64@112", 64, 2, 9, 64, 64, 112), ("64->64@112 acc4", 64, 4, 9, 64, 64, 112),
+LAYERS_ALL = [("64->64@112", 64, 2, 9, 64, 64, 112), ("64->64@112 acc3", 64, 3, 9, 64, 64, 112), ("64->64@112 acc4", 64, 4, 9, 64, 64, 112),
           ("64->128@56", 128, 2, 9, 64, 128, 56), ("64->128@56 acc4", 128, 4, 9, 64, 128, 56),
           ("128->128@56 acc2", 128, 2, 9, 128, 128, 56), ("128->128@28 acc2", 128, 2, 9, 128, 128, 28),
           ("128->128@56", 128, 4, 9, 128, 128, 56), ("1x1 128->128@56", 128, 4, 1, 128, 128, 56),
           ("256->256@28", 256, 2, 9, 256, 256, 28), ("128->128@28", 128, 4, 9, 128, 128, 28),
           ("64->64@28", 64, 4, 9, 64, 64, 28)]
-LAYERS = LAYERS_ALL
+LAYERS = [l for l in LAYERS_ALL if l[0] in ("64->64@112", "64->64@112 acc3", "64->64@28", "128->128@56", "256->256@28")]
 for name, nt, nacc, taps, cin, cout, H in LAYERS:
     N = a.batch
     P = N * (H + 2) * (H + 2)
-    plen = GUARD + (P + ROUND - 1) // ROUND * ROUND + GUARD
+    plen = GUARD + (P + ROUND - 1) // ROUND * ROUND + 512 + GUARD
     xin = (torch.randn((cin // 8, plen, 8), device="cuda") * 0.5).to(torch.bfloat16)
     k = 3 if taps == 9 else 1
     w = (torch.randn((cout // nt, taps, cin // 8, nt, 8), device="cuda") * 0.05).to(torch.bfloat16)
@@ -41,7 +41,7 @@ for name, nt, nacc, taps, cin, cout, H in LAYERS:
     ncta = (P + mt - 1) // mt
     probe = torch.zeros((ncta, 16), device="cuda", dtype=torch.int64)
     flops = 2.0 * N * H * H * cin * cout * taps
-    for dbg, label in ((0, "full"), (1, "no-mma"), (2, "no-epilogue")):
+    for dbg, label in ((0, "full"),):
         d = DebugConv(inp=xin[:, GUARD:].data_ptr(), in_plane_stride=plen * 8, w=w.data_ptr(), shift=shift.data_ptr(),
                       out=out[:, GUARD:].data_ptr(), out_plane_stride=plen * 8, res=None, res_plane_stride=0,
                       head_out=None, P=P, Hp=H + 2, Wp=H + 2, chunks=cin // 64, a_stages=2, act=1,
@@ -57,13 +57,13 @@ for name, nt, nacc, taps, cin, cout, H in LAYERS:
         torch.cuda.synchronize()
         t = e0.elapsed_time(e1) / 5 * 1e3
         print("%-18s %-18s %8.1f us  %7.1f TFLOP/s  (%d CTAs)" % (name, label, t, flops / t / 1e6, ncta))
-    d.dbg = 0
-    d.probe = probe.data_ptr()
-    lib.popnet_debug_conv(C.byref(d), None)
-    torch.cuda.synchronize()
-    pr = probe.cpu().numpy()
-    g = min(ncta, 148)
-    for cta in (0, g // 2, g - 1):
-        r = pr[cta]
-        print("   cta %4d: tiles %3d | mma thread: wait_a %7d wait_b %7d wait_acc %7d end +%7d | epilogue warp: wait %7d busy %7d "
-              "| lifetime %7d cycles" % (cta, r[9], r[3], r[4], r[10], r[5] - r[1], r[6], r[7], r[8] - r[0]))
+    for dbg in (0,):
+        d.dbg = dbg
+        d.probe = probe.data_ptr()
+        lib.popnet_debug_conv(C.byref(d), None)
+        torch.cuda.synchronize()
+        r = probe.cpu().numpy()[0]
+        nm = r[9] * nacc * 4 * taps * (cin // 64)
+        print("   dbg %2d cta 0: tiles %3d | mma thread: wait_a %7d wait_b %7d wait_acc %7d end +%7d (%.1f cyc/MMA net) | epilogue: "
+              "wait %7d busy %7d" % (dbg, r[9], r[3], r[4], r[10], r[5] - r[1], (r[5] - r[1] - r[3] - r[4] - r[10]) / max(nm, 1),
+                                     r[6], r[7]))

@@ -304,150 +304,180 @@ __device__ __forceinline__ float sum_pairwise_f32(const float* a, int n) {
   return r;
 }
 
-__global__ void __launch_bounds__(32) assemble_kernel(const float* __restrict__ heat, const float* __restrict__ depth,
-                                                      PopnetDecodeParams p, PopnetDecodeOut o) {
+constexpr int kAsmThreads = 128;
+
+__global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const float* __restrict__ heat, const float* __restrict__ depth,
+                                                               PopnetDecodeParams p, PopnetDecodeOut o) {
   __shared__ int16_t s_pj[POPNET_MAX_PERSONS][POPNET_MAX_JOINTS];
   __shared__ double s_ps[POPNET_MAX_PERSONS];
   __shared__ int s_pc[POPNET_MAX_PERSONS];
-  // the frame's connection lists and peak scores, staged once (the assembly itself is a serial chain of
-  // dependent steps; it must not pay a global-memory round trip per step)
+  // the frame's connection lists and peaks, staged once by the whole CTA (the assembly itself is a serial chain
+  // of dependent steps; it must not pay a global-memory round trip per step)
   __shared__ int s_nc[POPNET_MAX_LIMBS], s_npk[POPNET_MAX_JOINTS];
   __shared__ int16_t s_ci[POPNET_MAX_LIMBS][POPNET_MAX_PEAKS][2];
   __shared__ double s_cs[POPNET_MAX_LIMBS][POPNET_MAX_PEAKS];
   __shared__ float s_pk[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS];
-  const int b = blockIdx.x, lane = threadIdx.x;
+  __shared__ int16_t s_xy[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS][2];
+  __shared__ int s_keep[POPNET_MAX_PERSONS];
+  __shared__ int s_nout;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = p.num_joints, L = p.num_limbs, MP = p.max_peaks, MM = p.max_persons;
   const int H = p.grid_h, W = p.grid_w, cells = H * W;
-  int np_ = 0;
-  unsigned flags = 0;
-  if (lane < L) s_nc[lane] = o.conn_count[(size_t)b * L + lane];
-  if (lane < K) s_npk[lane] = o.peak_count[(size_t)b * K + lane];
-  __syncwarp();
-  for (int l = 0; l < L; ++l)
-    for (int i = lane; i < s_nc[l]; i += 32) {
-      const size_t slot = ((size_t)b * L + l) * MP + i;
-      s_ci[l][i][0] = o.conn_ij[slot * 2];
-      s_ci[l][i][1] = o.conn_ij[slot * 2 + 1];
-      s_cs[l][i] = o.conn_score[slot];
-    }
-  for (int k = 0; k < K; ++k)
-    for (int i = lane; i < s_npk[k]; i += 32) s_pk[k][i] = o.peak_score[((size_t)b * K + k) * MP + i];
-  __syncwarp();
-
-  for (int l = 0; l < L; ++l) {
-    const int ta = p.limbs[l][0], tb = p.limbs[l][1];
-    const int nc = s_nc[l];
-    for (int c = 0; c < nc; ++c) {
-      const int ia = s_ci[l][c][0], ib = s_ci[l][c][1];
-      const double ls = s_cs[l][c];
-      // persons whose src or dst slot already holds this joint (paf_to_pose.py:285-287)
-      unsigned long long hits = 0;
-      for (int q0 = 0; q0 < np_; q0 += 32) {
-        const int q = q0 + lane;
-        const bool h = q < np_ && (s_pj[q][ta] == ia || s_pj[q][tb] == ib);
-        hits |= (unsigned long long)__ballot_sync(kFull, h) << q0;
-      }
-      const int nh = __popcll(hits);
-      const double sb = (double)s_pk[tb][ib];
-      if (nh == 1) {
-        const int q = __ffsll((long long)hits) - 1;
-        if (lane == 0 && s_pj[q][tb] != ib) {
-          s_pj[q][tb] = (int16_t)ib;
-          s_pc[q] += 1;
-          s_ps[q] += sb + ls;
-        }
-      } else if (nh == 2) {
-        const int q1 = __ffsll((long long)hits) - 1;
-        const int q2 = __ffsll((long long)(hits & (hits - 1))) - 1;
-        const bool ov = lane < K && s_pj[q1][lane] >= 0 && s_pj[q2][lane] >= 0;
-        if (!__any_sync(kFull, ov)) {
-          if (lane < K) s_pj[q1][lane] = (int16_t)(s_pj[q1][lane] + s_pj[q2][lane] + 1);
-          if (lane == 0) {
-            s_ps[q1] += s_ps[q2];
-            s_pc[q1] += s_pc[q2];
-            s_ps[q1] += ls;
-          }
-          __syncwarp();
-          for (int q = q2; q + 1 < np_; ++q) {        // list.pop(q2): later persons move up
-            if (lane < K) s_pj[q][lane] = s_pj[q + 1][lane];
-            if (lane == 0) { s_ps[q] = s_ps[q + 1]; s_pc[q] = s_pc[q + 1]; }
-            __syncwarp();
-          }
-          --np_;
-        } else if (lane == 0) {
-          s_pj[q1][tb] = (int16_t)ib;
-          s_pc[q1] += 1;
-          s_ps[q1] += sb + ls;
-        }
-      } else {                                          // 0 or >= 3 matches: a new person
-        if (np_ >= MM) flags |= POPNET_FLAG_PERSON_OVERFLOW;
-        else {
-          if (lane < POPNET_MAX_JOINTS) s_pj[np_][lane] = (lane == ta) ? (int16_t)ia : (lane == tb) ? (int16_t)ib : (int16_t)-1;
-          if (lane == 0) {
-            const double sa = (double)s_pk[ta][ia];
-            s_pc[np_] = 2;
-            s_ps[np_] = ((0 + sa) + sb) + ls;
-          }
-          ++np_;
-        }
-      }
-      __syncwarp();
+  if (tid < L) s_nc[tid] = o.conn_count[(size_t)b * L + tid];
+  if (tid >= 32 && tid - 32 < K) s_npk[tid - 32] = o.peak_count[(size_t)b * K + tid - 32];
+  __syncthreads();
+  for (int i = tid; i < L * MP; i += kAsmThreads) {
+    const int l = i / MP, c = i - l * MP;
+    if (c < s_nc[l]) {
+      const size_t slot = ((size_t)b * L + l) * MP + c;
+      s_ci[l][c][0] = o.conn_ij[slot * 2];
+      s_ci[l][c][1] = o.conn_ij[slot * 2 + 1];
+      s_cs[l][c] = o.conn_score[slot];
     }
   }
-
-  int nout = 0;
-  for (int q = 0; q < np_; ++q) {
-    const double cnt = (double)s_pc[q], sc = s_ps[q];
-    if (cnt < 3 || sc / cnt < 0.2) continue;            // paf_to_pose.py:338-346
-    const size_t row = (size_t)b * MM + nout;
-    if (lane == 0) {
-      if (o.person_score) o.person_score[row] = sc;
-      if (o.person_njoint) o.person_njoint[row] = s_pc[q];
+  for (int i = tid; i < K * MP; i += kAsmThreads) {
+    const int k = i / MP, c = i - k * MP;
+    if (c < s_npk[k]) {
+      const size_t ps = ((size_t)b * K + k) * MP + c;
+      s_pk[k][c] = o.peak_score[ps];
+      s_xy[k][c][0] = o.peak_xy[ps * 2];
+      s_xy[k][c][1] = o.peak_xy[ps * 2 + 1];
     }
-    if (lane < K) {
-      const int k = lane, idx = s_pj[q][k];
-      if (o.person_peak) o.person_peak[row * K + k] = (int16_t)idx;
-      double x2 = -1, y2 = -1, Z = -1, conf = 0;
-      if (idx >= 0) {
-        const size_t ps = ((size_t)b * K + k) * MP + idx;
-        const int X = o.peak_xy[ps * 2], Y = o.peak_xy[ps * 2 + 1];
-        conf = (double)o.peak_score[ps];
-        if (depth) {                                     // common.py:272-293, fp32, NumPy pairwise order
-          const int cx = X / p.stride, cy = Y / p.stride;
-          const int x0 = clampi(cx - 1, 0, W - 1), x1 = clampi(cx + 1, 0, W - 1);
-          const int y0 = clampi(cy - 1, 0, H - 1), y1 = clampi(cy + 1, 0, H - 1);
-          const float* hm = heat + ((size_t)b * (K + 1) + k) * cells;
-          const float* dm = depth + ((size_t)b * K + k) * cells;
-          float wv[9], dv[9];
-          int n = 0;
-          for (int yy = y0; yy <= y1; ++yy)
-            for (int xx = x0; xx <= x1; ++xx) {
-              float hv = hm[yy * W + xx];
-              if (hv < 0) hv = 0;
-              const float w = hv + 0.000000001f;
-              float d = dm[yy * W + xx] * p.depth_std;
-              d = d + p.depth_mean;
-              wv[n] = w; dv[n] = d * w; ++n;
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ---- D5: serial assembly by one warp (paf_to_pose.py:267-351)
+    int np_ = 0;
+    unsigned flags = 0;
+    for (int l = 0; l < L; ++l) {
+      const int ta = p.limbs[l][0], tb = p.limbs[l][1];
+      const int nc = s_nc[l];
+      for (int c = 0; c < nc; ++c) {
+        const int ia = s_ci[l][c][0], ib = s_ci[l][c][1];
+        const double ls = s_cs[l][c];
+        // persons whose src or dst slot already holds this joint (paf_to_pose.py:285-287)
+        unsigned long long hits = 0;
+        for (int q0 = 0; q0 < np_; q0 += 32) {
+          const int q = q0 + lane;
+          const bool h = q < np_ && (s_pj[q][ta] == ia || s_pj[q][tb] == ib);
+          hits |= (unsigned long long)__ballot_sync(kFull, h) << q0;
+        }
+        const int nh = __popcll(hits);
+        const double sb = (double)s_pk[tb][ib];
+        if (nh == 1) {
+          const int q = __ffsll((long long)hits) - 1;
+          if (lane == 0 && s_pj[q][tb] != ib) {
+            s_pj[q][tb] = (int16_t)ib;
+            s_pc[q] += 1;
+            s_ps[q] += sb + ls;
+          }
+        } else if (nh == 2) {
+          const int q1 = __ffsll((long long)hits) - 1;
+          const int q2 = __ffsll((long long)(hits & (hits - 1))) - 1;
+          const bool ov = lane < K && s_pj[q1][lane] >= 0 && s_pj[q2][lane] >= 0;
+          if (!__any_sync(kFull, ov)) {
+            if (lane < K) s_pj[q1][lane] = (int16_t)(s_pj[q1][lane] + s_pj[q2][lane] + 1);
+            if (lane == 0) {
+              s_ps[q1] += s_ps[q2];
+              s_pc[q1] += s_pc[q2];
+              s_ps[q1] += ls;
             }
-          Z = (double)(sum_pairwise_f32(dv, n) / sum_pairwise_f32(wv, n));
+            __syncwarp();
+            for (int q = q2; q + 1 < np_; ++q) {        // list.pop(q2): later persons move up
+              if (lane < K) s_pj[q][lane] = s_pj[q + 1][lane];
+              if (lane == 0) { s_ps[q] = s_ps[q + 1]; s_pc[q] = s_pc[q + 1]; }
+              __syncwarp();
+            }
+            --np_;
+          } else if (lane == 0) {
+            s_pj[q1][tb] = (int16_t)ib;
+            s_pc[q1] += 1;
+            s_ps[q1] += sb + ls;
+          }
+        } else {                                          // 0 or >= 3 matches: a new person
+          if (np_ >= MM) flags |= POPNET_FLAG_PERSON_OVERFLOW;
+          else {
+            if (lane < POPNET_MAX_JOINTS) s_pj[np_][lane] = (lane == ta) ? (int16_t)ia : (lane == tb) ? (int16_t)ib : (int16_t)-1;
+            if (lane == 0) {
+              const double sa = (double)s_pk[ta][ia];
+              s_pc[np_] = 2;
+              s_ps[np_] = ((0 + sa) + sb) + ls;
+            }
+            ++np_;
+          }
         }
-        x2 = (double)X / p.input_size * p.w_org;
-        y2 = (double)Y / p.input_size * p.h_org;
-      }
-      if (o.pose2d) { o.pose2d[(row * K + k) * 2] = x2; o.pose2d[(row * K + k) * 2 + 1] = y2; }
-      if (o.pose_conf) o.pose_conf[row * K + k] = conf;
-      if (o.pose3d && depth) {
-        double X3 = (x2 - p.cx) * Z / p.fx, Y3 = (y2 - p.cy) * Z / p.fy;
-        if (p.flip_y) Y3 = -Y3;
-        double* d3 = o.pose3d + (row * K + k) * 3;
-        d3[0] = X3; d3[1] = Y3; d3[2] = Z;
+        __syncwarp();
       }
     }
-    ++nout;
+    // prune (paf_to_pose.py:338-346): ordered compaction of the survivors
+    int nout = 0;
+    for (int q0 = 0; q0 < np_; q0 += 32) {
+      const int q = q0 + lane;
+      bool keep = false;
+      if (q < np_) {
+        const double cnt = (double)s_pc[q], sc = s_ps[q];
+        keep = !(cnt < 3 || sc / cnt < 0.2);
+      }
+      const unsigned bal = __ballot_sync(kFull, keep);
+      if (keep) s_keep[nout + __popc(bal & ((1u << lane) - 1u))] = q;
+      nout += __popc(bal);
+    }
+    if (lane == 0) {
+      s_nout = nout;
+      o.n_person[b] = nout;
+      if (flags) atomicOr(o.flags + b, flags);
+    }
   }
-  if (lane == 0) {
-    o.n_person[b] = nout;
-    if (flags) atomicOr(o.flags + b, flags);
+  __syncthreads();
+
+  // ---- D7..D9: every (surviving person, joint) pair is independent -> whole CTA
+  const int nout = s_nout;
+  for (int i = tid; i < nout; i += kAsmThreads) {
+    const size_t row = (size_t)b * MM + i;
+    const int q = s_keep[i];
+    if (o.person_score) o.person_score[row] = s_ps[q];
+    if (o.person_njoint) o.person_njoint[row] = s_pc[q];
+  }
+  for (int i = tid; i < nout * K; i += kAsmThreads) {
+    const int pi_ = i / K, k = i - pi_ * K;
+    const int q = s_keep[pi_], idx = s_pj[q][k];
+    const size_t row = (size_t)b * MM + pi_;
+    if (o.person_peak) o.person_peak[row * K + k] = (int16_t)idx;
+    double x2 = -1, y2 = -1, Z = -1, conf = 0;
+    if (idx >= 0) {
+      const int X = s_xy[k][idx][0], Y = s_xy[k][idx][1];
+      conf = (double)s_pk[k][idx];
+      if (depth) {                                     // common.py:272-293, fp32, NumPy pairwise order
+        const int cx = X / p.stride, cy = Y / p.stride;
+        const int x0 = clampi(cx - 1, 0, W - 1), x1 = clampi(cx + 1, 0, W - 1);
+        const int y0 = clampi(cy - 1, 0, H - 1), y1 = clampi(cy + 1, 0, H - 1);
+        const float* hm = heat + ((size_t)b * (K + 1) + k) * cells;
+        const float* dm = depth + ((size_t)b * K + k) * cells;
+        float wv[9], dv[9];
+        int n = 0;
+        for (int yy = y0; yy <= y1; ++yy)
+          for (int xx = x0; xx <= x1; ++xx) {
+            float hv = hm[yy * W + xx];
+            if (hv < 0) hv = 0;
+            const float w = hv + 0.000000001f;
+            float d = dm[yy * W + xx] * p.depth_std;
+            d = d + p.depth_mean;
+            wv[n] = w; dv[n] = d * w; ++n;
+          }
+        Z = (double)(sum_pairwise_f32(dv, n) / sum_pairwise_f32(wv, n));
+      }
+      x2 = (double)X / p.input_size * p.w_org;
+      y2 = (double)Y / p.input_size * p.h_org;
+    }
+    if (o.pose2d) { o.pose2d[(row * K + k) * 2] = x2; o.pose2d[(row * K + k) * 2 + 1] = y2; }
+    if (o.pose_conf) o.pose_conf[row * K + k] = conf;
+    if (o.pose3d && depth) {
+      double X3 = (x2 - p.cx) * Z / p.fx, Y3 = (y2 - p.cy) * Z / p.fy;
+      if (p.flip_y) Y3 = -Y3;
+      double* d3 = o.pose3d + (row * K + k) * 3;
+      d3[0] = X3; d3[1] = Y3; d3[2] = Z;
+    }
   }
 }
 
@@ -506,7 +536,7 @@ extern "C" int popnet_decode(const float* heat, const float* paf, const float* d
   POPNET_AFTER_LAUNCH();
   limbs_kernel<<<dim3(p->num_limbs, batch), kThreads, smem_limbs, st>>>(paf, *p, *o);
   POPNET_AFTER_LAUNCH();
-  assemble_kernel<<<batch, 32, 0, st>>>(heat, depth, *p, *o);
+  assemble_kernel<<<batch, kAsmThreads, 0, st>>>(heat, depth, *p, *o);
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }

@@ -27,7 +27,7 @@ LAYERS_ALL = [("64->64@112", 64, 2, 9, 64, 64, 112), ("64->64@112 acc3", 64, 3, 
           ("128->128@56", 128, 4, 9, 128, 128, 56), ("1x1 128->128@56", 128, 4, 1, 128, 128, 56),
           ("256->256@28", 256, 2, 9, 256, 256, 28), ("128->128@28", 128, 4, 9, 128, 128, 28),
           ("64->64@28", 64, 4, 9, 64, 64, 28)]
-LAYERS = [l for l in LAYERS_ALL if l[0] in ("64->64@112", "64->64@112 acc3", "64->64@28", "128->128@56", "256->256@28")]
+LAYERS = [l for l in LAYERS_ALL if l[0] in ("64->64@112 acc3", "128->128@56", "128->128@56 acc2", "128->128@28", "128->128@28 acc2", "64->128@56", "64->128@56 acc4", "256->256@28")]
 for name, nt, nacc, taps, cin, cout, H in LAYERS:
     N = a.batch
     P = N * (H + 2) * (H + 2)

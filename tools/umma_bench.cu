@@ -59,9 +59,12 @@ __global__ void bench(int M, int N, int nacc, int layout_a, int layout_b, int a_
 #pragma unroll 1
     for (int i = 0; i < iters / 16; ++i) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        umma(dt[j], da[j], db[j], idesc, 1);
-        if (commit_every && ((j + 1) % commit_every) == 0) commit(smem_u32(&bar2[(j / commit_every) & 3]));
+      for (int j = 0; j < 16; ++j) umma(dt[j], da[j], db[j], idesc, 1);
+      if (commit_every > 0) {                      // idle gap of `commit_every` cycles after each group of 16 MMAs
+        const long long t = clock64();
+        while (clock64() - t < commit_every) {}
+      } else if (commit_every < 0) {
+        commit(smem_u32(&bar2[i & 3]));            // one commit per 16 MMAs
       }
     }
     commit(smem_u32(&bar));
@@ -81,17 +84,17 @@ int main() {
   const int iters = 2048;
   printf("%4s %4s %4s %3s %3s %5s %5s | cycles/MMA (1 CTA)   cycles/MMA (148 CTAs)  ideal\n", "M", "N", "nacc", "lA", "lB", "a_off", "same");
   for (int N : {64, 128, 256})
-    for (int nacc : {4})
-      for (int ce : {0, 16, 8, 4, 1}) {
-        if (nacc * N > 512) nacc = 512 / N;
-        long long h[148];
-        bench<<<148, 128, 200 * 1024>>>(128, N, nacc, 0, 0, 0, iters, 0, out, ce);
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
-        cudaMemcpy(h, out, 148 * 8, cudaMemcpyDeviceToHost);
-        long long mx = 0;
-        for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
-        printf("N %3d nacc %d commit_every %2d : %.1f cycles/MMA\n", N, nacc, ce, (double)mx / iters);
-      }
+    for (int gap : {0, -1, 100, 200, 400, 800, 1600}) {
+      int nacc = 512 / N > 4 ? 4 : 512 / N;
+      long long h[148];
+      bench<<<148, 128, 200 * 1024>>>(128, N, nacc, 0, 0, 0, iters, 0, out, gap);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+      cudaMemcpy(h, out, 148 * 8, cudaMemcpyDeviceToHost);
+      long long mx = 0;
+      for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+      printf("N %3d nacc %d gap %5d cycles per 16 MMAs (-1 = one commit): %.1f cycles/MMA  (%.0f cycles per group)\n", N, nacc, gap,
+             (double)mx / iters, (double)mx / iters * 16);
+    }
   return 0;
 }

@@ -117,6 +117,13 @@ typedef struct PopnetDecodeOut {
 POPNET_API int popnet_decode(const float* heat, const float* paf, const float* depth, int batch,
                   const PopnetDecodeParams* params_host, const PopnetDecodeOut* out_host, void* stream);
 
+/* retrieve_depth_heat_weighted(center, depthmap, heatmap, radius=1)   lib/utils/common.py:272-293, for n query points:
+ * queries [n][3] = (map plane index, cx, cy) in grid cells; heat / depth are stacks of [grid_h][grid_w] fp32 planes;
+ * out_z[i] = sum(d*w)/sum(w) over the clipped 3x3 window, w = max(heat,0)+1e-9, d = depth*std+mean, fp32 in NumPy's
+ * pairwise order (pass mean 0, std 1 for maps that are already de-normalised, like the reference's call site). */
+POPNET_API int popnet_lift_depth(const float* heat, const float* depth, const int32_t* queries, int n, int grid_h, int grid_w,
+                                 float depth_mean, float depth_std, float* out_z, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Evaluator.  Ragged lists-of-lists are CSR-packed by the host: humans of frame f are rows
  * off[f] .. off[f+1]-1; a human is K joints of D doubles; a missing joint is (-1, -1).

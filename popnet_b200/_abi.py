@@ -79,6 +79,7 @@ PROTOTYPES = {
     "popnet_last_cuda_error": (C.c_int, []),
     "popnet_launch_count": (C.c_longlong, []),
     "popnet_decode": (C.c_int, [vp, vp, vp, C.c_int, C.POINTER(DecodeParams), C.POINTER(DecodeOut), vp]),
+    "popnet_lift_depth": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp]),
     "popnet_eval_pck": (C.c_int, [C.POINTER(PckArgs), vp]),
     "popnet_eval_map_assign": (C.c_int, [C.POINTER(MapArgs), vp]),
     "popnet_num_conv_layers": (C.c_int, [C.POINTER(NetConfig)]),

@@ -112,3 +112,22 @@ class CudaBackend:
         res = {k: v.cpu().numpy() for k, v in out.items()}
         res["flags"] = res["flags"].view(np.uint32)
         return res
+
+    def lift_depth(self, heat, depth, queries, depth_mean=0.0, depth_std=1.0):
+        """heat/depth: [planes, gh, gw] fp32; queries [n,3] int32 (plane, cx, cy) -> fp32 [n] (NumPy)."""
+        h, d = _to_dev(heat, torch.float32), _to_dev(depth, torch.float32)
+        q = _to_dev(np.ascontiguousarray(queries, np.int32))
+        n = q.shape[0]
+        out = torch.empty((n,), dtype=torch.float32, device="cuda")
+        _lib.check(self.lib.popnet_lift_depth(_ptr(h), _ptr(d), _ptr(q), n, h.shape[-2], h.shape[-1], float(depth_mean),
+                                              float(depth_std), _ptr(out), _stream()), "popnet_lift_depth")
+        return out.cpu().numpy()
+
+    def preprocess_depth(self, frames, dst_hw, depth_max, depth_mean, depth_std):
+        """frames [B, H, W] fp32 metres (NumPy or CUDA) -> CUDA tensor [B, 1, dst_h, dst_w], normalised."""
+        src = _to_dev(frames, torch.float32)
+        B, H, W = src.shape
+        dst = torch.empty((B, 1, dst_hw[0], dst_hw[1]), dtype=torch.float32, device="cuda")
+        _lib.check(self.lib.popnet_preprocess_depth(_ptr(src), B, H, W, _ptr(dst), dst_hw[0], dst_hw[1], float(depth_max),
+                                                    float(depth_mean), float(depth_std), _stream()), "popnet_preprocess_depth")
+        return dst

@@ -74,6 +74,18 @@ def paf_to_human_list(joint_list, person_to_joint_assoc):
     return humans, visibility, conf_vec
 
 
+def retrieve_depth_heat_weighted(center, depthmap, heatmap, radius=1):
+    """lib/utils/common.py:272-293: heat-weighted depth in the clipped 3x3 window around ``center`` = (x, y) grid cell.
+    ``depthmap`` / ``heatmap`` are single [gh, gw] fp32 maps (already de-normalised depth, as at the reference's call
+    site, ...mpreal_ablation.py:212-215).  Returns np.float32.  (The batched decode does this on the device for every
+    assembled joint; this entry point exists for callers that use the helper on its own.)"""
+    if radius != 1:
+        raise NotImplementedError("only radius=1 (the value every reference call site uses) is implemented on the device")
+    z = _get_backend().lift_depth(np.asarray(heatmap, np.float32)[None], np.asarray(depthmap, np.float32)[None],
+                                  np.array([[0, int(center[0]), int(center[1])]], np.int32))
+    return np.float32(z[0])
+
+
 def _raise_on_overflow(flags):
     bad = np.nonzero(np.asarray(flags))[0]
     if len(bad):

@@ -1,0 +1,60 @@
+"""GPU tests of the "next" rows: device preprocessing, the stand-alone depth lift helper and the JSON wire
+formats driving the evaluator."""
+import json
+
+import numpy as np
+import pytest
+
+from popnet_b200 import synth
+from popnet_b200.topology import ITOP, MP3DHP
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("cam,shape", [(MP3DHP, (512, 480)), (ITOP, (240, 320))], ids=["mp3dhp", "itop"])
+def test_preprocess_matches_opencv(cam, shape, cuda_backend):
+    cv2 = pytest.importorskip("cv2")
+    from popnet_b200 import preprocess
+    rng = np.random.default_rng(0)
+    raw = rng.uniform(0.0, cam.depth_max + 1.0, (3,) + shape).astype(np.float32)
+    raw[rng.random(raw.shape) < 0.04] = 0.0
+    got = preprocess.preprocess_depth(raw, cam, 224).cpu().numpy()
+    prev = cv2.ipp.useIPP()
+    try:
+        cv2.ipp.setUseIPP(False)          # OpenCV's own C++ bilinear path
+        for b in range(3):
+            img = cv2.resize(raw[b], (224, 224), interpolation=cv2.INTER_LINEAR)
+            want = ((np.clip(img, 0, cam.depth_max) - cam.depth_mean) / cam.depth_std).astype(np.float32)
+            assert np.abs(got[b, 0] - want).max() <= 2e-6
+    finally:
+        cv2.ipp.setUseIPP(prev)
+
+
+def test_retrieve_depth_heat_weighted_matches_oracle(cuda_backend):
+    from oracle import decode_np
+    from popnet_b200.decode import retrieve_depth_heat_weighted
+    rng = np.random.default_rng(1)
+    heat = rng.random((28, 28), dtype=np.float32)
+    depth = (rng.random((28, 28), dtype=np.float32) * 4 + 1).astype(np.float32)
+    for c in [(0, 0), (27, 27), (0, 13), (5, 27), (12, 9)]:
+        got = retrieve_depth_heat_weighted(c, depth, heat, radius=1)
+        want = decode_np.retrieve_depth_heat_weighted(c, depth, heat, 1)
+        assert got == want, (c, got, want)
+
+
+def test_json_wire_formats_round_trip(tmp_path, cuda_backend):
+    from popnet_b200 import io as pio
+    ds = synth.eval_set(60, seed=21)
+    labels = {"intrinsics": {"fx": MP3DHP.fx}}
+    for i, (g2, g3) in enumerate(zip(ds["gt2d"], ds["gt3d"])):
+        labels["%06d" % i] = [{"2d_joints": a, "3d_joints": b} for a, b in zip(g2, g3)]
+    res = {"human_pred_set_2d": ds["pred2d"], "human_pred_set_3d": ds["pred3d"], "human_pred_set_part_conf": ds["conf"]}
+    lp, rp = tmp_path / "labels.json", tmp_path / "results.json"
+    lp.write_text(json.dumps(labels))
+    rp.write_text(json.dumps(res))
+    out = pio.evaluate_mp_human_3d(str(lp), str(rp))
+    # same numbers as calling the evaluator directly on the lists
+    from popnet_b200 import evaluate as E
+    _, k2 = E.eval_human_dataset_2d_PCKh(ds["pred2d"], ds["gt2d"], 0, 1, 15, 0.5, 0.5)
+    assert np.array_equal(np.asarray(out["pckh_2d"]), np.asarray(k2))
+    assert 0.0 < out["overall"]["pckh_2d"] <= 1.0 and 0.0 < out["overall"]["map_3d"] <= 100.0

@@ -184,14 +184,14 @@ def run_ours(args, rank, local_rank, world):
         if evs is not None:
             evs[2].record()
         if world > 1:
-            out = pipeline.gather_records(out)
+            return pipeline.gather_records(out, unpack=False)     # one NCCL all-gather of the packed record bytes
         return out
 
     def step_e2e(i):
         est.inject = dev_maps[i % R]
         rec = est.infer(host_frames[i % R])
         if world > 1:
-            rec = pipeline.gather_records({k: est._out[k] for k in pipeline.RECORD_KEYS})
+            pipeline.gather_records(est._out, unpack=False)
         return rec
 
     # ---- value leg

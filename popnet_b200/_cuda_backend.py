@@ -37,18 +37,47 @@ def _to_dev(a, dtype=None):
     return t.cuda()
 
 
+_FIELDS = (  # name, dtype, shape suffix builder -- 8-byte fields first so every view stays aligned
+    ("conn_score", torch.float64, lambda K, L, P, M: (L, P)),
+    ("person_score", torch.float64, lambda K, L, P, M: (M,)),
+    ("pose2d", torch.float64, lambda K, L, P, M: (M, K, 2)),
+    ("pose3d", torch.float64, lambda K, L, P, M: (M, K, 3)),
+    ("pose_conf", torch.float64, lambda K, L, P, M: (M, K)),
+    ("peak_count", torch.int32, lambda K, L, P, M: (K,)),
+    ("peak_score", torch.float32, lambda K, L, P, M: (K, P)),
+    ("conn_count", torch.int32, lambda K, L, P, M: (L,)),
+    ("n_person", torch.int32, lambda K, L, P, M: ()),
+    ("person_njoint", torch.int32, lambda K, L, P, M: (M,)),
+    ("flags", torch.int32, lambda K, L, P, M: ()),
+    ("peak_xy", torch.int16, lambda K, L, P, M: (K, P, 2)),
+    ("conn_ij", torch.int16, lambda K, L, P, M: (L, P, 2)),
+    ("person_peak", torch.int16, lambda K, L, P, M: (M, K)),
+)
+#: the fields that leave the device / cross the NVLink fabric, laid out contiguously at the END of the buffer
+RECORD_FIELDS = ("person_score", "pose2d", "pose3d", "pose_conf", "n_person", "person_njoint", "flags", "person_peak")
+
+
 def alloc_decode_out(B, params, device="cuda"):
+    """All decode outputs of a batch live in ONE device buffer (field-major: [field][B][...]); the pose-record fields
+    sit contiguously at its end so that the multi-GPU all-gather (and the D2H copy) is a single transfer of
+    ``out["_records"]`` without any packing kernel."""
     K, L, P, M = params.num_joints, params.num_limbs, params.max_peaks, params.max_persons
-    z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
-    return {
-        "peak_count": z((B, K), torch.int32), "peak_xy": z((B, K, P, 2), torch.int16),
-        "peak_score": z((B, K, P), torch.float32), "conn_count": z((B, L), torch.int32),
-        "conn_ij": z((B, L, P, 2), torch.int16), "conn_score": z((B, L, P), torch.float64),
-        "n_person": z((B,), torch.int32), "person_peak": z((B, M, K), torch.int16),
-        "person_score": z((B, M), torch.float64), "person_njoint": z((B, M), torch.int32),
-        "pose2d": z((B, M, K, 2), torch.float64), "pose3d": z((B, M, K, 3), torch.float64),
-        "pose_conf": z((B, M, K), torch.float64), "flags": z((B,), torch.int32),
-    }
+    order = [f for f in _FIELDS if f[0] not in RECORD_FIELDS] + [f for f in _FIELDS if f[0] in RECORD_FIELDS]
+    sizes, off = [], 0
+    rec_start = None
+    for name, dt, shp in order:
+        if name in RECORD_FIELDS and rec_start is None:
+            off = (off + 15) // 16 * 16
+            rec_start = off
+        n = B * int(np.prod(shp(K, L, P, M), dtype=np.int64)) * torch.empty((), dtype=dt).element_size()
+        sizes.append((name, dt, shp(K, L, P, M), off, n))
+        off = (off + n + 7) // 8 * 8
+    buf = torch.zeros(off, dtype=torch.uint8, device=device)
+    out = {"_buffer": buf, "_records": buf[rec_start:], "_layout": [(n_, dt, shp_, o - rec_start, nb) for n_, dt, shp_, o, nb in sizes
+                                                                    if n_ in RECORD_FIELDS]}
+    for name, dt, shp_, o, nb in sizes:
+        out[name] = buf[o:o + nb].view(dt).reshape((B,) + tuple(shp_))
+    return out
 
 
 class CudaBackend:
@@ -100,7 +129,7 @@ class CudaBackend:
         B = heat.shape[0]
         if out is None:
             out = alloc_decode_out(B, params)
-        o = _abi.DecodeOut(**{k: _ptr(v) for k, v in out.items()})
+        o = _abi.DecodeOut(**{k: _ptr(v) for k, v in out.items() if not k.startswith("_")})
         _lib.check(self.lib.popnet_decode(_ptr(heat), _ptr(paf), _ptr(depth), B, C.byref(params), C.byref(o),
                                           _stream()), "popnet_decode")
         return out
@@ -109,7 +138,7 @@ class CudaBackend:
         """NumPy (or torch) maps in, dict of NumPy arrays out -- same keys/strides as the C oracle."""
         h, p_, d = _to_dev(heat, torch.float32), _to_dev(paf, torch.float32), _to_dev(depth, torch.float32)
         out = self.decode_device(h, p_, d, params)
-        res = {k: v.cpu().numpy() for k, v in out.items()}
+        res = {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
         res["flags"] = res["flags"].view(np.uint32)
         return res
 

@@ -45,7 +45,7 @@ class PoseEstimator:
             from ._cuda_backend import alloc_decode_out
             self._out = alloc_decode_out(B, self.params)
             self._x_dev = torch.empty((B, 1, self.input_size, self.input_size), dtype=torch.float32, device="cuda")
-            self._host = {k: torch.empty(self._out[k].shape, dtype=self._out[k].dtype).pin_memory() for k in RECORD_KEYS}
+            self._host = torch.empty(self._out["_records"].shape, dtype=torch.uint8).pin_memory()
         return self._out
 
     def infer_device(self, x_dev):
@@ -66,50 +66,61 @@ class PoseEstimator:
         self._buffers(B)
         self._x_dev.copy_(x, non_blocking=True)
         out = self.infer_device(self._x_dev)
-        for k in RECORD_KEYS:
-            self._host[k].copy_(out[k], non_blocking=True)
+        self._host.copy_(out["_records"], non_blocking=True)          # one D2H transfer for all record fields
         torch.cuda.current_stream().synchronize()
-        res = {k: self._host[k].numpy() for k in RECORD_KEYS}
-        return res
+        return unpack_records(self._host, out["_layout"], B)
 
     def h2d_bytes(self, B):
         return B * self.input_size * self.input_size * 4
 
     def d2h_bytes(self, B):
         self._buffers(B)
-        return int(sum(self._out[k].numel() * self._out[k].element_size() for k in RECORD_KEYS))
+        return int(self._out["_records"].numel())
 
 
 # ---------------------------------------------------------------------------------------------
 # the collective
 # ---------------------------------------------------------------------------------------------
-def gather_records(records, group=None):
-    """All-gather fixed-size pose records of equal-sized batch shards; rank r's frames land at
-    [r*B, (r+1)*B).  Works on CUDA tensors (NCCL) and CPU tensors (gloo).  The eight record arrays of a
-    frame are packed into one byte row so that the step issues ONE collective (int16 fields are not a
-    collective dtype in either backend anyway).  Returns a dict of tensors."""
+def unpack_records(buf, layout, B, world=None):
+    """Views of the record fields inside a packed byte buffer (NumPy for host buffers, torch for device buffers).
+    With ``world`` the buffer holds `world` rank chunks back to back and every view gets a leading rank axis."""
+    is_torch = isinstance(buf, torch.Tensor) and buf.is_cuda
+    res = {}
+    if world is None:
+        base = buf if is_torch else (buf.numpy() if isinstance(buf, torch.Tensor) else buf)
+        for name, dt, shp, off, nb in layout:
+            if is_torch:
+                res[name] = base[off:off + nb].view(dt).reshape((B,) + tuple(shp))
+            else:
+                res[name] = base[off:off + nb].view(_NP[dt]).reshape((B,) + tuple(shp))
+        return res
+    chunk = buf.shape[0] // world
+    base = buf.reshape(world, chunk) if is_torch else (buf.numpy() if isinstance(buf, torch.Tensor) else buf).reshape(world, chunk)
+    for name, dt, shp, off, nb in layout:
+        if is_torch:
+            res[name] = base[:, off:off + nb].contiguous().view(dt).reshape((world * B,) + tuple(shp))
+        else:
+            res[name] = np.ascontiguousarray(base[:, off:off + nb]).view(_NP[dt]).reshape((world * B,) + tuple(shp))
+    return res
+
+
+_NP = {torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32, torch.int16: np.int16}
+
+
+def gather_records(out, group=None, unpack=True):
+    """All-gather the pose records of equal-sized batch shards: ONE collective on the packed record bytes
+    (``out["_records"]``, see _cuda_backend.alloc_decode_out); rank r's frames land at [r*B, (r+1)*B).
+    Works on CUDA buffers (NCCL over NVLink) and CPU buffers (gloo, used by the tests)."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    parts, meta = [], []
-    B = None
-    for k in RECORD_KEYS:
-        t = records[k]
-        t = t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t))
-        if t.dtype == torch.uint32:
-            t = t.view(torch.int32)
-        t = t.contiguous()
-        B = t.shape[0]
-        row = t.reshape(B, -1).view(torch.uint8)
-        parts.append(row)
-        meta.append((k, t.dtype, tuple(t.shape[1:]), row.shape[1]))
-    packed = torch.cat(parts, dim=1).contiguous()
-    full = torch.empty((world * B, packed.shape[1]), dtype=torch.uint8, device=packed.device)
-    dist.all_gather_into_tensor(full, packed, group=group)
-    out, off = {}, 0
-    for k, dt, shape, nbytes in meta:
-        out[k] = full[:, off:off + nbytes].contiguous().view(dt).reshape((world * B,) + shape)
-        off += nbytes
-    return out
+    rec = out["_records"]
+    rec = rec if isinstance(rec, torch.Tensor) else torch.from_numpy(rec)
+    full = torch.empty((world * rec.shape[0],), dtype=torch.uint8, device=rec.device)
+    dist.all_gather_into_tensor(full, rec, group=group)
+    if not unpack:
+        return full
+    B = out["n_person"].shape[0]
+    return unpack_records(full, out["_layout"], B, world)
 
 
 def reduce_counts(counts, group=None):

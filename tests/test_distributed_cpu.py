@@ -32,8 +32,12 @@ def _worker(rank, world, port, q):
     params = helpers.params_for("MP3DHP", max_persons=32)
     sl = pipeline.shard(B, rank, world)
     local = c_oracle.decode(heat[sl], paf[sl], depth[sl], params)            # this rank's frames only
-    full = pipeline.gather_records({k: torch.from_numpy(np.ascontiguousarray(local[k].view(np.int32) if local[k].dtype == np.uint32 else local[k]))
-                                    for k in pipeline.RECORD_KEYS})
+    from popnet_b200._cuda_backend import alloc_decode_out
+    out = alloc_decode_out(sl.stop - sl.start, params, device="cpu")         # same packed layout as on the GPU
+    for k in pipeline.RECORD_KEYS:
+        src = local[k].view(np.int32) if local[k].dtype == np.uint32 else local[k]
+        out[k].copy_(torch.from_numpy(np.ascontiguousarray(src)))
+    full = pipeline.gather_records(out)
     # evaluator counters: shard the frames, all-reduce the integer counters
     ds = synth.eval_set(60, seed=5)
     evaluate._backend = OracleBackend()
@@ -43,7 +47,7 @@ def _worker(rank, world, port, q):
     red = pipeline.reduce_counts({"hit_cnt": part["hit_cnt"], "valid_cnt": part["valid_cnt"],
                                   "samples": np.array([part["samples_cnt"]])})
     if rank == 0:
-        q.put(({k: v.numpy() for k, v in full.items()}, {k: v.numpy() for k, v in red.items()}))
+        q.put(({k: np.asarray(v) for k, v in full.items()}, {k: v.numpy() for k, v in red.items()}))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -36,39 +36,74 @@ class PoseEstimator:
                                               max_persons=max_persons)
         self._out = None
         self._x_dev = None
-        self._host = None
+        self._slots = None
         self.inject = None          # optional (heat, paf, depth) device tensors decoded INSTEAD of the network's maps
 
     # ---------------------------------------------------------------------------------------
+    NSLOT = 2      # double buffering: the H2D copy of batch i+1 overlaps the compute of batch i
+
     def _buffers(self, B):
         if self._out is None or self._out["n_person"].shape[0] != B:
             from ._cuda_backend import alloc_decode_out
-            self._out = alloc_decode_out(B, self.params)
-            self._x_dev = torch.empty((B, 1, self.input_size, self.input_size), dtype=torch.float32, device="cuda")
-            self._host = torch.empty(self._out["_records"].shape, dtype=torch.uint8).pin_memory()
+            self._slots = []
+            for _ in range(self.NSLOT):
+                out = alloc_decode_out(B, self.params)
+                self._slots.append({
+                    "out": out,
+                    "x": torch.empty((B, 1, self.input_size, self.input_size), dtype=torch.float32, device="cuda"),
+                    "host": torch.empty(out["_records"].shape, dtype=torch.uint8).pin_memory(),
+                    "h2d": torch.cuda.Event(), "done": torch.cuda.Event(), "busy": False,
+                })
+            self._out = self._slots[0]["out"]
+            self._x_dev = self._slots[0]["x"]
+            self._copy_stream = torch.cuda.Stream()
+            self._next = 0
         return self._out
 
-    def infer_device(self, x_dev):
+    def infer_device(self, x_dev, out=None):
         """x_dev [B,1,H,W] fp32 CUDA -> dict of device record tensors (no synchronisation)."""
         B = x_dev.shape[0]
-        out = self._buffers(B)
+        self._buffers(B)
+        out = self._out if out is None else out
         (paf, heat, depth), _ = self.model(x_dev)
         if self.inject is not None:
             heat, paf, depth = self.inject
         self.backend.decode_device(heat, paf, depth, self.params, out)
         return out
 
-    def infer(self, frames):
-        """The user-facing call: ``frames`` [B,1,H,W] fp32 on the HOST (NumPy array or, to avoid a staging copy,
-        a pinned torch tensor) -> dict of NumPy pose records.  Includes H2D of the frames and D2H of the records."""
+    def submit(self, frames):
+        """Asynchronous half of ``infer``: enqueue H2D (copy stream) -> forward -> decode -> D2H for one batch of HOST
+        frames and return a ticket.  Up to NSLOT batches may be in flight; ``collect`` them in submission order."""
         x = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames, np.float32))
         B = x.shape[0]
         self._buffers(B)
-        self._x_dev.copy_(x, non_blocking=True)
-        out = self.infer_device(self._x_dev)
-        self._host.copy_(out["_records"], non_blocking=True)          # one D2H transfer for all record fields
-        torch.cuda.current_stream().synchronize()
-        return unpack_records(self._host, out["_layout"], B)
+        slot = self._slots[self._next % self.NSLOT]
+        if slot["busy"]:
+            raise RuntimeError("collect() the oldest batch before submitting a %dth one" % (self.NSLOT + 1))
+        main = torch.cuda.current_stream()
+        self._copy_stream.wait_event(slot["done"])          # the previous user of this slot has finished with x / host
+        with torch.cuda.stream(self._copy_stream):
+            slot["x"].copy_(x, non_blocking=True)
+            slot["h2d"].record(self._copy_stream)
+        main.wait_event(slot["h2d"])
+        out = self.infer_device(slot["x"], slot["out"])
+        slot["host"].copy_(out["_records"], non_blocking=True)          # one D2H transfer for all record fields
+        slot["done"].record(main)
+        slot["busy"] = True
+        self._next += 1
+        return (slot, B)
+
+    def collect(self, ticket):
+        """Wait for a submitted batch; returns NumPy views of its pose records (valid until the slot is reused)."""
+        slot, B = ticket
+        slot["done"].synchronize()
+        slot["busy"] = False
+        return unpack_records(slot["host"], slot["out"]["_layout"], B)
+
+    def infer(self, frames):
+        """The user-facing call: ``frames`` [B,1,H,W] fp32 on the HOST (NumPy array or, to avoid a staging copy,
+        a pinned torch tensor) -> dict of NumPy pose records.  Includes H2D of the frames and D2H of the records."""
+        return self.collect(self.submit(frames))
 
     def h2d_bytes(self, B):
         return B * self.input_size * self.input_size * 4

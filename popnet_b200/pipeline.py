@@ -57,18 +57,42 @@ class PoseEstimator:
             self._out = self._slots[0]["out"]
             self._x_dev = self._slots[0]["x"]
             self._copy_stream = torch.cuda.Stream()
+            self.decode_stream = torch.cuda.Stream()
             self._next = 0
         return self._out
 
-    def infer_device(self, x_dev, out=None):
-        """x_dev [B,1,H,W] fp32 CUDA -> dict of device record tensors (no synchronisation)."""
+    def infer_device(self, x_dev, out=None, after=None, _evs=None):
+        """x_dev [B,1,H,W] fp32 CUDA -> dict of device record tensors (no synchronisation).
+
+        The forward runs on the current stream; decode + lift run on a second stream that waits on the forward's
+        completion event, so the (latency-bound, low-occupancy) decode of batch i overlaps the forward of batch i+1.
+        Work later enqueued on ``self.decode_stream`` (D2H, all-gather) is ordered after the decode; callers that read
+        the records from another stream must wait on ``out["_ready"]``.  ``after``: optional callable run on the decode
+        stream right after the decode (used for the D2H copy / the collective)."""
         B = x_dev.shape[0]
         self._buffers(B)
         out = self._out if out is None else out
+        main = torch.cuda.current_stream()
         (paf, heat, depth), _ = self.model(x_dev)
+        if _evs is not None:
+            _evs[1].record(main)            # bench hook: end of the forward on its stream
         if self.inject is not None:
             heat, paf, depth = self.inject
-        self.backend.decode_device(heat, paf, depth, self.params, out)
+        fwd_done = torch.cuda.Event()
+        fwd_done.record(main)
+        ds = self.decode_stream
+        ds.wait_event(fwd_done)
+        with torch.cuda.stream(ds):
+            if _evs is not None:
+                _evs[2].record(ds)          # bench hook: start of the decode on the decode stream
+            self.backend.decode_device(heat, paf, depth, self.params, out)
+            for t in (heat, paf, depth):
+                t.record_stream(ds)
+            res = after(out) if after is not None else None
+            ready = torch.cuda.Event()
+            ready.record(ds)
+        out["_ready"] = ready
+        out["_after"] = res
         return out
 
     def submit(self, frames):
@@ -86,9 +110,9 @@ class PoseEstimator:
             slot["x"].copy_(x, non_blocking=True)
             slot["h2d"].record(self._copy_stream)
         main.wait_event(slot["h2d"])
-        out = self.infer_device(slot["x"], slot["out"])
-        slot["host"].copy_(out["_records"], non_blocking=True)          # one D2H transfer for all record fields
-        slot["done"].record(main)
+        # one D2H transfer for all record fields, on the decode stream right behind the decode
+        out = self.infer_device(slot["x"], slot["out"], after=lambda o: slot["host"].copy_(o["_records"], non_blocking=True))
+        slot["done"] = out["_ready"]
         slot["busy"] = True
         self._next += 1
         return (slot, B)

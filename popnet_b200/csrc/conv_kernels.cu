@@ -158,21 +158,7 @@ __host__ __device__ constexpr uint32_t umma_idesc(int n, int fmt) {
 // ------------------------------------------------------------------------------------------------
 // epilogue shared by the tensor-core and the SIMT kernels
 // ------------------------------------------------------------------------------------------------
-struct PosInfo {
-  bool in_range, interior;
-  int n, h, w;
-};
-
-__device__ __forceinline__ PosInfo locate(int pos, const ConvArgs& a) {
-  PosInfo r;
-  r.in_range = pos < a.P;
-  const int per = a.Hp * a.Wp;
-  const int n = pos / per, rem = pos - n * per;
-  const int hp = rem / a.Wp, wp = rem - hp * a.Wp;
-  r.interior = r.in_range && hp >= 1 && hp <= a.Hp - 2 && wp >= 1 && wp <= a.Wp - 2;
-  r.n = n; r.h = hp - 1; r.w = wp - 1;
-  return r;
-}
+__device__ __forceinline__ PosInfo locate(int pos, const ConvArgs& a) { return c8p_locate(pos, a.P, a.Hs, a.Wp); }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -201,7 +187,7 @@ __device__ __forceinline__ void finish8(const ConvArgs& a, int pos, const PosInf
         default: break;
       }
       if (a.head_out && ch0 + i < a.cout) {
-        const int H = a.Hp - 2, W = a.Wp - 2;
+        const int H = a.Hs - 1, W = a.Wp - 1;
         a.head_out[(((long long)pi.n * a.cout + ch0 + i) * H + pi.h) * W + pi.w] = x;
       }
       if (ch0 + i >= a.cout) x = 0.f;                                  // padded channels stay zero
@@ -565,8 +551,8 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const StemArgs a) {
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int Ho = a.H / 2, Wo = a.W / 2, Hp = Ho + 2, Wp = Wo + 2;
-  const int P = a.N * Hp * Wp;
+  const int Ho = a.H / 2, Wo = a.W / 2, Hs = Ho + 1, Wp = Wo + 1;
+  const int P = (int)c8p_positions(a.N, Ho, Wo);
   const int tiles = (P + 127) / 128;
   for (int i = tid; i < 8 * 64; i += kStemThreads)
     reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(a.w)[i];
@@ -590,13 +576,13 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const StemArgs a) {
   pdl_wait();
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int pos = tile * 128 + tid;
-    const int n = pos / (Hp * Wp), rem = pos - n * Hp * Wp;
-    const int hp = rem / Wp, wp = rem - hp * Wp;
-    const bool interior = pos < P && hp >= 1 && hp <= Ho && wp >= 1 && wp <= Wo;
+    const PosInfo pi = c8p_locate(pos, P, Hs, Wp);
+    const int n = pi.n;
+    const bool interior = pi.interior;
     // ---- im2col: this thread's 49 taps -> 8 vectors of 8 K-values
     {
       const float* img = a.x + (long long)n * a.H * a.W;
-      const int iy0 = (hp - 1) * 2 - 3, ix0 = (wp - 1) * 2 - 3;
+      const int iy0 = pi.h * 2 - 3, ix0 = pi.w * 2 - 3;
       uint32_t pk[32];
 #pragma unroll
       for (int k2 = 0; k2 < 32; ++k2) {
@@ -659,28 +645,29 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const StemArgs a) {
 // AvgPool2d(3, stride 2, pad 1), divisor always 9; the zero ring of the input IS the padding
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) pool_kernel(const PoolArgs a) {
-  const int Ho = a.H / 2, Wo = a.W / 2, Hpo = Ho + 2, Wpo = Wo + 2, Wpi = a.W + 2, Hpi = a.H + 2;
-  const int P = a.N * Hpo * Wpo;
+  const int Ho = a.H / 2, Wo = a.W / 2, Wpi = a.W + 1, Hsi = a.H + 1;
+  const int P = (int)c8p_positions(a.N, Ho, Wo);
   const int pos = blockIdx.x * 128 + threadIdx.x;
   pdl_launch_dependents();
   pdl_wait();
   if (pos >= P) return;
   const int g = blockIdx.y;
-  const int n = pos / (Hpo * Wpo), rem = pos - n * Hpo * Wpo;
-  const int hp = rem / Wpo, wp = rem - hp * Wpo;
+  const PosInfo pi = c8p_locate(pos, P, Ho + 1, Wo + 1);
   __align__(16) h16 ob[8];
-  if (hp >= 1 && hp <= Ho && wp >= 1 && wp <= Wo) {
+  if (pi.interior) {
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    // output (oy, ox) covers input rows 2oy-1 .. 2oy+1 -> padded rows 2oy .. 2oy+2
-    const h16* src = a.in + (long long)g * a.in_plane_stride + ((long long)n * Hpi * Wpi) * 8;
-    const int py = 2 * (hp - 1), px = 2 * (wp - 1);
+    // output (oy, ox) covers input rows 2oy-1 .. 2oy+1, cols 2ox-1 .. 2ox+1; the zero row above / below an image and
+    // the zero cell that ends every row ARE the padding (col -1 of a row is the zero cell of the row before it)
+    const h16* src = a.in + (long long)g * a.in_plane_stride;
+    const long long row0 = 2 + (long long)pi.n * Hsi + 2 * pi.h - 1;
+    const int col0 = 2 * pi.w - 1;
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        const uint4 q = *reinterpret_cast<const uint4*>(src + ((long long)(py + dy) * Wpi + px + dx) * 8);
+        const uint4 q = *reinterpret_cast<const uint4*>(src + ((row0 + dy) * Wpi + col0 + dx) * 8);
         const h16* qb = reinterpret_cast<const h16*>(&q);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += h162f(qb[i], a.fmt);
@@ -788,7 +775,7 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
 }
 
 int launch_stem(const StemArgs& a, cudaStream_t st) {
-  const int P = a.N * (a.H / 2 + 2) * (a.W / 2 + 2);
+  const int P = (int)c8p_positions(a.N, a.H / 2, a.W / 2);
   const int tiles = (P + 127) / 128;
   const int grid = tiles < 148 * 6 ? tiles : 148 * 6;      // persistent: six CTAs per SM walk the tiles
   cudaLaunchConfig_t cfg = pdl_config(dim3(grid), dim3(kStemThreads), 0, st);
@@ -798,7 +785,7 @@ int launch_stem(const StemArgs& a, cudaStream_t st) {
 }
 
 int launch_pool(const PoolArgs& a, cudaStream_t st) {
-  const int P = a.N * (a.H / 2 + 2) * (a.W / 2 + 2);
+  const int P = (int)c8p_positions(a.N, a.H / 2, a.W / 2);
   dim3 grid((P + 127) / 128, a.planes);
   cudaLaunchConfig_t cfg = pdl_config(grid, dim3(128), 0, st);
   POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, pool_kernel, a));

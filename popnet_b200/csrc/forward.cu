@@ -25,7 +25,7 @@ struct Buf {
   int C, H, W;
   size_t off;             // bf16 elements from the workspace start
   long long plane_stride; // bf16 elements
-  int P;                  // N * (H+2) * (W+2)
+  int P;                  // (2 + N * (H+1)) * (W+1)
 };
 
 enum BufId { A112, B112, C112, D56, E56, F56, G56, S2IN, LA, LB, LC, SA, SB_, DA, DB, DC, kNumBufs };
@@ -55,7 +55,7 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   if (cfg.operand_dtype != 0 && cfg.operand_dtype != 1) return false;
   if (cfg.input_dim != 1 || cfg.height % 8 || cfg.width % 8 || cfg.height < 16 || cfg.width < 16) return false;
   if (cfg.num_parts < 1 || cfg.num_parts > 15 || cfg.num_limbs < 1 || cfg.num_limbs > 15) return false;
-  if (cfg.width / 2 + 3 > kGuard) return false;
+  if (cfg.width / 2 + 2 > kGuard) return false;
   p.K = cfg.num_parts; p.L = cfg.num_limbs;
   p.pl = 32; p.ph = 16; p.pd = 16;
   const int H2 = cfg.height / 2, W2 = cfg.width / 2, H4 = H2 / 2, W4 = W2 / 2, H8 = H4 / 2, W8 = W4 / 2;
@@ -69,7 +69,7 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   size_t off = 0;
   for (int i = 0; i < kNumBufs; ++i) {
     Buf& b = p.bufs[i];
-    b.P = batch * (b.H + 2) * (b.W + 2);
+    b.P = (int)c8p_positions(batch, b.H, b.W);
     b.plane_stride = (long long)(kGuard + align_up((size_t)(batch > 0 ? b.P : 0), kPosRound) + kPosSlack + kGuard) * 8;
     b.off = off;
     off += (size_t)(b.C / 8) * b.plane_stride;
@@ -271,7 +271,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
       float* s2[4] = {nullptr, paf, heat, depth};
       a.head_out = (l.stage == 1) ? s1[l.head] : s2[l.head];
     }
-    a.P = bi.P; a.Hp = bi.H + 2; a.Wp = bi.W + 2;
+    a.P = bi.P; a.Hs = bi.H + 1; a.Wp = bi.W + 1;
     a.chunks = l.cin_pad / 64;
     a.a_stages = 2;                       // double-buffered across chunks AND across tiles (persistent kernel)
     a.act = l.act; a.cout = l.cout; a.cout_pad = l.cout_pad; a.nt = l.nt; a.taps = l.k * l.k;
@@ -342,7 +342,7 @@ struct PopnetDebugConv {
   void* out; long long out_plane_stride;
   const void* res; long long res_plane_stride;
   float* head_out;
-  int P, Hp, Wp, chunks, a_stages, act, cout, cout_pad, nt, nacc, taps, impl, fmt, dbg;
+  int P, Hs, Wp, chunks, a_stages, act, cout, cout_pad, nt, nacc, taps, impl, fmt, dbg;
   long long* probe;
 };
 
@@ -354,7 +354,7 @@ extern "C" __attribute__((visibility("default"))) int popnet_debug_conv(const Po
   a.out = static_cast<h16*>(d->out); a.out_plane_stride = d->out_plane_stride;
   a.res = static_cast<const h16*>(d->res); a.res_plane_stride = d->res_plane_stride;
   a.head_out = d->head_out;
-  a.P = d->P; a.Hp = d->Hp; a.Wp = d->Wp; a.chunks = d->chunks; a.a_stages = d->a_stages; a.act = d->act;
+  a.P = d->P; a.Hs = d->Hs; a.Wp = d->Wp; a.chunks = d->chunks; a.a_stages = d->a_stages; a.act = d->act;
   a.cout = d->cout; a.cout_pad = d->cout_pad; a.nt = d->nt; a.taps = d->taps; a.fmt = d->fmt; a.dbg = d->dbg; a.probe = d->probe;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return d->impl == POPNET_FWD_IMPL_SIMT ? launch_conv_simt(a, st) : launch_conv_tc(a, d->nacc, st);

@@ -30,7 +30,7 @@ LAYERS_ALL = [("64->64@112", 64, 2, 9, 64, 64, 112), ("64->64@112 acc3", 64, 3, 
 LAYERS = [l for l in LAYERS_ALL if l[0] in ("64->64@112 acc3", "128->128@56", "128->128@56 acc2", "128->128@28", "128->128@28 acc2", "64->128@56", "64->128@56 acc4", "256->256@28")]
 for name, nt, nacc, taps, cin, cout, H in LAYERS:
     N = a.batch
-    P = N * (H + 2) * (H + 2)
+    P = (2 + N * (H + 1)) * (H + 1)
     plen = GUARD + (P + ROUND - 1) // ROUND * ROUND + 512 + GUARD
     xin = (torch.randn((cin // 8, plen, 8), device="cuda") * 0.5).to(torch.bfloat16)
     k = 3 if taps == 9 else 1
@@ -44,7 +44,7 @@ for name, nt, nacc, taps, cin, cout, H in LAYERS:
     for dbg, label in ((0, "full"),):
         d = DebugConv(inp=xin[:, GUARD:].data_ptr(), in_plane_stride=plen * 8, w=w.data_ptr(), shift=shift.data_ptr(),
                       out=out[:, GUARD:].data_ptr(), out_plane_stride=plen * 8, res=None, res_plane_stride=0,
-                      head_out=None, P=P, Hp=H + 2, Wp=H + 2, chunks=cin // 64, a_stages=2, act=1,
+                      head_out=None, P=P, Hs=H + 1, Wp=H + 1, chunks=cin // 64, a_stages=2, act=1,
                       cout=cout, cout_pad=cout, nt=nt, nacc=nacc, taps=taps, impl=0, fmt=0, dbg=dbg, probe=None)
         for _ in range(2):
             assert lib.popnet_debug_conv(C.byref(d), None) == 0

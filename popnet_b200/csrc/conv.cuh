@@ -45,7 +45,9 @@ enum Act : int { kActNone = 0, kActRelu = 1, kActLeaky = 2, kActHeadPaf = 3, kAc
 struct ConvArgs {
   const h16* in;                // position 0 of the first input plane
   long long in_plane_stride;    // 16-bit elements between planes
-  const h16* w;                 // packed [n_tile][tap][cin_pad/8][NT][8], BN scale folded in
+  const h16* in2;               // optional second input (same geometry) feeding `chunks2` extra 1x1 chunks: the
+  long long in2_plane_stride;   //   fused projection shortcut of a residual block (K-concatenation), else nullptr
+  const h16* w;                 // packed [tap][cin_pad/8][NT][8] (+ [chunks2*8][NT][8] for the extra chunks), scale folded in
   const float* shift;           // [cout_pad] folded BN shift + conv bias
   h16* out;                     // position 0 of the first output plane, or nullptr
   long long out_plane_stride;
@@ -55,6 +57,7 @@ struct ConvArgs {
   int P;                        // (2 + N * Hs) * Wp positions
   int Hs, Wp;                   // row period of an image (H + 1) and row pitch (W + 1)
   int chunks;                   // cin_pad / 64
+  int chunks2;                  // extra 64-channel chunks read from in2 with the centre tap only
   int a_stages;                 // 1 or 2
   int act;                      // Act
   int cout;                     // logical output channels (head_out bound)
@@ -68,7 +71,7 @@ struct ConvArgs {
 
 struct StemArgs {
   const float* x;               // [N][H][W] fp32
-  const h16* w;                 // [8 k8][64 cout][8]: K = ky*7+kx (49 taps, zero padded to 64), scale folded
+  const h16* w;                 // [8 kernel rows (8th zero)][64 cout][8 column slots (slot 0 zero)], scale folded
   const float* shift;           // [64]
   h16* out;                     // C8P, 64 channels at (H/2, W/2)
   long long out_plane_stride;

@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   const int dbg = DBG ? a.dbg : 0;
   if (probe && threadIdx.x == 0) probe[0] = clock64();
   const int chunks = a.chunks;
+  const int chunks_all = chunks + (BRES ? 0 : a.chunks2);
   const int k8_total = chunks * 8;
   pdl_launch_dependents();
 
@@ -323,7 +324,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
       }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int t0 = tile * MT;
-        for (int c = 0; c < chunks; ++c, ++ia) {
+        for (int c = 0; c < chunks_all; ++c, ++ia) {
+          const bool ex = c >= chunks;                      // extra 1x1 chunk of the fused shortcut
+          const h16* src = ex ? a.in2 + (long long)((c - chunks) * 8) * a.in2_plane_stride
+                              : a.in + (long long)(c * 8) * a.in_plane_stride;
+          const long long pstride = ex ? a.in2_plane_stride : a.in_plane_stride;
           const int as = ia % ast;
           if (ia >= ast) mbar_wait_relaxed(a_empty(as), ((ia / ast) - 1) & 1);
           if ((dbg & 16) && ia >= ast) mbar_arrive(a_full(as));      // tuning: no copy traffic after the first fill
@@ -331,17 +336,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
             mbar_expect_tx(a_full(as), a_stage_bytes);
             for (int g = 0; g < 8; ++g)
               bulk_g2s(smem_u32(sA + (size_t)as * a_stage_bytes + (size_t)g * a_plane_bytes),
-                       a.in + (long long)(c * 8 + g) * a.in_plane_stride + (long long)(t0 - halo) * 8, a_plane_bytes,
-                       a_full(as));
+                       src + (long long)g * pstride + (long long)(t0 - halo) * 8, a_plane_bytes, a_full(as));
           }
-          for (int t = 0; t < TAPS && !BRES; ++t, ++ib) {
+          const int ntap = ex ? 1 : TAPS;
+          for (int t = 0; t < ntap && !BRES; ++t, ++ib) {
             const int bs = ib % BST;
             if (ib >= BST) mbar_wait_relaxed(b_empty(bs), ((ib / BST) - 1) & 1);
             if ((dbg & 16) && ib >= BST) mbar_arrive(b_full(bs));
             else {
+              const long long woff = ex ? ((long long)TAPS * k8_total + (c - chunks) * 8) * NT * 8
+                                        : ((long long)t * k8_total + c * 8) * NT * 8;
               mbar_expect_tx(b_full(bs), kBStageBytes);
-              bulk_g2s(smem_u32(sB + (size_t)bs * kBStageBytes), a.w + ((long long)t * k8_total + c * 8) * NT * 8,
-                       kBStageBytes, b_full(bs));
+              bulk_g2s(smem_u32(sB + (size_t)bs * kBStageBytes), a.w + woff, kBStageBytes, b_full(bs));
             }
           }
         }
@@ -375,7 +381,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
         }
         const uint32_t tmem_acc = tmem_base + (uint32_t)s * kAccCols;
         uint32_t accumulate = 0;
-        for (int c = 0; c < chunks; ++c, ++ia) {
+        for (int c = 0; c < chunks_all; ++c, ++ia) {
+          const bool ex = c >= chunks;            // extra 1x1 chunk: centre tap only
+          const int ntap = ex ? 1 : TAPS;
           const int as = ia % ast;
           long long tw = probe ? clock64() : 0;
           mbar_wait(a_full(as), (ia / ast) & 1);
@@ -383,9 +391,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
           const uint32_t a_lo_stage = a_lo0 + ((as * a_stage_bytes) >> 4);
           int bs = ib % BST;
           uint32_t bph = (ib / BST) & 1;
-          int dh = -1, dw = -1;                   // tap offsets without div/mod
+          int dh = ex ? 0 : -1, dw = ex ? 0 : -1; // tap offsets without div/mod
 #pragma unroll 1
-          for (int t = 0; t < TAPS; ++t, ++ib) {
+          for (int t = 0; t < ntap; ++t, ++ib) {
             int nbs = bs + 1;
             uint32_t nbph = bph;
             if (!BRES) {
@@ -532,6 +540,18 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvArgs a) {
         }
       }
     }
+    for (int g = 0; g < a.chunks2 * 8; ++g) {              // fused 1x1 shortcut on the second input
+      const uint4 xa = *reinterpret_cast<const uint4*>(a.in2 + (long long)g * a.in2_plane_stride + (long long)pos * 8);
+      const h16* xb = reinterpret_cast<const h16*>(&xa);
+      const h16* wrow = a.w + (((long long)a.taps * k8_total + g) * a.nt + nn) * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 wa = *reinterpret_cast<const uint4*>(wrow + i * 8);
+        const h16* wb = reinterpret_cast<const h16*>(&wa);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i] = fmaf(h162f(xb[j], a.fmt), h162f(wb[j], a.fmt), acc[i]);
+      }
+    }
   }
   finish8(a, pos, pi, ch0, acc);
 }
@@ -539,7 +559,7 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvArgs a) {
 // ------------------------------------------------------------------------------------------------
 // stem: model0.conv1 (7x7, stride 2, pad 3, one input channel) + folded BN + ReLU -> C8P (64 channels).
 // Also on the tensor cores: each CTA im2col's 128 output positions into the K-major core-matrix layout
-// (K = 49 taps padded to 64), issues four M128 x N64 x K16 MMAs against the resident weights and runs the
+// (K = 8 input rows x 8 input columns = 64, of which the 7x7 kernel uses 49), issues four M128 x N64 x K16 MMAs against the resident weights and runs the
 // same TMEM epilogue; the input image is read through L1 (every pixel feeds ~12 taps).
 // ------------------------------------------------------------------------------------------------
 constexpr int kStemThreads = 128;
@@ -579,29 +599,29 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const StemArgs a) {
     const PosInfo pi = c8p_locate(pos, P, Hs, Wp);
     const int n = pi.n;
     const bool interior = pi.interior;
-    // ---- im2col: this thread's 49 taps -> 8 vectors of 8 K-values
+    // ---- im2col: K = 8 input rows x 8 input columns (rows 2oy-3 .. 2oy+4, columns 2ox-4 .. 2ox+3; the 7x7 kernel
+    // occupies rows 0..6 / columns 1..7, the extra row and column carry zero weights).  One k8 group = one input
+    // row = four aligned float2 loads, packed straight into the 16-byte operand vector.
     {
       const float* img = a.x + (long long)n * a.H * a.W;
-      const int iy0 = pi.h * 2 - 3, ix0 = pi.w * 2 - 3;
-      uint32_t pk[32];
+      const int iy0 = pi.h * 2 - 3, ix0 = pi.w * 2 - 4;
 #pragma unroll
-      for (int k2 = 0; k2 < 32; ++k2) {
-        float v[2];
+      for (int ry = 0; ry < 8; ++ry) {
+        const int iy = iy0 + ry;
+        uint32_t w4[4] = {0u, 0u, 0u, 0u};
+        if (interior && iy >= 0 && iy < a.H) {
+          const float* row = img + (long long)iy * a.W;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int k = 2 * k2 + e;
-          float x = 0.f;
-          if (k < 49 && interior) {
-            const int iy = iy0 + k / 7, ix = ix0 + k % 7;
-            if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) x = __ldg(img + iy * a.W + ix);
+          for (int j = 0; j < 4; ++j) {
+            const int ix = ix0 + 2 * j;                    // even: the pair (ix, ix+1) is inside or outside together
+            if (ix >= 0 && ix < a.W) {
+              const float2 v = __ldg(reinterpret_cast<const float2*>(row + ix));
+              w4[j] = pack2(v.x, v.y, a.fmt);
+            }
           }
-          v[e] = x;
         }
-        pk[k2] = pack2(v[0], v[1], a.fmt);
+        reinterpret_cast<uint4*>(sA)[ry * 128 + tid] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
       }
-#pragma unroll
-      for (int g = 0; g < 8; ++g)
-        reinterpret_cast<uint4*>(sA)[g * 128 + tid] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
     }
     // generic-proxy smem writes -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -39,6 +39,8 @@ struct Layer {
   int head;                  // 0 none, 1 paf, 2 heat, 3 depth
   int stage;                 // 0 block0, 1, 2
   int remap_s2;              // input channels follow the S2IN layout
+  int fuse_layer;            // index of a 1x1 layer whose weights are K-concatenated here (-1 = none); its input is in2_buf
+  int in2_buf;
   size_t w_off, shift_off;   // bytes in the packed blob
 };
 
@@ -85,7 +87,7 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
     l.cout_pad = (int)align_up(cout, nt);
     l.nt = nt; l.nacc = nacc; l.act = act;
     l.in_buf = in_buf; l.in_plane0 = in_plane0; l.out_buf = out_buf; l.out_plane0 = out_plane0; l.res_buf = res_buf;
-    l.head = head; l.stage = stage; l.remap_s2 = remap;
+    l.head = head; l.stage = stage; l.remap_s2 = remap; l.fuse_layer = -1; l.in2_buf = -1;
     p.layers.push_back(l);
   };
   p.layers.clear();
@@ -96,8 +98,9 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   add(64, 64, 3, 64, 3, kActRelu, C112, 0, B112, 0, -1, 0, 0, 0);           // 3 layer1.1.conv1
   add(64, 64, 3, 64, 3, kActRelu, B112, 0, A112, 0, C112, 0, 0, 0);         // 4 layer1.1.conv2 (+x)
   add(64, 128, 3, 128, 2, kActRelu, D56, 0, E56, 0, -1, 0, 0, 0);           // 5 layer2.0.conv1
-  add(128, 128, 3, 128, 4, kActRelu, E56, 0, G56, 0, F56, 0, 0, 0);         // 6 layer2.0.conv2 (+downsample)
-  add(64, 128, 1, 128, 4, kActNone, D56, 0, F56, 0, -1, 0, 0, 0);           // 7 layer2.0.downsample
+  add(128, 128, 3, 128, 4, kActRelu, E56, 0, G56, 0, -1, 0, 0, 0);          // 6 layer2.0.conv2, projection shortcut fused:
+  p.layers.back().fuse_layer = 7; p.layers.back().in2_buf = D56;            //   relu(bn2(conv2(e)) + bn_d(conv1x1(d))) as ONE K = 9*128 + 64 GEMM
+  add(64, 128, 1, 128, 4, kActNone, D56, 0, F56, 0, -1, 0, 0, 0);           // 7 layer2.0.downsample (weights only; never launched)
   add(128, 128, 1, 128, 4, kActRelu, G56, 0, E56, 0, -1, 0, 0, 0);          // 8 conv2
   const int K1 = p.K + 1, L2 = 2 * p.L, L1 = p.L + 1;
   for (int s = 1; s <= 2; ++s) {
@@ -125,8 +128,8 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   }
   size_t boff = 0;
   for (Layer& l : p.layers) {
-    const size_t wbytes = (l.k == 7) ? (size_t)64 * 64 * sizeof(h16)
-                                     : (size_t)l.k * l.k * l.cin_pad * l.cout_pad * sizeof(h16);
+    size_t wbytes = (l.k == 7) ? (size_t)64 * 64 * sizeof(h16) : (size_t)l.k * l.k * l.cin_pad * l.cout_pad * sizeof(h16);
+    if (l.fuse_layer >= 0) wbytes += (size_t)64 * l.cout_pad * sizeof(h16);   // one extra 64-channel 1x1 chunk
     l.w_off = boff; boff = align_up(boff + wbytes, 256);
     l.shift_off = boff; boff = align_up(boff + (size_t)l.cout_pad * sizeof(float), 256);
   }
@@ -187,12 +190,14 @@ extern "C" int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvH
       return POPNET_ERR_INVALID_ARG;
     float* shift = reinterpret_cast<float*>(blob.data() + l.shift_off);
     for (int n = 0; n < l.cout; ++n) shift[n] = h.shift_host[n];
-    if (l.k == 7) {                                      // stem: [k8][cout][8] with K = tap index, padded to 64
+    if (l.k == 7) {                                      // stem: [k8 = kernel row (8th is zero)][cout][8 = column slot]
       h16* w = reinterpret_cast<h16*>(blob.data() + l.w_off);
       for (int n = 0; n < 64; ++n)
-        for (int t = 0; t < 64; ++t)
-          w[((t >> 3) * 64 + n) * 8 + (t & 7)] =
-              f2h16(t < 49 ? h.weight_host[(size_t)n * 49 + t] * h.scale_host[n] : 0.f, cfg->operand_dtype);
+        for (int ry = 0; ry < 8; ++ry)
+          for (int rx = 0; rx < 8; ++rx) {               // column slot rx holds input column 2ox-4+rx = kernel column rx-1
+            const float v = (ry < 7 && rx >= 1) ? h.weight_host[(size_t)n * 49 + ry * 7 + (rx - 1)] * h.scale_host[n] : 0.f;
+            w[(ry * 64 + n) * 8 + rx] = f2h16(v, cfg->operand_dtype);
+          }
       continue;
     }
     h16* w = reinterpret_cast<h16*>(blob.data() + l.w_off);
@@ -208,6 +213,20 @@ extern "C" int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvH
               if (n < l.cout && cref >= 0) v = h.weight_host[((size_t)n * l.cin + cref) * taps + t] * h.scale_host[n];
               w[((((size_t)ti * taps + t) * k8 + g) * l.nt + nn) * 8 + j] = f2h16(v, cfg->operand_dtype);
             }
+    if (l.fuse_layer >= 0) {                             // K-concatenated projection shortcut (cin 64, 1x1, own BN scale)
+      const Layer& f = p.layers[l.fuse_layer];
+      const PopnetConvHost& hf = layers[l.fuse_layer];
+      if (f.cin != 64 || f.cout != l.cout || f.k != 1 || ntiles != 1) return POPNET_ERR_UNSUPPORTED;
+      h16* we = w + (size_t)taps * k8 * l.nt * 8;
+      for (int g = 0; g < 8; ++g)
+        for (int nn = 0; nn < l.nt; ++nn)
+          for (int j = 0; j < 8; ++j) {
+            const int ci = g * 8 + j;
+            we[((size_t)g * l.nt + nn) * 8 + j] =
+                f2h16(nn < l.cout ? hf.weight_host[(size_t)nn * f.cin + ci] * hf.scale_host[nn] : 0.f, cfg->operand_dtype);
+          }
+      for (int n = 0; n < l.cout; ++n) shift[n] += hf.shift_host[n];
+    }
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   POPNET_CUDA_TRY(cudaMemcpyAsync(packed_dev, blob.data(), p.blob_bytes, cudaMemcpyHostToDevice, st));
@@ -273,6 +292,11 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     }
     a.P = bi.P; a.Hs = bi.H + 1; a.Wp = bi.W + 1;
     a.chunks = l.cin_pad / 64;
+    if (l.fuse_layer >= 0) {
+      a.in2 = buf_ptr(workspace, p.bufs[l.in2_buf], 0);
+      a.in2_plane_stride = p.bufs[l.in2_buf].plane_stride;
+      a.chunks2 = 1;
+    }
     a.a_stages = 2;                       // double-buffered across chunks AND across tiles (persistent kernel)
     a.act = l.act; a.cout = l.cout; a.cout_pad = l.cout_pad; a.nt = l.nt; a.taps = l.k * l.k;
     a.fmt = cfg->operand_dtype;
@@ -304,8 +328,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
   for (int li = 1; li <= 4; ++li) POPNET_TRY(run_conv(li));
   POPNET_TRY(run_pool(A112, D56, 0));
   POPNET_TRY(run_conv(5));
-  POPNET_TRY(run_conv(7));
-  POPNET_TRY(run_conv(6));
+  POPNET_TRY(run_conv(6));                 // includes the projection shortcut (layer 7) as an extra K chunk
   POPNET_TRY(run_conv(8));
   POPNET_TRY(run_pool(E56, S2IN, (p.pl + p.ph + p.pd) / 8));
   // The three branches of a stage are independent 5-conv chains on the same input: run the heat-map and

@@ -252,6 +252,11 @@ def run_ours(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
     pk = peaks()
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_forward_dram_traffic.json")
+    if os.path.exists(tp) and B == 64:
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj["dram_bytes_total"], "profiles/r1_forward_dram_traffic.json (ncu, one forward at batch 64)"
     frames_per_step = B * world
     value = frames_per_step * args.steps / (elapsed_ms * 1e-3)
     e2e = frames_per_step * args.steps / (e2e_ms * 1e-3)
@@ -276,7 +281,9 @@ def run_ours(args, rank, local_rank, world):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (38 launches) + stem_kernel = the forward",
                      "achieved": tflops, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tflops / pk["tflops"],
-                     "frac_of_burst_peak": tflops / pk["tflops_burst"], "peak_source": pk["src"], "traffic": None,
+                     "frac_of_burst_peak": tflops / pk["tflops_burst"], "peak_source": pk["src"], "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_flop_per_step": B * FLOP_PER_FRAME,
+                     "min_hbm_bytes_per_step": B * (224 * 224 * 4 + 2 * 46256 * 4) + 11_051_628,
                      "forward_ms": fwd_ms, "decode_ms": dec_ms,
                      "decode_hbm": {"bound": "hbm", "achieved": B * DECODE_BYTES_PER_FRAME / (dec_ms * 1e-3) / 1e9,
                                     "peak": pk["hbm"], "unit": "GB/s",

@@ -605,23 +605,24 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const StemArgs a) {
     {
       const float* img = a.x + (long long)n * a.H * a.W;
       const int iy0 = pi.h * 2 - 3, ix0 = pi.w * 2 - 4;
+      float2 v[8][4];                                    // all 32 loads are issued before the first use
 #pragma unroll
       for (int ry = 0; ry < 8; ++ry) {
         const int iy = iy0 + ry;
-        uint32_t w4[4] = {0u, 0u, 0u, 0u};
-        if (interior && iy >= 0 && iy < a.H) {
-          const float* row = img + (long long)iy * a.W;
+        const bool rok = interior && iy >= 0 && iy < a.H;
+        const float* row = img + (long long)(rok ? iy : 0) * a.W;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int ix = ix0 + 2 * j;                    // even: the pair (ix, ix+1) is inside or outside together
-            if (ix >= 0 && ix < a.W) {
-              const float2 v = __ldg(reinterpret_cast<const float2*>(row + ix));
-              w4[j] = pack2(v.x, v.y, a.fmt);
-            }
-          }
+        for (int j = 0; j < 4; ++j) {
+          const int ix = ix0 + 2 * j;                      // even: the pair (ix, ix+1) is inside or outside together
+          const bool ok = rok && ix >= 0 && ix < a.W;
+          v[ry][j] = ok ? __ldg(reinterpret_cast<const float2*>(row + ix)) : make_float2(0.f, 0.f);
         }
-        reinterpret_cast<uint4*>(sA)[ry * 128 + tid] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
       }
+#pragma unroll
+      for (int ry = 0; ry < 8; ++ry)
+        reinterpret_cast<uint4*>(sA)[ry * 128 + tid] =
+            make_uint4(pack2(v[ry][0].x, v[ry][0].y, a.fmt), pack2(v[ry][1].x, v[ry][1].y, a.fmt),
+                       pack2(v[ry][2].x, v[ry][2].y, a.fmt), pack2(v[ry][3].x, v[ry][3].y, a.fmt));
     }
     // generic-proxy smem writes -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

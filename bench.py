@@ -15,6 +15,7 @@ on all host cores on a bounded sample of the same workload -- the reference itse
 travel to the GPU box (/root/reference is not there).
 """
 import argparse
+import collections
 import json
 import os
 import subprocess
@@ -185,29 +186,26 @@ def run_ours(args, rank, local_rank, world):
                 evs[3].record(torch.cuda.current_stream())
             if world > 1:
                 pipeline.gather_records(o, unpack=False)  # one NCCL all-gather of the packed record bytes
-        if evs is not None:
-            evs[0].record()
-        # forward-only events: recorded around the model call inside infer_device would need hooks; time it here
         out = est.infer_device(x, slot["out"], after=after, _evs=evs)
         return out
 
     def submit_e2e(i):
         est.inject = dev_maps[i % R]
-        t = est.submit(host_frames[i % R])                 # H2D (copy stream) -> forward -> decode -> D2H, asynchronous
-        if world > 1:
-            pipeline.gather_records(t[0]["out"], unpack=False)
-        return t
+        # H2D (copy stream) -> forward -> decode -> D2H (-> all-gather of the record bytes), asynchronous
+        gather = (lambda o: pipeline.gather_records(o, unpack=False)) if world > 1 else None
+        return est.submit(host_frames[i % R], after=gather)
 
     def run_e2e(n):
-        """n steps through the public API, software-pipelined two deep: the H2D copy of step i+1 overlaps the compute of
-        step i; every step's records are read back on the host."""
-        rec = None
-        t = submit_e2e(0)
-        for i in range(1, n):
-            t2 = submit_e2e(i)
-            rec = est.collect(t)
-            t = t2
-        return est.collect(t)
+        """n steps through the public API, software-pipelined NSLOT deep: the H2D copy of step i+2 and the forward of step
+        i+1 overlap the decode + D2H of step i; every step's records are read back on the host."""
+        rec, q = None, collections.deque()
+        for i in range(n):
+            if len(q) == est.NSLOT:
+                rec = est.collect(q.popleft())
+            q.append(submit_e2e(i))
+        while q:
+            rec = est.collect(q.popleft())
+        return rec
 
     # ---- value leg
     for i in range(args.warmup):

@@ -780,6 +780,11 @@ int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st) {
   POPNET_TC_CASE(64, 4, 9, false)
   POPNET_TC_CASE(128, 2, 9, false)
   POPNET_TC_CASE(128, 4, 9, false)
+  POPNET_TC_CASE(128, 3, 9, false)
+  POPNET_TC_CASE(128, 3, 1, false)
+  POPNET_TC_CASE(64, 3, 9, false)
+  POPNET_TC_CASE(32, 3, 1, false)
+  POPNET_TC_CASE(16, 3, 9, false)
   POPNET_TC_CASE(128, 4, 1, false)
   POPNET_TC_CASE(256, 2, 9, false)
   POPNET_TC_CASE(32, 4, 1, false)

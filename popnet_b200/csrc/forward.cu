@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -103,6 +104,11 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   add(64, 128, 1, 128, 4, kActNone, D56, 0, F56, 0, -1, 0, 0, 0);           // 7 layer2.0.downsample (weights only; never launched)
   add(128, 128, 1, 128, 4, kActRelu, G56, 0, E56, 0, -1, 0, 0, 0);          // 8 conv2
   const int K1 = p.K + 1, L2 = 2 * p.L, L1 = p.L + 1;
+  // 28x28 stage layers: 512-position tiles.  At batch 64 the 53,882 positions make 106 tiles (72 % of the 148 SMs), 384-position
+  // tiles (POPNET_STAGE_NACC=3) make 141 (95 %); measured identical (1.065 vs 1.067 ms per forward) because the three concurrent
+  // branches already fill each other's idle SMs.
+  int kStageNacc = 4;
+  if (const char* e = getenv("POPNET_STAGE_NACC")) { const int v = atoi(e); if (v == 3 || v == 4) kStageNacc = v; }
   for (int s = 1; s <= 2; ++s) {
     const int in0 = (s == 1) ? (p.pl + p.ph + p.pd) / 8 : 0;     // stage 1 reads only the feature planes
     const int cin = (s == 1) ? 128 : 128 + L2 + K1 + L1;
@@ -111,20 +117,20 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
     add(cin, 256, 3, 256, 2, kActLeaky, S2IN, in0, LA, 0, -1, 0, s, remap);
     add(256, 256, 3, 256, 2, kActLeaky, LA, 0, LB, 0, -1, 0, s, 0);
     add(256, 256, 3, 256, 2, kActLeaky, LB, 0, LA, 0, -1, 0, s, 0);
-    add(256, 128, 1, 128, 4, kActLeaky, LA, 0, LC, 0, -1, 0, s, 0);
-    add(128, L2, 1, 32, 4, kActHeadPaf, LC, 0, (s == 1) ? S2IN : -1, 0, -1, 1, s, 0);
+    add(256, 128, 1, 128, kStageNacc, kActLeaky, LA, 0, LC, 0, -1, 0, s, 0);
+    add(128, L2, 1, 32, kStageNacc, kActHeadPaf, LC, 0, (s == 1) ? S2IN : -1, 0, -1, 1, s, 0);
     // heat-map branch: 3x3 -> 128 x4, 3x3 -> K+1
-    add(cin, 128, 3, 128, 4, kActLeaky, S2IN, in0, SA, 0, -1, 0, s, remap);
-    add(128, 128, 3, 128, 4, kActLeaky, SA, 0, SB_, 0, -1, 0, s, 0);
-    add(128, 128, 3, 128, 4, kActLeaky, SB_, 0, SA, 0, -1, 0, s, 0);
-    add(128, 128, 3, 128, 4, kActLeaky, SA, 0, SB_, 0, -1, 0, s, 0);
-    add(128, K1, 3, 16, 4, kActHeadHeat, SB_, 0, (s == 1) ? S2IN : -1, p.pl / 8, -1, 2, s, 0);
+    add(cin, 128, 3, 128, kStageNacc, kActLeaky, S2IN, in0, SA, 0, -1, 0, s, remap);
+    add(128, 128, 3, 128, kStageNacc, kActLeaky, SA, 0, SB_, 0, -1, 0, s, 0);
+    add(128, 128, 3, 128, kStageNacc, kActLeaky, SB_, 0, SA, 0, -1, 0, s, 0);
+    add(128, 128, 3, 128, kStageNacc, kActLeaky, SA, 0, SB_, 0, -1, 0, s, 0);
+    add(128, K1, 3, 16, kStageNacc, kActHeadHeat, SB_, 0, (s == 1) ? S2IN : -1, p.pl / 8, -1, 2, s, 0);
     // depth branch: 3x3 -> 128, 64, 64, 64, 3x3 -> L+1
-    add(cin, 128, 3, 128, 4, kActLeaky, S2IN, in0, DA, 0, -1, 0, s, remap);
-    add(128, 64, 3, 64, 4, kActLeaky, DA, 0, DB, 0, -1, 0, s, 0);
-    add(64, 64, 3, 64, 4, kActLeaky, DB, 0, DC, 0, -1, 0, s, 0);
-    add(64, 64, 3, 64, 4, kActLeaky, DC, 0, DB, 0, -1, 0, s, 0);
-    add(64, L1, 3, 16, 4, kActHeadPaf, DB, 0, (s == 1) ? S2IN : -1, (p.pl + p.ph) / 8, -1, 3, s, 0);
+    add(cin, 128, 3, 128, kStageNacc, kActLeaky, S2IN, in0, DA, 0, -1, 0, s, remap);
+    add(128, 64, 3, 64, kStageNacc, kActLeaky, DA, 0, DB, 0, -1, 0, s, 0);
+    add(64, 64, 3, 64, kStageNacc, kActLeaky, DB, 0, DC, 0, -1, 0, s, 0);
+    add(64, 64, 3, 64, kStageNacc, kActLeaky, DC, 0, DB, 0, -1, 0, s, 0);
+    add(64, L1, 3, 16, kStageNacc, kActHeadPaf, DB, 0, (s == 1) ? S2IN : -1, (p.pl + p.ph) / 8, -1, 3, s, 0);
   }
   size_t boff = 0;
   for (Layer& l : p.layers) {
@@ -247,6 +253,8 @@ AuxStreams* aux_streams() {
   int expected = 0;
   if (state.compare_exchange_strong(expected, 1)) {
     bool ok = true;
+    // default priority on purpose: giving the forward's streams the highest priority (so that the overlapped decode of the
+    // previous batch only gets idle SMs) was measured 3 % SLOWER per step (1.110 vs 1.082 ms, same box, A/B/A/B)
     for (int i = 0; i < 2; ++i) ok &= cudaStreamCreateWithFlags(&aux.s[i], cudaStreamNonBlocking) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&aux.fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2; ++i) ok &= cudaEventCreateWithFlags(&aux.join[i], cudaEventDisableTiming) == cudaSuccess;

@@ -40,7 +40,7 @@ class PoseEstimator:
         self.inject = None          # optional (heat, paf, depth) device tensors decoded INSTEAD of the network's maps
 
     # ---------------------------------------------------------------------------------------
-    NSLOT = 2      # double buffering: the H2D copy of batch i+1 overlaps the compute of batch i
+    NSLOT = 3      # batches in flight: H2D of batch i+2, forward of batch i+1 and decode + D2H of batch i overlap
 
     def _buffers(self, B):
         if self._out is None or self._out["n_person"].shape[0] != B:
@@ -73,13 +73,15 @@ class PoseEstimator:
         self._buffers(B)
         out = self._out if out is None else out
         main = torch.cuda.current_stream()
+        if _evs is not None:
+            _evs[0].record(main)            # bench hook: start of the forward on its stream
         (paf, heat, depth), _ = self.model(x_dev)
         if _evs is not None:
-            _evs[1].record(main)            # bench hook: end of the forward on its stream
-        if self.inject is not None:
-            heat, paf, depth = self.inject
+            _evs[1].record(main)            # bench hook: end of the forward
         fwd_done = torch.cuda.Event()
         fwd_done.record(main)
+        if self.inject is not None:
+            heat, paf, depth = self.inject
         ds = self.decode_stream
         ds.wait_event(fwd_done)
         with torch.cuda.stream(ds):
@@ -95,23 +97,26 @@ class PoseEstimator:
         out["_after"] = res
         return out
 
-    def submit(self, frames):
+    def submit(self, frames, after=None):
         """Asynchronous half of ``infer``: enqueue H2D (copy stream) -> forward -> decode -> D2H for one batch of HOST
-        frames and return a ticket.  Up to NSLOT batches may be in flight; ``collect`` them in submission order."""
+        frames and return a ticket.  Up to NSLOT batches may be in flight; ``collect`` them in submission order.
+        ``after(out)``: optional callable enqueued on the decode stream behind the D2H copy (e.g. ``gather_records``)."""
         x = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames, np.float32))
         B = x.shape[0]
         self._buffers(B)
         slot = self._slots[self._next % self.NSLOT]
         if slot["busy"]:
             raise RuntimeError("collect() the oldest batch before submitting a %dth one" % (self.NSLOT + 1))
-        main = torch.cuda.current_stream()
         self._copy_stream.wait_event(slot["done"])          # the previous user of this slot has finished with x / host
         with torch.cuda.stream(self._copy_stream):
             slot["x"].copy_(x, non_blocking=True)
             slot["h2d"].record(self._copy_stream)
-        main.wait_event(slot["h2d"])
+        torch.cuda.current_stream().wait_event(slot["h2d"])
         # one D2H transfer for all record fields, on the decode stream right behind the decode
-        out = self.infer_device(slot["x"], slot["out"], after=lambda o: slot["host"].copy_(o["_records"], non_blocking=True))
+        def tail(o):
+            slot["host"].copy_(o["_records"], non_blocking=True)
+            return after(o) if after is not None else None
+        out = self.infer_device(slot["x"], slot["out"], after=tail)
         slot["done"] = out["_ready"]
         slot["busy"] = True
         self._next += 1

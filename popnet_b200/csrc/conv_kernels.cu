@@ -67,6 +67,20 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// One lane of a fully converged warp.  Unlike `lane == 0`, the compiler knows the elected region runs on exactly one
+// thread and issues the uniform-datapath tcgen05 instructions directly; behind a plain lane test it wraps EVERY
+// tcgen05.mma / commit in an ELECT + BRA.U.ANY serialisation loop (4 extra dependent instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
 }
@@ -314,7 +328,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   if (probe && threadIdx.x == 0) probe[1] = clock64();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- producer ----------------
       int ia = 0, ib = 0;
       if (BRES) {                                   // all taps of the (single) chunk, once
@@ -354,7 +368,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = umma_idesc(NT, a.fmt);
       const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
@@ -628,7 +642,7 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const StemArgs a) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32 && elect_one()) {
       tc_fence_after();
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
 #pragma unroll

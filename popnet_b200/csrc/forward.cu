@@ -13,8 +13,10 @@
 #include <cuda_bf16.h>
 
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "conv.cuh"
@@ -241,28 +243,32 @@ extern "C" int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvH
 }
 
 namespace {
-// Two auxiliary streams + fork/join events, created once per process (diagnostic-free plumbing state;
-// no results live here).  Guarded for concurrent first use.
+// Two auxiliary streams + fork/join events per CALLER stream, created on first use and kept for the life of the
+// process (plumbing state; no results live here).  Keyed by the caller's stream so that forwards issued on different
+// streams (two batches in flight) do not serialise on each other's branch streams.
 struct AuxStreams {
+  cudaStream_t owner;
   cudaStream_t s[2];
   cudaEvent_t fork, join[2];
 };
-AuxStreams* aux_streams() {
-  static AuxStreams aux;
-  static std::atomic<int> state{0};     // 0 = uninitialised, 1 = initialising, 2 = ready, 3 = failed
-  int expected = 0;
-  if (state.compare_exchange_strong(expected, 1)) {
-    bool ok = true;
-    // default priority on purpose: giving the forward's streams the highest priority (so that the overlapped decode of the
-    // previous batch only gets idle SMs) was measured 3 % SLOWER per step (1.110 vs 1.082 ms, same box, A/B/A/B)
-    for (int i = 0; i < 2; ++i) ok &= cudaStreamCreateWithFlags(&aux.s[i], cudaStreamNonBlocking) == cudaSuccess;
-    ok &= cudaEventCreateWithFlags(&aux.fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 2; ++i) ok &= cudaEventCreateWithFlags(&aux.join[i], cudaEventDisableTiming) == cudaSuccess;
-    state.store(ok ? 2 : 3);
-  }
-  while (state.load() == 1) {
-  }
-  return state.load() == 2 ? &aux : nullptr;
+AuxStreams* aux_streams(cudaStream_t owner) {
+  static std::mutex mu;
+  static std::vector<AuxStreams*> sets;
+  std::lock_guard<std::mutex> lock(mu);
+  for (AuxStreams* a : sets)
+    if (a->owner == owner) return a;
+  if (sets.size() >= 16) return sets[reinterpret_cast<uintptr_t>(owner) / 64 % 16];     // bounded: share beyond 16 streams
+  AuxStreams* aux = new AuxStreams();
+  aux->owner = owner;
+  bool ok = true;
+  // default priority on purpose: giving the forward's streams the highest priority (so that the overlapped decode of the
+  // previous batch only gets idle SMs) was measured 3 % SLOWER per step (1.110 vs 1.082 ms, same box, A/B/A/B)
+  for (int i = 0; i < 2; ++i) ok &= cudaStreamCreateWithFlags(&aux->s[i], cudaStreamNonBlocking) == cudaSuccess;
+  ok &= cudaEventCreateWithFlags(&aux->fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < 2; ++i) ok &= cudaEventCreateWithFlags(&aux->join[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { delete aux; return nullptr; }
+  sets.push_back(aux);
+  return aux;
 }
 }  // namespace
 
@@ -342,7 +348,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
   // The three branches of a stage are independent 5-conv chains on the same input: run the heat-map and
   // depth branches on two auxiliary streams so that their CTAs fill the SMs the (two-wave) PAF branch
   // leaves idle.  Fork/join through events keeps the whole forward capturable in a CUDA graph.
-  AuxStreams* aux = aux_streams();
+  AuxStreams* aux = aux_streams(st);
   if (!aux) return POPNET_ERR_CUDA;
   for (int s = 1; s <= 2; ++s) {
     const int base = 9 + 15 * (s - 1);

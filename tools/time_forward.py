@@ -15,6 +15,7 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--impl", default="tc")
+ap.add_argument("--streams", type=int, default=1)
 a = ap.parse_args()
 
 m = network.rtpose_light3d(15, 14, 2, input_dim=1)
@@ -36,3 +37,35 @@ ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.iters)]
 t = float(np.median(ts))
 print("forward batch %d: median %.3f ms  (%.0f frames/s, %.1f TFLOP/s)  all: %s" %
       (a.batch, t, a.batch / t * 1e3, a.batch * 13.343404032 / t, ["%.3f" % v for v in ts]))
+
+# ---- optional: K forwards in flight on K streams (K model instances = K workspaces); aggregate throughput
+if a.streams > 1:
+    ms = [m]
+    for _ in range(a.streams - 1):
+        mm = network.rtpose_light3d(15, 14, 2, input_dim=1)
+        mm.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        mm.operand_dtype, mm.impl = m.operand_dtype, m.impl
+        ms.append(mm)
+    sts = [torch.cuda.Stream() for _ in ms]
+    xs = [x.clone() for _ in ms]
+    torch.cuda.synchronize()
+
+    def run(n):
+        for i in range(n):
+            k = i % len(ms)
+            with torch.cuda.stream(sts[k]):
+                ms[k](xs[k])
+    run(2 * len(ms))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s_ in sts:
+        s_.wait_event(e0)
+    run(a.iters)
+    for s_ in sts:
+        torch.cuda.current_stream().wait_stream(s_)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / a.iters
+    print("%d streams: %.3f ms per forward of %d  (%.0f frames/s, %.1f TFLOP/s)" %
+          (a.streams, t, a.batch, a.batch / t * 1e3, a.batch * 13.343404032 / t))

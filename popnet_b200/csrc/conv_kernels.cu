@@ -21,6 +21,8 @@
 // stem and the pools.
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <type_traits>
+#include <utility>
 
 #include "conv.cuh"
 
@@ -118,6 +120,37 @@ __device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32
       "}" ::"r"(tmem_d),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Same, with compile-time offsets added to the descriptor start addresses and the TMEM column INSIDE the volatile asm
+// block: the compiler cannot hoist the descriptor arithmetic of a whole unrolled tap group above its first MMA (which
+// made it spill uniform registers between the MMAs); each MMA is preceded by exactly its own three adds.
+template <int A_OFF, int B_OFF, int D_OFF>
+__device__ __forceinline__ void umma_off(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 ta, tb, td;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "add.u32 ta, %1, %7;\n\t"
+      "add.u32 tb, %3, %8;\n\t"
+      "add.u32 td, %0, %9;\n\t"
+      "mov.b64 da, {ta, %2};\n\t"
+      "mov.b64 db, {tb, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [td], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "n"(A_OFF), "n"(B_OFF), "n"(D_OFF)
+      : "memory");
+}
+// compile-time loop: f(std::integral_constant<int, 0>{}) ... f(std::integral_constant<int, N-1>{})
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+  (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
 }
 // mbarrier arrive when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -383,8 +416,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
       // The tensor core's instruction queue is shallow: whatever this thread does between two MMAs is exposed.
       // Hence (1) no divisions / 64-bit math in the loop, (2) the B-ring wait of the NEXT tap is taken before the
       // MMAs of the current tap are issued (always deadlock-free: that slot was released by a tap already issued).
-      int ia = 0, ib = 0, ti = 0;
-      bool b_ready = false;                       // b_full of step `ib` already observed
+      int ti = 0;
+      int as = 0, bs = 0;                         // A / B ring positions and their barrier phases
+      uint32_t aph = 0, bph = 0;
+      bool b_ready = false;                       // b_full(bs) already observed
       if (BRES) { mbar_wait(b_full(0), 0); b_ready = true; }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
         const int s = ti % AS;
@@ -395,19 +430,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
         }
         const uint32_t tmem_acc = tmem_base + (uint32_t)s * kAccCols;
         uint32_t accumulate = 0;
-        for (int c = 0; c < chunks_all; ++c, ++ia) {
+        for (int c = 0; c < chunks_all; ++c) {
           const bool ex = c >= chunks;            // extra 1x1 chunk: centre tap only
-          const int ntap = ex ? 1 : TAPS;
-          const int as = ia % ast;
           long long tw = probe ? clock64() : 0;
-          mbar_wait(a_full(as), (ia / ast) & 1);
+          mbar_wait(a_full(as), aph);
           if (probe) wait_a += clock64() - tw;
           const uint32_t a_lo_stage = a_lo0 + ((as * a_stage_bytes) >> 4);
-          int bs = ib % BST;
-          uint32_t bph = (ib / BST) & 1;
-          int dh = ex ? 0 : -1, dw = ex ? 0 : -1; // tap offsets without div/mod
-#pragma unroll 1
-          for (int t = 0; t < ntap; ++t, ++ib) {
+          // The issuing thread runs at most about one MMA ahead of the tensor core, so every instruction between two
+          // MMAs beyond ~1 MMA time is exposed.  Hence: taps fully unrolled (their A shifts fold to constants), the
+          // release of the previous tap's B stage and the look-ahead probe of the next one are issued BETWEEN the first
+          // MMAs of the current tap (hidden behind their execution) instead of at the tap boundary.
+          int prev_bs = -1;                        // B stage whose release (commit) is still owed
+          auto tap_body = [&](const int shift, const int t) {
             int nbs = bs + 1;
             uint32_t nbph = bph;
             if (!BRES) {
@@ -416,33 +450,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
                 mbar_wait(b_full(bs), bph);
                 if (probe) wait_b += clock64() - tw;
               }
-              // look ahead: next B stage (also across chunk / tile boundaries)
               if (nbs == BST) { nbs = 0; nbph ^= 1; }
-              tw = probe ? clock64() : 0;
-              b_ready = mbar_try_wait(b_full(nbs), nbph);     // one probe only; if not there yet, block next time
-              if (probe) wait_b += clock64() - tw;
               tc_fence_after();
             } else if (t == 0) {
               tc_fence_after();
             }
-            const int shift = (TAPS == 9) ? (dh * a.Wp + dw + halo) : 0;
             const uint32_t a_lo_tap = a_lo_stage + (uint32_t)shift;          // one position = one 16-byte unit
             const uint32_t b_lo_tap = b_lo0 + (((BRES ? t : bs) * kBStageBytes) >> 4);
             if (!(dbg & 1)) {
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-                for (int acc = 0; acc < NACC; ++acc)
-                  umma_lohi(tmem_acc + acc * NT, a_lo_tap + kk * a_kstep + acc * 128, desc_hi, b_lo_tap + kk * b_kstep, desc_hi,
-                            idesc, (kk == 0) ? accumulate : 1u);
-              }
+              static_for<4>([&](auto kk_c) {
+                constexpr int kk = decltype(kk_c)::value;
+                const uint32_t a_lo_k = a_lo_tap + kk * a_kstep;
+                static_for<NACC>([&](auto acc_c) {
+                  constexpr int acc = decltype(acc_c)::value;
+                  umma_off<acc * 128, kk * (int)b_kstep, acc * NT>(tmem_acc, a_lo_k, desc_hi, b_lo_tap, desc_hi, idesc,
+                                                                   (kk == 0) ? accumulate : 1u);
+                  if (!BRES && kk == 0 && acc == 0 && prev_bs >= 0) umma_commit(b_empty(prev_bs));   // (also covers the MMA above)
+                  if (!BRES && (NACC > 1 ? (kk == 0 && acc == 1) : (kk == 1))) {
+                    // look ahead: next B stage (also across chunk / tile boundaries); one probe only -- if it is not there
+                    // yet, block at the top of the next tap.  Deadlock-free: that slot was released by a tap already issued
+                    // or is released by the commit just above.
+                    b_ready = mbar_try_wait(b_full(nbs), nbph);
+                  }
+                });
+              });
+            } else if (!BRES) {
+              if (prev_bs >= 0) umma_commit(b_empty(prev_bs));
+              b_ready = mbar_try_wait(b_full(nbs), nbph);
             }
             accumulate = 1u;
-            if (!BRES) umma_commit(b_empty(bs));       // B stage reusable once these MMAs retire
+            prev_bs = bs;
             bs = nbs; bph = nbph;
-            if (++dw == 2) { dw = -1; ++dh; }
+          };
+          if (ex || TAPS == 1) {
+            tap_body(halo, 0);
+          } else {
+            // resident weights: one kernel row (36 MMAs) per unrolled body -- all 108 at once make the compiler spill
+            // uniform registers between the MMAs (measured 70 vs 56 cycles per MMA)
+            int row0 = halo - a.Wp;
+#pragma unroll(BRES ? 1 : 3)
+            for (int r = 0; r < 3; ++r, row0 += a.Wp) {
+#pragma unroll
+              for (int d = 0; d < 3; ++d) tap_body(row0 + d - 1, r * 3 + d);
+            }
           }
+          if (!BRES) umma_commit(b_empty(prev_bs));      // last tap of the chunk
           umma_commit(a_empty(as));
+          if (++as == ast) { as = 0; aph ^= 1; }
         }
         umma_commit(acc_full(s));
       }

@@ -22,6 +22,15 @@ __device__ __forceinline__ uint64_t desc(uint32_t addr, uint32_t lbo, uint32_t s
          ((uint64_t)layout << 61);
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// ELECT: issue from an elect.sync region (the compiler then emits bare UTCHMMA) instead of behind `threadIdx.x == 0`
+// (every UTCHMMA wrapped in an ELECT + BRA.U.ANY loop)
+template <bool ELECT>
 __global__ void bench(int M, int N, int nacc, int layout_a, int layout_b, int a_off, int iters, int same_addr, long long* out, int commit_every) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -38,7 +47,7 @@ __global__ void bench(int M, int N, int nacc, int layout_a, int layout_b, int a_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tb = tslot;
-  if (threadIdx.x == 0) {
+  if (ELECT ? (threadIdx.x < 32 && elect_one()) : (threadIdx.x == 0)) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
     const uint32_t sA = smem_u32(smem), sB = sA + 96 * 1024;
     // no-swizzle: compact K-major planes: row stride 16 B, SBO 128, LBO = rows*16
@@ -77,24 +86,30 @@ __global__ void bench(int M, int N, int nacc, int layout_a, int layout_b, int a_
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
 }
 
+template <bool ELECT>
+int sweep(long long* out) {
+  const int iters = 2048;
+  cudaFuncSetAttribute(bench<ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  for (int M : {128, 64})
+    for (int N : {32, 64, 128, 256})
+      for (int gap : {0, -1, 100, 200}) {
+        int nacc = 512 / N > 4 ? 4 : 512 / N;
+        long long h[148];
+        bench<ELECT><<<148, 128, 200 * 1024>>>(M, N, nacc, 0, 0, 0, iters, 0, out, gap);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+        cudaMemcpy(h, out, 148 * 8, cudaMemcpyDeviceToHost);
+        long long mx = 0;
+        for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+        printf("elect %d M %3d N %3d nacc %d gap %5d (cycles idle per 16 MMAs; -1 = one commit): %.1f cycles/MMA\n", (int)ELECT, M, N, nacc, gap,
+               (double)mx / iters);
+      }
+  return 0;
+}
+
 int main() {
   long long* out;
   cudaMalloc(&out, 148 * 8);
-  cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const int iters = 2048;
-  printf("%4s %4s %4s %3s %3s %5s %5s | cycles/MMA (1 CTA)   cycles/MMA (148 CTAs)  ideal\n", "M", "N", "nacc", "lA", "lB", "a_off", "same");
-  for (int N : {64, 128, 256})
-    for (int gap : {0, -1, 100, 200, 400, 800, 1600}) {
-      int nacc = 512 / N > 4 ? 4 : 512 / N;
-      long long h[148];
-      bench<<<148, 128, 200 * 1024>>>(128, N, nacc, 0, 0, 0, iters, 0, out, gap);
-      cudaError_t e = cudaDeviceSynchronize();
-      if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
-      cudaMemcpy(h, out, 148 * 8, cudaMemcpyDeviceToHost);
-      long long mx = 0;
-      for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
-      printf("N %3d nacc %d gap %5d cycles per 16 MMAs (-1 = one commit): %.1f cycles/MMA  (%.0f cycles per group)\n", N, nacc, gap,
-             (double)mx / iters, (double)mx / iters * 16);
-    }
-  return 0;
+  if (sweep<false>(out)) return 1;
+  return sweep<true>(out);
 }

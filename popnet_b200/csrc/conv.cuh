@@ -104,6 +104,27 @@ struct PosInfo {
   int n, h, w;
 };
 __host__ __device__ inline long long c8p_positions(int N, int H, int W) { return (long long)(2 + (long long)N * (H + 1)) * (W + 1); }
+// Division by a loop-invariant divisor d (2 <= d < 2^16): q = umulhi(n, magic(d)) over-estimates n / d by at most one for
+// every 32-bit n; one multiply-subtract and a conditional fix-up make it exact (4 instructions instead of ~20).
+__host__ __device__ inline uint32_t div_magic(int d) { return 0xFFFFFFFFu / (uint32_t)d + 1u; }
+__device__ __forceinline__ void fast_divmod(int n, int d, uint32_t magic, int& q, int& r) {
+  q = (int)__umulhi((uint32_t)n, magic);
+  r = n - q * d;
+  if (r < 0) { --q; r += d; }
+}
+// same as c8p_locate with the two divisions by magic numbers (mWp = div_magic(Wp), mHs = div_magic(Hs))
+__device__ __forceinline__ PosInfo c8p_locate_fast(int pos, int P, int Hs, int Wp, uint32_t mHs, uint32_t mWp) {
+  PosInfo r;
+  r.in_range = pos < P;
+  int row, c;
+  fast_divmod(pos, Wp, mWp, row, c);
+  const int rr = row - 2;
+  int n = 0, h = rr;
+  if (rr >= 0) fast_divmod(rr, Hs, mHs, n, h);
+  r.interior = r.in_range && rr >= 0 && c < Wp - 1 && h < Hs - 1;
+  r.n = n; r.h = h; r.w = c;
+  return r;
+}
 __device__ __forceinline__ PosInfo c8p_locate(int pos, int P, int Hs, int Wp) {
   PosInfo r;
   r.in_range = pos < P;

@@ -21,6 +21,7 @@
 // stem and the pools.
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <cstdlib>
 #include <type_traits>
 #include <utility>
 
@@ -265,8 +266,13 @@ __device__ __forceinline__ uint4 finish8_fast(const uint32_t* acc, const float* 
       x[2 * i + 1] += f.y;
     }
   }
+  if (slope == 0.f) {                                                // warp-uniform: ReLU without the multiply
 #pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], slope * x[i]);      // slope in [0,1]: ReLU 0, LeakyReLU 0.1, identity 1
+    for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], slope * x[i]);    // slope in (0,1]: LeakyReLU 0.1, identity 1
+  }
   uint4 o;
   o.x = pack2(x[0], x[1], fmt); o.y = pack2(x[2], x[3], fmt); o.z = pack2(x[4], x[5], fmt); o.w = pack2(x[6], x[7], fmt);
   if (!interior) o = make_uint4(0u, 0u, 0u, 0u);                     // padding ring stays zero
@@ -509,6 +515,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
     const int sub = (warp - kEpiWarp0) >> 2;            // 0..3: the four warps of a lane quarter split the work items
     const bool head = a.act == kActHeadPaf || a.act == kActHeadHeat;
     const float slope = a.act == kActRelu ? 0.f : (a.act == kActLeaky ? 0.1f : 1.f);
+    const uint32_t mHs = div_magic(a.Hs), mWp = div_magic(a.Wp);
     long long wait_full = 0, busy = 0;
     int ti = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
@@ -526,7 +533,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
         for (int it = sub; it < kItems; it += 4) {
           const int acc = it / (NT / 16), j = it - acc * (NT / 16);
           const int pos = t0 + acc * 128 + q * 32 + lane;
-          const PosInfo pi = locate(pos, a);
+          const PosInfo pi = c8p_locate_fast(pos, a.P, a.Hs, a.Wp, mHs, mWp);
           uint32_t r[16];
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + acc * NT + j * 16), r);
           tmem_ld_wait();
@@ -544,7 +551,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
         for (int it = sub; it < kItems; it += 4) {
           const int acc = it / (NT / 32), j = it - acc * (NT / 32);
           const int pos = t0 + acc * 128 + q * 32 + lane;
-          const PosInfo pi = locate(pos, a);
+          const PosInfo pi = c8p_locate_fast(pos, a.P, a.Hs, a.Wp, mHs, mWp);
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + acc * NT + j * 32), r);
           const int plane = (j * 32) >> 3;
@@ -632,7 +639,7 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvArgs a) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kStemThreads = 128;
 
-__global__ void __launch_bounds__(kStemThreads) stem_kernel(const StemArgs a) {
+__global__ void __launch_bounds__(kStemThreads, 8) stem_kernel(const StemArgs a) {
   __shared__ __align__(128) h16 sA[8 * 128 * 8];          // [k8][row][8]
   __shared__ __align__(128) h16 sB[8 * 64 * 8];           // [k8][cout][8]
   __shared__ float s_shift[64];
@@ -660,37 +667,45 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const StemArgs a) {
   const uint32_t tmem_base = s_tmem;
   const uint32_t idesc = umma_idesc(64, a.fmt);
   uint32_t phase = 0;
+  const uint32_t mHs = div_magic(Hs), mWp = div_magic(Wp);
   pdl_launch_dependents();
   pdl_wait();
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int pos = tile * 128 + tid;
-    const PosInfo pi = c8p_locate(pos, P, Hs, Wp);
+    const PosInfo pi = c8p_locate_fast(pos, P, Hs, Wp, mHs, mWp);
     const int n = pi.n;
     const bool interior = pi.interior;
     // ---- im2col: K = 8 input rows x 8 input columns (rows 2oy-3 .. 2oy+4, columns 2ox-4 .. 2ox+3; the 7x7 kernel
     // occupies rows 0..6 / columns 1..7, the extra row and column carry zero weights).  One k8 group = one input
     // row = four aligned float2 loads, packed straight into the 16-byte operand vector.
     {
-      const float* img = a.x + (long long)n * a.H * a.W;
       const int iy0 = pi.h * 2 - 3, ix0 = pi.w * 2 - 4;
-      float2 v[8][4];                                    // all 32 loads are issued before the first use
+      // one base pointer (possibly outside the image: only dereferenced under its predicate), four column predicates
+      // shared by all rows, one unsigned compare per row
+      const float* p0 = a.x + ((long long)n * a.H + iy0) * a.W + ix0;
+      bool cok[4];
 #pragma unroll
-      for (int ry = 0; ry < 8; ++ry) {
-        const int iy = iy0 + ry;
-        const bool rok = interior && iy >= 0 && iy < a.H;
-        const float* row = img + (long long)(rok ? iy : 0) * a.W;
+      for (int j = 0; j < 4; ++j) cok[j] = interior && (unsigned)(ix0 + 2 * j) < (unsigned)a.W;   // even: the pair is in or out together
+      // two batches of four rows: 16 loads in flight per thread (the 6-8 co-resident CTAs supply the rest of the
+      // memory-level parallelism) and half the registers of a single 32-load batch
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int ix = ix0 + 2 * j;                      // even: the pair (ix, ix+1) is inside or outside together
-          const bool ok = rok && ix >= 0 && ix < a.W;
-          v[ry][j] = ok ? __ldg(reinterpret_cast<const float2*>(row + ix)) : make_float2(0.f, 0.f);
+      for (int half = 0; half < 2; ++half) {
+        float2 v[4][4];
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+          const int ry = half * 4 + r4;
+          const bool rok = (unsigned)(iy0 + ry) < (unsigned)a.H;
+          const float* row = p0 + ry * a.W;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[r4][j] = (rok && cok[j]) ? __ldg(reinterpret_cast<const float2*>(row + 2 * j)) : make_float2(0.f, 0.f);
         }
-      }
 #pragma unroll
-      for (int ry = 0; ry < 8; ++ry)
-        reinterpret_cast<uint4*>(sA)[ry * 128 + tid] =
-            make_uint4(pack2(v[ry][0].x, v[ry][0].y, a.fmt), pack2(v[ry][1].x, v[ry][1].y, a.fmt),
-                       pack2(v[ry][2].x, v[ry][2].y, a.fmt), pack2(v[ry][3].x, v[ry][3].y, a.fmt));
+        for (int r4 = 0; r4 < 4; ++r4)
+          reinterpret_cast<uint4*>(sA)[(half * 4 + r4) * 128 + tid] =
+              make_uint4(pack2(v[r4][0].x, v[r4][0].y, a.fmt), pack2(v[r4][1].x, v[r4][1].y, a.fmt),
+                         pack2(v[r4][2].x, v[r4][2].y, a.fmt), pack2(v[r4][3].x, v[r4][3].y, a.fmt));
+      }
     }
     // generic-proxy smem writes -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -849,6 +864,9 @@ int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st) {
   POPNET_TC_CASE(128, 2, 9, false)
   POPNET_TC_CASE(128, 4, 9, false)
   POPNET_TC_CASE(128, 3, 9, false)
+  POPNET_TC_CASE(128, 2, 1, false)
+  POPNET_TC_CASE(32, 2, 1, false)
+  POPNET_TC_CASE(16, 2, 9, false)
   POPNET_TC_CASE(128, 3, 1, false)
   POPNET_TC_CASE(64, 3, 9, false)
   POPNET_TC_CASE(32, 3, 1, false)
@@ -871,7 +889,11 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
 int launch_stem(const StemArgs& a, cudaStream_t st) {
   const int P = (int)c8p_positions(a.N, a.H / 2, a.W / 2);
   const int tiles = (P + 127) / 128;
-  const int grid = tiles < 148 * 6 ? tiles : 148 * 6;      // persistent: six CTAs per SM walk the tiles
+  int cps = 8;
+  if (const char* e = getenv("POPNET_STEM_CPS")) cps = atoi(e);
+  static bool once = false;
+  if (!once) { cudaFuncSetAttribute(stem_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); once = true; }
+  const int grid = tiles < 148 * cps ? tiles : 148 * cps;      // persistent: `cps` CTAs per SM walk the tiles
   cudaLaunchConfig_t cfg = pdl_config(dim3(grid), dim3(kStemThreads), 0, st);
   POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, stem_kernel, a));
   POPNET_AFTER_LAUNCH();

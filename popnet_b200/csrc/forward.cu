@@ -101,16 +101,19 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   add(64, 64, 3, 64, 3, kActRelu, C112, 0, B112, 0, -1, 0, 0, 0);           // 3 layer1.1.conv1
   add(64, 64, 3, 64, 3, kActRelu, B112, 0, A112, 0, C112, 0, 0, 0);         // 4 layer1.1.conv2 (+x)
   add(64, 128, 3, 128, 2, kActRelu, D56, 0, E56, 0, -1, 0, 0, 0);           // 5 layer2.0.conv1
-  add(128, 128, 3, 128, 4, kActRelu, E56, 0, G56, 0, -1, 0, 0, 0);          // 6 layer2.0.conv2, projection shortcut fused:
+  int n6 = 4, n8 = 4;
+  if (const char* e = getenv("POPNET_L6_NACC")) n6 = atoi(e);
+  if (const char* e = getenv("POPNET_L8_NACC")) n8 = atoi(e);
+  add(128, 128, 3, 128, n6, kActRelu, E56, 0, G56, 0, -1, 0, 0, 0);         // 6 layer2.0.conv2, projection shortcut fused:
   p.layers.back().fuse_layer = 7; p.layers.back().in2_buf = D56;            //   relu(bn2(conv2(e)) + bn_d(conv1x1(d))) as ONE K = 9*128 + 64 GEMM
   add(64, 128, 1, 128, 4, kActNone, D56, 0, F56, 0, -1, 0, 0, 0);           // 7 layer2.0.downsample (weights only; never launched)
-  add(128, 128, 1, 128, 4, kActRelu, G56, 0, E56, 0, -1, 0, 0, 0);          // 8 conv2
+  add(128, 128, 1, 128, n8, kActRelu, G56, 0, E56, 0, -1, 0, 0, 0);         // 8 conv2
   const int K1 = p.K + 1, L2 = 2 * p.L, L1 = p.L + 1;
   // 28x28 stage layers: 512-position tiles.  At batch 64 the 53,882 positions make 106 tiles (72 % of the 148 SMs), 384-position
   // tiles (POPNET_STAGE_NACC=3) make 141 (95 %); measured identical (1.065 vs 1.067 ms per forward) because the three concurrent
   // branches already fill each other's idle SMs.
   int kStageNacc = 4;
-  if (const char* e = getenv("POPNET_STAGE_NACC")) { const int v = atoi(e); if (v == 3 || v == 4) kStageNacc = v; }
+  if (const char* e = getenv("POPNET_STAGE_NACC")) { const int v = atoi(e); if (v >= 2 && v <= 4) kStageNacc = v; }
   for (int s = 1; s <= 2; ++s) {
     const int in0 = (s == 1) ? (p.pl + p.ph + p.pd) / 8 : 0;     // stage 1 reads only the feature planes
     const int cin = (s == 1) ? 128 : 128 + L2 + K1 + L1;

@@ -66,7 +66,7 @@ def build(force=False, verbose=False):
         failed |= pr.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [NVCC, *ARCH, "-shared", "-o", OUT, *objs, "-lcudart", "-lcuda"]
+    link = [NVCC, *ARCH, "-shared", "-Xlinker", "--no-undefined", "-o", OUT, *objs, "-lcudart", "-lcuda"]
     subprocess.run(link, check=True)
     with open(STAMP, "w") as f:
         f.write(digest)

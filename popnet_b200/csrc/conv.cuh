@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -67,6 +68,7 @@ struct ConvArgs {
   int fmt;                      // 0 = bf16, 1 = fp16 operands
   long long* probe;             // optional [gridDim.x][16] clock64 stamps (bring-up / tuning), else nullptr
   int dbg;                      // bring-up switches: 1 = skip MMA issue, 2 = skip epilogue stores
+  unsigned long long* trace;    // optional [3] globaltimer stamps {first CTA in, first CTA past griddepcontrol.wait, last CTA out}
 };
 
 struct StemArgs {
@@ -77,6 +79,7 @@ struct StemArgs {
   long long out_plane_stride;
   int N, H, W;                  // input size
   int fmt;
+  unsigned long long* trace;
 };
 
 struct PoolArgs {
@@ -87,8 +90,14 @@ struct PoolArgs {
   int planes;
   int N, H, W;                  // input spatial size (output is H/2 x W/2)
   int fmt;
+  unsigned long long* trace;
 };
 
+// timeline tracing state (conv_kernels.cu); set through popnet_debug_trace (forward.cu)
+extern unsigned long long* g_trace_buf;
+extern int g_trace_cap;
+extern std::atomic<int> g_trace_next;
+extern int g_trace_tags[1024];
 int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st);
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int launch_stem(const StemArgs& a, cudaStream_t st);

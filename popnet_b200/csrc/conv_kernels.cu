@@ -21,6 +21,7 @@
 // stem and the pools.
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <atomic>
 #include <cstdlib>
 #include <type_traits>
 #include <utility>
@@ -28,6 +29,11 @@
 #include "conv.cuh"
 
 namespace popnet {
+// ---- timeline tracing: the debug entry points in forward.cu hand out one 4-word slot per launch
+unsigned long long* g_trace_buf = nullptr;
+int g_trace_cap = 0;
+std::atomic<int> g_trace_next{0};
+int g_trace_tags[1024];
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -293,6 +299,20 @@ constexpr int kEpiWarp0 = 4;
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Timeline tracing (tools/forward_timeline.py): per launch three globaltimer stamps, reduced over the CTAs with atomics.
+// `tr` is nullptr in normal operation.
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_min(unsigned long long* tr, int slot) {
+  if (tr && threadIdx.x == 0) atomicMin(tr + slot, gtime());
+}
+__device__ __forceinline__ void trace_max(unsigned long long* tr, int slot) {
+  if (tr && threadIdx.x == 0) atomicMax(tr + slot, gtime());
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -345,6 +365,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   long long* probe = (DBG && a.probe) ? a.probe + (long long)blockIdx.x * 16 : nullptr;
   const int dbg = DBG ? a.dbg : 0;
   if (probe && threadIdx.x == 0) probe[0] = clock64();
+  trace_min(a.trace, 0);
   const int chunks = a.chunks;
   const int chunks_all = chunks + (BRES ? 0 : a.chunks2);
   const int k8_total = chunks * 8;
@@ -364,6 +385,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                 // activations of the previous layer are complete and visible from here on
+  trace_min(a.trace, 1);
   if (probe && threadIdx.x == 0) probe[1] = clock64();
 
   if (warp == 0) {
@@ -547,6 +569,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
         }
       } else if constexpr (NT >= 32) {
         constexpr int kItems = NACC * (NT / 32);
+        // Residual layers: this warp's residual vectors of its NEXT tile are pulled into L2 now (one 128-byte line per
+        // 8 lanes), one epilogue ahead of their use -- the residual tensor was written two layers ago and has left the
+        // L2; without this the epilogue of the 64-channel residual layers waits on DRAM and outlasts the MMA phase.
+        if (a.res != nullptr && tile + (int)gridDim.x < num_tiles && (lane & 7) == 0) {
+          const int tn0 = (tile + (int)gridDim.x) * MT;
+#pragma unroll 1
+          for (int it = sub; it < kItems; it += 4) {
+            const int acc = it / (NT / 32), j = it - acc * (NT / 32);
+            const int pos = tn0 + acc * 128 + q * 32 + lane;
+            if (pos < a.P) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + (long long)(j * 4 + g) * a.res_plane_stride + (long long)pos * 8));
+            }
+          }
+        }
 #pragma unroll 1
         for (int it = sub; it < kItems; it += 4) {
           const int acc = it / (NT / 32), j = it - acc * (NT / 32);
@@ -583,6 +621,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   tc_fence_before();
   __syncthreads();
   if (probe && threadIdx.x == 0) probe[8] = clock64();
+  trace_max(a.trace, 2);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kCols);
@@ -668,8 +707,10 @@ __global__ void __launch_bounds__(kStemThreads, 8) stem_kernel(const StemArgs a)
   const uint32_t idesc = umma_idesc(64, a.fmt);
   uint32_t phase = 0;
   const uint32_t mHs = div_magic(Hs), mWp = div_magic(Wp);
+  trace_min(a.trace, 0);
   pdl_launch_dependents();
   pdl_wait();
+  trace_min(a.trace, 1);
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int pos = tile * 128 + tid;
     const PosInfo pi = c8p_locate_fast(pos, P, Hs, Wp, mHs, mWp);
@@ -742,6 +783,7 @@ __global__ void __launch_bounds__(kStemThreads, 8) stem_kernel(const StemArgs a)
     tc_fence_after();
   }
   __syncthreads();
+  trace_max(a.trace, 2);
   if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
 
@@ -752,8 +794,11 @@ __global__ void __launch_bounds__(128) pool_kernel(const PoolArgs a) {
   const int Ho = a.H / 2, Wo = a.W / 2, Wpi = a.W + 1, Hsi = a.H + 1;
   const int P = (int)c8p_positions(a.N, Ho, Wo);
   const int pos = blockIdx.x * 128 + threadIdx.x;
+  trace_min(a.trace, 0);
   pdl_launch_dependents();
   pdl_wait();
+  trace_min(a.trace, 1);
+  trace_max(a.trace, 2);              // (entry of the last CTA; a pool CTA lives ~1 us)
   if (pos >= P) return;
   const int g = blockIdx.y;
   const PosInfo pi = c8p_locate(pos, P, Ho + 1, Wo + 1);
@@ -785,6 +830,14 @@ __global__ void __launch_bounds__(128) pool_kernel(const PoolArgs a) {
   *reinterpret_cast<uint4*>(a.out + (long long)g * a.out_plane_stride + (long long)pos * 8) = *reinterpret_cast<const uint4*>(ob);
 }
 
+unsigned long long* next_trace_slot(int tag) {
+  if (!g_trace_buf) return nullptr;
+  const int i = g_trace_next.fetch_add(1);
+  if (i >= g_trace_cap || i >= 1024) return nullptr;
+  g_trace_tags[i] = tag;
+  return g_trace_buf + 4 * (size_t)i;
+}
+
 // launch configuration with programmatic stream serialization (PDL) enabled
 cudaLaunchAttribute g_pdl_attr[1];
 cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
@@ -807,7 +860,9 @@ int launch_tc_inst(const ConvArgs& a, size_t smem, cudaStream_t st) {
   const int tiles = (a.P + MT - 1) / MT;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;        // persistent: one CTA per SM walks the tiles
   cudaLaunchConfig_t cfg = pdl_config(dim3(grid), dim3(kTcThreads), smem, st);
-  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+  ConvArgs at = a;
+  at.trace = next_trace_slot(NT * 1000 + NACC * 100 + TAPS * 10);
+  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, at));
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }
@@ -895,7 +950,9 @@ int launch_stem(const StemArgs& a, cudaStream_t st) {
   if (!once) { cudaFuncSetAttribute(stem_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); once = true; }
   const int grid = tiles < 148 * cps ? tiles : 148 * cps;      // persistent: `cps` CTAs per SM walk the tiles
   cudaLaunchConfig_t cfg = pdl_config(dim3(grid), dim3(kStemThreads), 0, st);
-  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, stem_kernel, a));
+  StemArgs at = a;
+  at.trace = next_trace_slot(1);
+  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, stem_kernel, at));
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }
@@ -904,7 +961,9 @@ int launch_pool(const PoolArgs& a, cudaStream_t st) {
   const int P = (int)c8p_positions(a.N, a.H / 2, a.W / 2);
   dim3 grid((P + 127) / 128, a.planes);
   cudaLaunchConfig_t cfg = pdl_config(grid, dim3(128), 0, st);
-  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, pool_kernel, a));
+  PoolArgs at = a;
+  at.trace = next_trace_slot(2);
+  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, pool_kernel, at));
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }

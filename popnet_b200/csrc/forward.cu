@@ -14,6 +14,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -101,13 +102,10 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   add(64, 64, 3, 64, 3, kActRelu, C112, 0, B112, 0, -1, 0, 0, 0);           // 3 layer1.1.conv1
   add(64, 64, 3, 64, 3, kActRelu, B112, 0, A112, 0, C112, 0, 0, 0);         // 4 layer1.1.conv2 (+x)
   add(64, 128, 3, 128, 2, kActRelu, D56, 0, E56, 0, -1, 0, 0, 0);           // 5 layer2.0.conv1
-  int n6 = 4, n8 = 4;
-  if (const char* e = getenv("POPNET_L6_NACC")) n6 = atoi(e);
-  if (const char* e = getenv("POPNET_L8_NACC")) n8 = atoi(e);
-  add(128, 128, 3, 128, n6, kActRelu, E56, 0, G56, 0, -1, 0, 0, 0);         // 6 layer2.0.conv2, projection shortcut fused:
+  add(128, 128, 3, 128, 4, kActRelu, E56, 0, G56, 0, -1, 0, 0, 0);         // 6 layer2.0.conv2, projection shortcut fused:
   p.layers.back().fuse_layer = 7; p.layers.back().in2_buf = D56;            //   relu(bn2(conv2(e)) + bn_d(conv1x1(d))) as ONE K = 9*128 + 64 GEMM
   add(64, 128, 1, 128, 4, kActNone, D56, 0, F56, 0, -1, 0, 0, 0);           // 7 layer2.0.downsample (weights only; never launched)
-  add(128, 128, 1, 128, n8, kActRelu, G56, 0, E56, 0, -1, 0, 0, 0);         // 8 conv2
+  add(128, 128, 1, 128, 4, kActRelu, G56, 0, E56, 0, -1, 0, 0, 0);         // 8 conv2
   const int K1 = p.K + 1, L2 = 2 * p.L, L1 = p.L + 1;
   // 28x28 stage layers: 512-position tiles.  At batch 64 the 53,882 positions make 106 tiles (72 % of the 148 SMs), 384-position
   // tiles (POPNET_STAGE_NACC=3) make 141 (95 %); measured identical (1.065 vs 1.067 ms per forward) because the three concurrent
@@ -351,6 +349,9 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
   // The three branches of a stage are independent 5-conv chains on the same input: run the heat-map and
   // depth branches on two auxiliary streams so that their CTAs fill the SMs the (two-wave) PAF branch
   // leaves idle.  Fork/join through events keeps the whole forward capturable in a CUDA graph.
+  // (Measured alternative, rejected: giving each chain a fixed SM partition -- e.g. 80/38/30 persistent CTAs -- so
+  // that all three run side by side from the start: 1.13 ms per forward instead of 0.97; the CTA-time of the stage
+  // layers is the same either way and the shared-queue schedule below is already work-conserving.)
   AuxStreams* aux = aux_streams(st);
   if (!aux) return POPNET_ERR_CUDA;
   for (int s = 1; s <= 2; ++s) {
@@ -398,4 +399,18 @@ extern "C" __attribute__((visibility("default"))) int popnet_debug_conv(const Po
   a.cout = d->cout; a.cout_pad = d->cout_pad; a.nt = d->nt; a.taps = d->taps; a.fmt = d->fmt; a.dbg = d->dbg; a.probe = d->probe;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return d->impl == POPNET_FWD_IMPL_SIMT ? launch_conv_simt(a, st) : launch_conv_tc(a, d->nacc, st);
+}
+
+// Timeline tracing hook (not in the public header; tools/forward_timeline.py).  buf: device array of 4*cap uint64 words,
+// initialised by the caller to {~0, ~0, 0, 0} per slot; every conv / stem / pool launch after this call takes the next
+// slot.  Call with buf = nullptr to stop; returns the number of slots handed out and copies their tags
+// (NT*1000 + NACC*100 + TAPS*10 for conv_tc, 1 = stem, 2 = pool) into tags_out.
+extern "C" __attribute__((visibility("default"))) int popnet_debug_trace(unsigned long long* buf, int cap, int* tags_out, int max_tags) {
+  const int n = popnet::g_trace_next.load() < popnet::g_trace_cap ? popnet::g_trace_next.load() : popnet::g_trace_cap;
+  if (tags_out)
+    for (int i = 0; i < n && i < max_tags && i < 1024; ++i) tags_out[i] = popnet::g_trace_tags[i];
+  popnet::g_trace_buf = buf;
+  popnet::g_trace_cap = buf ? cap : 0;
+  popnet::g_trace_next.store(0);
+  return n;
 }

@@ -27,7 +27,7 @@ LAYERS_ALL = [("64->64@112", 64, 2, 9, 64, 64, 112), ("64->64@112 acc3", 64, 3, 
           ("128->128@56", 128, 4, 9, 128, 128, 56), ("1x1 128->128@56", 128, 4, 1, 128, 128, 56),
           ("256->256@28", 256, 2, 9, 256, 256, 28), ("128->128@28", 128, 4, 9, 128, 128, 28),
           ("64->64@28", 64, 4, 9, 64, 64, 28)]
-LAYERS = [l for l in LAYERS_ALL if l[0] in ("64->64@112 acc3", "128->128@56", "128->128@56 acc2", "128->128@28", "128->128@28 acc2", "64->128@56", "64->128@56 acc4", "256->256@28")]
+LAYERS = [l for l in LAYERS_ALL if l[0] in ("128->128@28", "256->256@28") or l[0] in ("none",) and l[0] in ("64->64@112 acc3", "128->128@56", "128->128@56 acc2", "128->128@28", "128->128@28 acc2", "64->128@56", "64->128@56 acc4", "256->256@28")]
 for name, nt, nacc, taps, cin, cout, H in LAYERS:
     N = a.batch
     P = (2 + N * (H + 1)) * (H + 1)
@@ -57,7 +57,7 @@ for name, nt, nacc, taps, cin, cout, H in LAYERS:
         torch.cuda.synchronize()
         t = e0.elapsed_time(e1) / 5 * 1e3
         print("%-18s %-18s %8.1f us  %7.1f TFLOP/s  (%d CTAs)" % (name, label, t, flops / t / 1e6, ncta))
-    for dbg in (0,):
+    for dbg in (0, 2):
         d.dbg = dbg
         d.probe = probe.data_ptr()
         lib.popnet_debug_conv(C.byref(d), None)

@@ -944,8 +944,7 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
 int launch_stem(const StemArgs& a, cudaStream_t st) {
   const int P = (int)c8p_positions(a.N, a.H / 2, a.W / 2);
   const int tiles = (P + 127) / 128;
-  int cps = 8;
-  if (const char* e = getenv("POPNET_STEM_CPS")) cps = atoi(e);
+  const int cps = 8;                    // CTAs per SM (TMEM: 8 x 64 columns; registers: 8 x 128 x 64); 4 / 6 / 8 measured equal
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(stem_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); once = true; }
   const int grid = tiles < 148 * cps ? tiles : 148 * cps;      // persistent: `cps` CTAs per SM walk the tiles

@@ -137,6 +137,72 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
+def evaluator_leg(n_frames=4000, iters=20, with_cpu=True):
+    """Secondary metric of SURVEY.md 8(d): the best-match evaluator (3D PCK matching + 3D mAP assignment) on the C3 set.
+    `device`: kernels only, CSR arrays resident in HBM (CUDA events); `e2e`: the public reference-signature calls on
+    the ragged Python lists (host packing, H2D, kernels, D2H, AP tail); `cpu_port`: the C oracle on the same arrays."""
+    import io
+    import contextlib
+    import torch
+    from popnet_b200 import evaluate, synth, topology
+    from popnet_b200._cuda_backend import CudaBackend, _to_dev
+    K = 15
+    es = synth.eval_set(n_frames, seed=0)
+    names = list(topology.JOINT_NAMES)
+    captured = {}
+    be = CudaBackend()
+
+    class Tap:                                     # records the packed CSR arrays the public API hands to the backend
+        def pck(self, arrs, **kw):
+            captured["pck"] = (arrs, kw)
+            return be.pck(arrs, **kw)
+
+        def map_assign(self, arrs, **kw):
+            captured["map"] = (arrs, kw)
+            return be.map_assign(arrs, **kw)
+
+    evaluate._backend = Tap()
+    sink = io.StringIO()
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(sink):
+        evaluate.eval_human_dataset_3d(es["pred2d"], es["gt2d"], es["pred3d"], es["gt3d"], K, 0.1, 0.5)
+        evaluate.eval_ap_3D(es["pred3d"], es["conf"], es["gt3d"], [], names, 0.1)
+    e2e_s = time.perf_counter() - t0
+    evaluate._backend = None
+    (pa, pkw), (ma, mkw) = captured["pck"], captured["map"]
+    dp = {k: _to_dev(v) for k, v in pa.items()}
+    dm = {k: _to_dev(v) for k, v in ma.items()}
+    op = be.pck_device(dp, **pkw)
+    om = be.map_assign_device(dm, **mkw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        be.pck_device(dp, out=op, **pkw)
+        be.map_assign_device(dm, out=om, **mkw)
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / iters
+    n_pred, n_gt = int(pa["pred2d"].shape[0]), int(pa["gt2d"].shape[0])
+    alg_bytes = 8 * K * (n_pred * (2 + 3 + 1) + n_gt * (2 + 3)) + 8 * K * n_gt          # SURVEY 8(d): reads + distances written
+    res = {"workload": "C3: %d frames, %d GT / %d predicted humans; eval_human_dataset_3d + eval_ap_3D" % (n_frames, n_gt, n_pred),
+           "device": {"value": n_frames / (dev_ms * 1e-3), "unit": "frames/s", "ms": dev_ms, "launches": 2,
+                      "achieved_GBps": alg_bytes / (dev_ms * 1e-3) / 1e9, "algorithmic_bytes": alg_bytes,
+                      "bound": "hbm (latency-bound: one warp per frame; the 19 MB of CSR arrays stay in the 126 MB L2 between iterations)"},
+           "e2e": {"value": n_frames / e2e_s, "unit": "frames/s", "s": e2e_s,
+                   "note": "public API on ragged Python lists: list->CSR packing and the NumPy AP tail dominate"}}
+    if with_cpu:
+        from oracle.backend import OracleBackend          # checker / baseline only
+        ob = OracleBackend()
+        t0 = time.perf_counter()
+        ob.pck(pa, **pkw)
+        ob.map_assign(ma, **mkw)
+        cpu_s = time.perf_counter() - t0
+        res["cpu_port"] = {"value": n_frames / cpu_s, "unit": "frames/s", "s": cpu_s, "cores": 1,
+                           "what": "C oracle (oracle/popnet_oracle.c) on the same CSR arrays"}
+    return res
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -294,6 +360,8 @@ def run_ours(args, rank, local_rank, world):
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": "64 frames x 12 repeats: fp32 torch forward (%d threads) + C-oracle decode/lift "
                                           "over %d threads (%.1f s)" % (cores, cores, sum(ts))}
+    if world == 1 and not args.no_evaluator:
+        line["evaluator"] = evaluator_leg(with_cpu=not args.no_cpu_baseline)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -309,6 +377,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--rotate", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-evaluator", action="store_true", help="skip the secondary evaluator metric")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -88,40 +88,53 @@ class CudaBackend:
         self.lib = _lib.get()
 
     # ------------------------------------------------------------------ evaluator
-    def pck(self, arrs, *, dist_th, iou_th, K):
-        d = {k: _to_dev(v) for k, v in arrs.items()}
+    def pck_device(self, d, *, dist_th, iou_th, K, out=None):
+        """popnet_eval_pck on device-resident CSR tensors; returns device tensors (no synchronisation).  `out` may be
+        passed back in to reuse the result buffers."""
         SG = d["gt2d"].shape[0]
         N = d["gt_off"].shape[0] - 1
-        out = {"dists": torch.empty((SG, K), dtype=torch.float64, device="cuda"),
-               "hit": torch.empty((SG, K), dtype=torch.uint8, device="cuda"),
-               "matched_pred": torch.empty((SG,), dtype=torch.int32, device="cuda"),
-               "hit_cnt": torch.empty((K,), dtype=torch.int64, device="cuda"),
-               "valid_cnt": torch.empty((K,), dtype=torch.int64, device="cuda"),
-               "status": torch.zeros((max(N, 1),), dtype=torch.int32, device="cuda")}
+        if out is None:
+            out = {"dists": torch.empty((SG, K), dtype=torch.float64, device="cuda"),
+                   "hit": torch.empty((SG, K), dtype=torch.uint8, device="cuda"),
+                   "matched_pred": torch.empty((SG,), dtype=torch.int32, device="cuda"),
+                   "hit_cnt": torch.empty((K,), dtype=torch.int64, device="cuda"),
+                   "valid_cnt": torch.empty((K,), dtype=torch.int64, device="cuda"),
+                   "status": torch.zeros((max(N, 1),), dtype=torch.int32, device="cuda")}
         a = _abi.PckArgs(pred2d=_ptr(d["pred2d"]), pred3d=_ptr(d.get("pred3d")), pred_off=_ptr(d["pred_off"]),
                          gt2d=_ptr(d["gt2d"]), gt3d=_ptr(d.get("gt3d")), gt_off=_ptr(d["gt_off"]),
                          gt_vis=_ptr(d.get("gt_vis")), gt_thresh=_ptr(d.get("gt_thresh")),
                          dist_th=dist_th, iou_th=iou_th, num_frames=N, num_joints=K,
                          **{k: _ptr(v) for k, v in out.items()})
         _lib.check(self.lib.popnet_eval_pck(C.byref(a), _stream()), "popnet_eval_pck")
+        return out
+
+    def pck(self, arrs, *, dist_th, iou_th, K):
+        d = {k: _to_dev(v) for k, v in arrs.items()}
+        N = d["gt_off"].shape[0] - 1
+        out = self.pck_device(d, dist_th=dist_th, iou_th=iou_th, K=K)
         res = {k: v.cpu().numpy() for k, v in out.items()}
         res["status"] = res["status"][:N]
         return res
 
-    def map_assign(self, arrs, *, thresh, K, D):
-        d = {k: _to_dev(v) for k, v in arrs.items()}
+    def map_assign_device(self, d, *, thresh, K, D, out=None):
+        """popnet_eval_map_assign on device-resident CSR tensors; returns device tensors (no synchronisation)."""
         SP = d["pred"].shape[0]
         N = d["gt_off"].shape[0] - 1
-        out = {"labels": torch.zeros((SP, K), dtype=torch.uint8, device="cuda"),
-               "matched_gt": torch.full((SP,), -1, dtype=torch.int32, device="cuda"),
-               "n_gt": torch.empty((K,), dtype=torch.int64, device="cuda"),
-               "n_pos": torch.empty((K,), dtype=torch.int64, device="cuda")}
+        if out is None:
+            out = {"labels": torch.zeros((SP, K), dtype=torch.uint8, device="cuda"),
+                   "matched_gt": torch.full((SP,), -1, dtype=torch.int32, device="cuda"),
+                   "n_gt": torch.empty((K,), dtype=torch.int64, device="cuda"),
+                   "n_pos": torch.empty((K,), dtype=torch.int64, device="cuda")}
         a = _abi.MapArgs(pred=_ptr(d["pred"]), pred_off=_ptr(d["pred_off"]), gt=_ptr(d["gt"]),
                          gt_off=_ptr(d["gt_off"]), gt_vis=_ptr(d.get("gt_vis")), ref_dist=_ptr(d["ref_dist"]),
                          thresh=thresh, num_frames=N, num_joints=K, dim=D,
                          **{k: _ptr(v) for k, v in out.items()})
         _lib.check(self.lib.popnet_eval_map_assign(C.byref(a), _stream()), "popnet_eval_map_assign")
-        return {k: v.cpu().numpy() for k, v in out.items()}
+        return out
+
+    def map_assign(self, arrs, *, thresh, K, D):
+        d = {k: _to_dev(v) for k, v in arrs.items()}
+        return {k: v.cpu().numpy() for k, v in self.map_assign_device(d, thresh=thresh, K=K, D=D).items()}
 
     # ------------------------------------------------------------------ decode
     def decode_device(self, heat, paf, depth, params, out=None):

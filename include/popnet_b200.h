@@ -124,6 +124,18 @@ POPNET_API int popnet_decode(const float* heat, const float* paf, const float* d
 POPNET_API int popnet_lift_depth(const float* heat, const float* depth, const int32_t* queries, int n, int grid_h, int grid_w,
                                  float depth_mean, float depth_std, float* out_z, void* stream);
 
+/* The sibling depth reads of the same helper family, same window, queries and de-normalisation:
+ *   POPNET_LIFT_HEAT_WEIGHTED (0)  retrieve_depth_heat_weighted   lib/utils/common.py:272-293  (= popnet_lift_depth)
+ *   POPNET_LIFT_MEAN          (1)  retrieve_depth_weighted        lib/utils/common.py:251-269  np.mean of the fp32 window
+ *                                  (pairwise sum in fp32, divided by the count; `heat` may be NULL)
+ *   POPNET_LIFT_HEAT_MAX      (2)  retrieve_depth_heat_max        lib/utils/common.py:296-318  depth at the first
+ *                                  (row-major) maximum of max(heat, 0) in the window */
+#define POPNET_LIFT_HEAT_WEIGHTED 0
+#define POPNET_LIFT_MEAN 1
+#define POPNET_LIFT_HEAT_MAX 2
+POPNET_API int popnet_lift_depth_mode(const float* heat, const float* depth, const int32_t* queries, int n, int grid_h,
+                                      int grid_w, float depth_mean, float depth_std, int mode, float* out_z, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Evaluator.  Ragged lists-of-lists are CSR-packed by the host: humans of frame f are rows
  * off[f] .. off[f+1]-1; a human is K joints of D doubles; a missing joint is (-1, -1).

@@ -326,6 +326,30 @@ def retrieve_depth_heat_weighted(center, depthmap: np.ndarray, heatmap: np.ndarr
     return f32(_np_sum_f32((d * w).astype(f32)) / _np_sum_f32(w))
 
 
+def retrieve_depth_weighted(center, depthmap: np.ndarray, radius: int = 1) -> f32:
+    """common.py:251-269: np.mean of the clipped window (fp32 pairwise sum, fp32 division by the count)."""
+    gx, gy = depthmap.shape[1], depthmap.shape[0]
+    x0 = min(max(int(center[0] - radius), 0), gx - 1); x1 = max(min(int(center[0] + radius), gx - 1), 0)
+    y0 = min(max(int(center[1] - radius), 0), gy - 1); y1 = max(min(int(center[1] + radius), gy - 1), 0)
+    d = depthmap[y0:y1 + 1, x0:x1 + 1].astype(f32)
+    return f32(_np_sum_f32(d) / f32(d.size))
+
+
+def retrieve_depth_heat_max(center, depthmap: np.ndarray, heatmap: np.ndarray, radius: int = 1) -> f32:
+    """common.py:296-318: depth at the first (row-major) maximum of max(heat, 0) in the clipped window."""
+    heatmap = np.where(heatmap < 0, f32(0), heatmap).astype(f32)
+    gx, gy = depthmap.shape[1], depthmap.shape[0]
+    x0 = min(max(int(center[0] - radius), 0), gx - 1); x1 = max(min(int(center[0] + radius), gx - 1), 0)
+    y0 = min(max(int(center[1] - radius), 0), gy - 1); y1 = max(min(int(center[1] + radius), gy - 1), 0)
+    w = heatmap[y0:y1 + 1, x0:x1 + 1].ravel()
+    d = depthmap[y0:y1 + 1, x0:x1 + 1].astype(f32).ravel()
+    best = 0
+    for i in range(1, len(w)):
+        if w[i] > w[best]:
+            best = i
+    return f32(d[best])
+
+
 def lift_frame(heat_chw, depth_chw, joint_list, assoc, *, scale=8, size=224, w_org=480, h_org=512,
                fx=504.1189880371094, fy=504.042724609375, cx=231.7421875, cy=320.62640380859375,
                depth_mean=3.0, depth_std=2.0, flip_y=False):

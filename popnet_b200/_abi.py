@@ -6,6 +6,7 @@ import ctypes as C
 
 MAX_JOINTS = 24
 MAX_LIMBS = 24
+LIFT_HEAT_WEIGHTED, LIFT_MEAN, LIFT_HEAT_MAX = 0, 1, 2
 MAX_PEAKS = 64
 MAX_PERSONS = 64
 ABI_VERSION = 1
@@ -80,6 +81,7 @@ PROTOTYPES = {
     "popnet_launch_count": (C.c_longlong, []),
     "popnet_decode": (C.c_int, [vp, vp, vp, C.c_int, C.POINTER(DecodeParams), C.POINTER(DecodeOut), vp]),
     "popnet_lift_depth": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp]),
+    "popnet_lift_depth_mode": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, vp, vp]),
     "popnet_eval_pck": (C.c_int, [C.POINTER(PckArgs), vp]),
     "popnet_eval_map_assign": (C.c_int, [C.POINTER(MapArgs), vp]),
     "popnet_num_conv_layers": (C.c_int, [C.POINTER(NetConfig)]),

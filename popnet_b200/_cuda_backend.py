@@ -155,14 +155,16 @@ class CudaBackend:
         res["flags"] = res["flags"].view(np.uint32)
         return res
 
-    def lift_depth(self, heat, depth, queries, depth_mean=0.0, depth_std=1.0):
-        """heat/depth: [planes, gh, gw] fp32; queries [n,3] int32 (plane, cx, cy) -> fp32 [n] (NumPy)."""
-        h, d = _to_dev(heat, torch.float32), _to_dev(depth, torch.float32)
+    def lift_depth(self, heat, depth, queries, depth_mean=0.0, depth_std=1.0, mode=_abi.LIFT_HEAT_WEIGHTED):
+        """heat/depth: [planes, gh, gw] fp32 (heat may be None for LIFT_MEAN); queries [n,3] int32 (plane, cx, cy)
+        -> fp32 [n] (NumPy)."""
+        d = _to_dev(depth, torch.float32)
+        h = _to_dev(heat, torch.float32) if heat is not None else None
         q = _to_dev(np.ascontiguousarray(queries, np.int32))
         n = q.shape[0]
         out = torch.empty((n,), dtype=torch.float32, device="cuda")
-        _lib.check(self.lib.popnet_lift_depth(_ptr(h), _ptr(d), _ptr(q), n, h.shape[-2], h.shape[-1], float(depth_mean),
-                                              float(depth_std), _ptr(out), _stream()), "popnet_lift_depth")
+        _lib.check(self.lib.popnet_lift_depth_mode(_ptr(h), _ptr(d), _ptr(q), n, d.shape[-2], d.shape[-1], float(depth_mean),
+                                                   float(depth_std), int(mode), _ptr(out), _stream()), "popnet_lift_depth_mode")
         return out.cpu().numpy()
 
     def preprocess_depth(self, frames, dst_hw, depth_max, depth_mean, depth_std):

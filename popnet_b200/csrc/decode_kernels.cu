@@ -484,26 +484,35 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const float* __re
 // retrieve_depth_heat_weighted (lib/utils/common.py:272-293) for arbitrary query points: one thread per query
 __global__ void __launch_bounds__(128) lift_points_kernel(const float* __restrict__ heat, const float* __restrict__ depth,
                                                           const int32_t* __restrict__ queries, int n, int H, int W,
-                                                          float depth_mean, float depth_std, float* __restrict__ out) {
+                                                          float depth_mean, float depth_std, int mode, float* __restrict__ out) {
   const int i = blockIdx.x * 128 + threadIdx.x;
   if (i >= n) return;
   const int plane = queries[3 * i], cx = queries[3 * i + 1], cy = queries[3 * i + 2];
   const int x0 = clampi(cx - 1, 0, W - 1), x1 = clampi(cx + 1, 0, W - 1);
   const int y0 = clampi(cy - 1, 0, H - 1), y1 = clampi(cy + 1, 0, H - 1);
-  const float* hm = heat + (size_t)plane * H * W;
+  const float* hm = heat ? heat + (size_t)plane * H * W : nullptr;
   const float* dm = depth + (size_t)plane * H * W;
   float wv[9], dv[9];
   int m = 0;
+  float best_w = 0.f, best_d = 0.f;
   for (int yy = y0; yy <= y1; ++yy)
     for (int xx = x0; xx <= x1; ++xx) {
-      float hv = hm[yy * W + xx];
+      float hv = hm ? hm[yy * W + xx] : 0.f;
       if (hv < 0) hv = 0;
-      const float w = hv + 0.000000001f;
       float d = dm[yy * W + xx] * depth_std;
       d = d + depth_mean;
-      wv[m] = w; dv[m] = d * w; ++m;
+      if (mode == POPNET_LIFT_HEAT_WEIGHTED) {
+        const float w = hv + 0.000000001f;
+        wv[m] = w; dv[m] = d * w;
+      } else {
+        dv[m] = d;
+        if (m == 0 || hv > best_w) { best_w = hv; best_d = d; }     // np.argmax: first maximum, row-major (NaN-free maps)
+      }
+      ++m;
     }
-  out[i] = sum_pairwise_f32(dv, m) / sum_pairwise_f32(wv, m);
+  if (mode == POPNET_LIFT_HEAT_WEIGHTED) out[i] = sum_pairwise_f32(dv, m) / sum_pairwise_f32(wv, m);
+  else if (mode == POPNET_LIFT_MEAN) out[i] = sum_pairwise_f32(dv, m) / (float)m;     // np.mean of an fp32 window
+  else out[i] = best_d;
 }
 
 bool g_tables_uploaded = false;
@@ -566,12 +575,20 @@ extern "C" int popnet_decode(const float* heat, const float* paf, const float* d
   return POPNET_OK;
 }
 
-extern "C" int popnet_lift_depth(const float* heat, const float* depth, const int32_t* queries, int n, int grid_h, int grid_w,
-                                 float depth_mean, float depth_std, float* out_z, void* stream) {
-  if (!heat || !depth || !queries || !out_z || n < 0 || grid_h < 1 || grid_w < 1) return POPNET_ERR_INVALID_ARG;
+extern "C" int popnet_lift_depth_mode(const float* heat, const float* depth, const int32_t* queries, int n, int grid_h,
+                                      int grid_w, float depth_mean, float depth_std, int mode, float* out_z, void* stream) {
+  if (mode < POPNET_LIFT_HEAT_WEIGHTED || mode > POPNET_LIFT_HEAT_MAX) return POPNET_ERR_INVALID_ARG;
+  if ((!heat && mode != POPNET_LIFT_MEAN) || !depth || !queries || !out_z || n < 0 || grid_h < 1 || grid_w < 1)
+    return POPNET_ERR_INVALID_ARG;
   if (n == 0) return POPNET_OK;
   lift_points_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(heat, depth, queries, n, grid_h, grid_w,
-                                                                                    depth_mean, depth_std, out_z);
+                                                                                    depth_mean, depth_std, mode, out_z);
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
+}
+
+extern "C" int popnet_lift_depth(const float* heat, const float* depth, const int32_t* queries, int n, int grid_h, int grid_w,
+                                 float depth_mean, float depth_std, float* out_z, void* stream) {
+  return popnet_lift_depth_mode(heat, depth, queries, n, grid_h, grid_w, depth_mean, depth_std, POPNET_LIFT_HEAT_WEIGHTED, out_z,
+                                stream);
 }

@@ -86,6 +86,25 @@ def retrieve_depth_heat_weighted(center, depthmap, heatmap, radius=1):
     return np.float32(z[0])
 
 
+def retrieve_depth_weighted(center, depthmap, radius=1):
+    """lib/utils/common.py:251-269: plain mean of the clipped 3x3 depth window (np.mean of an fp32 window)."""
+    if radius != 1:
+        raise NotImplementedError("only radius=1 is implemented on the device")
+    z = _get_backend().lift_depth(None, np.asarray(depthmap, np.float32)[None],
+                                  np.array([[0, int(center[0]), int(center[1])]], np.int32), mode=_abi.LIFT_MEAN)
+    return np.float32(z[0])
+
+
+def retrieve_depth_heat_max(center, depthmap, heatmap, radius=1):
+    """lib/utils/common.py:296-318: depth at the (first, row-major) maximum of the heat-map inside the clipped 3x3
+    window; like the reference, negative heat values count as 0."""
+    if radius != 1:
+        raise NotImplementedError("only radius=1 is implemented on the device")
+    z = _get_backend().lift_depth(np.asarray(heatmap, np.float32)[None], np.asarray(depthmap, np.float32)[None],
+                                  np.array([[0, int(center[0]), int(center[1])]], np.int32), mode=_abi.LIFT_HEAT_MAX)
+    return np.float32(z[0])
+
+
 def _raise_on_overflow(flags):
     bad = np.nonzero(np.asarray(flags))[0]
     if len(bad):

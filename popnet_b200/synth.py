@@ -28,17 +28,25 @@ _TEMPLATE = np.array([
     [0.11, 0.75], [-0.12, 0.96], [0.12, 0.96]], dtype=np.float64)
 
 
+#: COCO 18-keypoint template (topology.COCO_JOINT_NAMES order), same normalisation
+_TEMPLATE_COCO = np.array([
+    [0.00, 0.06], [0.00, 0.17], [-0.17, 0.21], [-0.24, 0.39], [-0.27, 0.55], [0.17, 0.21], [0.24, 0.39], [0.27, 0.55],
+    [-0.09, 0.55], [-0.11, 0.75], [-0.12, 0.96], [0.09, 0.55], [0.11, 0.75], [0.12, 0.96],
+    [-0.03, 0.03], [0.03, 0.03], [-0.07, 0.05], [0.07, 0.05]], dtype=np.float64)
+
+
 def random_skeletons(rng: np.random.Generator, n_persons: int, size: int = 224,
-                     height_range=(70.0, 190.0), jitter: float = 0.025):
-    """Return (joints2d [P,15,2] float64 in network-input pixels, z [P] metres)."""
-    out = np.zeros((n_persons, NUM_JOINTS, 2), np.float64)
+                     height_range=(70.0, 190.0), jitter: float = 0.025, template: np.ndarray | None = None):
+    """Return (joints2d [P,K,2] float64 in network-input pixels, z [P] metres); K = 15 unless `template` is given."""
+    _T = _TEMPLATE if template is None else template
+    out = np.zeros((n_persons, _T.shape[0], 2), np.float64)
     zs = np.zeros(n_persons, np.float64)
     for p in range(n_persons):
         h = rng.uniform(*height_range)
         cx = rng.uniform(0.12 * size, 0.88 * size)
         top = rng.uniform(-0.05 * size, size - 0.75 * h)
         lean = rng.uniform(-0.25, 0.25)
-        pts = _TEMPLATE.copy()
+        pts = _T.copy()
         pts += rng.normal(0.0, jitter, pts.shape)
         pts[:, 0] += lean * (pts[:, 1] - 0.5)
         out[p, :, 0] = cx + pts[:, 0] * h
@@ -49,7 +57,7 @@ def random_skeletons(rng: np.random.Generator, n_persons: int, size: int = 224,
 
 def render_maps(joints2d: np.ndarray, z: np.ndarray, *, size: int = 224, stride: int = 8,
                 sigma: float = 7.0, cam: Camera = MP3DHP, noise: float = 0.0,
-                rng: np.random.Generator | None = None):
+                rng: np.random.Generator | None = None, limbs=None):
     """Render one frame's maps in the network's output layout (channel-major, fp32).
 
     Returns heat [K+1, g, g], paf [2L, g, g], depth [K, g, g] with g = size // stride; depth is
@@ -57,6 +65,9 @@ def render_maps(joints2d: np.ndarray, z: np.ndarray, *, size: int = 224, stride:
     """
     g = size // stride
     P = joints2d.shape[0]
+    LIMBS = globals()["LIMBS"] if limbs is None else tuple(limbs)      # topology: default = the depth path's 15 / 14
+    NUM_JOINTS = joints2d.shape[1] if limbs is not None else globals()["NUM_JOINTS"]
+    NUM_LIMBS = len(LIMBS)
     centres = np.arange(g, dtype=np.float64) * stride + (stride / 2.0 - 0.5)
     xx, yy = np.meshgrid(centres, centres)
     heat = np.zeros((NUM_JOINTS + 1, g, g), np.float64)
@@ -120,21 +131,23 @@ def render_maps(joints2d: np.ndarray, z: np.ndarray, *, size: int = 224, stride:
 
 
 def map_batch(batch: int, *, seed: int = 1234, persons=(1, 6), noise: float = 0.01, size: int = 224,
-              stride: int = 8):
+              stride: int = 8, limbs=None, template: np.ndarray | None = None):
     """C2/C4/C5 decode inputs: ``batch`` frames, persons ~ U{lo..hi} per frame, frame f seeded with
     ``default_rng(seed + f)``.  Returns (heat [B,16,g,g], paf [B,28,g,g], depth [B,15,g,g], skeletons)."""
     g = size // stride
-    heat = np.zeros((batch, NUM_JOINTS + 1, g, g), np.float32)
-    paf = np.zeros((batch, 2 * NUM_LIMBS, g, g), np.float32)
-    depth = np.zeros((batch, NUM_JOINTS, g, g), np.float32)
+    K = NUM_JOINTS if template is None else template.shape[0]
+    L = NUM_LIMBS if limbs is None else len(limbs)
+    heat = np.zeros((batch, K + 1, g, g), np.float32)
+    paf = np.zeros((batch, 2 * L, g, g), np.float32)
+    depth = np.zeros((batch, K, g, g), np.float32)
     skels = []
     for f in range(batch):
         rng = np.random.default_rng(seed + f)
         n = int(rng.integers(persons[0], persons[1] + 1))
-        j2d, z = random_skeletons(rng, n, size)
+        j2d, z = random_skeletons(rng, n, size, template=template)
         # every third frame keeps the clean (plateau-rich) rendering; the rest get sensor-like noise
         nz = 0.0 if f % 3 == 0 else noise
-        heat[f], paf[f], depth[f] = render_maps(j2d, z, size=size, stride=stride, noise=nz, rng=rng)
+        heat[f], paf[f], depth[f] = render_maps(j2d, z, size=size, stride=stride, noise=nz, rng=rng, limbs=limbs)
         skels.append((j2d, z))
     return heat, paf, depth, skels
 

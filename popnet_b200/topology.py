@@ -37,6 +37,20 @@ HEAD_ID, NECK_ID = 0, 1
 MAX_JOINTS = 24                 # compile-time capacity of the CUDA decode (COCO's 18 fits)
 MAX_LIMBS = 24
 
+#: COCO body topology of the reference's other PAF users: 18 keypoints
+#: (third_party_methods/lib/datasets/datasets_coco.py:40-64) and the 19 limbs of the native decoder
+#: (third_party_methods/lib/pafprocess/pafprocess.h:21-24, COCOPAIRS).  The decode kernels take the topology as
+#: data (DecodeParams.limbs), so this is a second parameter block, not a second code path.
+COCO_JOINT_NAMES: Tuple[str, ...] = (
+    "nose", "neck", "right_shoulder", "right_elbow", "right_wrist", "left_shoulder", "left_elbow", "left_wrist",
+    "right_hip", "right_knee", "right_ankle", "left_hip", "left_knee", "left_ankle", "right_eye", "left_eye",
+    "right_ear", "left_ear",
+)
+COCO_LIMBS: Tuple[Tuple[int, int], ...] = (
+    (1, 2), (1, 5), (2, 3), (3, 4), (5, 6), (6, 7), (1, 8), (8, 9), (9, 10), (1, 11),
+    (11, 12), (12, 13), (1, 0), (0, 14), (14, 16), (0, 15), (15, 17), (2, 16), (5, 17),
+)
+
 
 def get_keypoints() -> List[str]:
     """Same return value as util/util_functions.py:37-55."""
@@ -97,3 +111,8 @@ class DecodeConfig:
             thresh_paf=float(cfg.TEST.THRESH_PAF),
             num_intermed_pts=int(cfg.TEST.NUM_INTERMED_PTS_BETWEEN_KEYPOINTS),
         )
+
+
+def coco_config(**kw) -> DecodeConfig:
+    """DecodeConfig of the COCO 18-keypoint / 19-limb topology (same thresholds as the depth path unless overridden)."""
+    return DecodeConfig(num_keypoints=len(COCO_JOINT_NAMES), num_limbs=len(COCO_LIMBS), limbs=COCO_LIMBS, **kw)

@@ -5,6 +5,8 @@ import json
 import numpy as np
 import pytest
 
+import helpers
+
 from popnet_b200 import synth
 from popnet_b200.topology import ITOP, MP3DHP
 
@@ -58,3 +60,36 @@ def test_json_wire_formats_round_trip(tmp_path, cuda_backend):
     _, k2 = E.eval_human_dataset_2d_PCKh(ds["pred2d"], ds["gt2d"], 0, 1, 15, 0.5, 0.5)
     assert np.array_equal(np.asarray(out["pckh_2d"]), np.asarray(k2))
     assert 0.0 < out["overall"]["pckh_2d"] <= 1.0 and 0.0 < out["overall"]["map_3d"] <= 100.0
+
+
+def test_depth_read_variants_match_oracle(cuda_backend):
+    """retrieve_depth_weighted / retrieve_depth_heat_max (lib/utils/common.py:251-318), SURVEY.md 8(f) row 4."""
+    from oracle import decode_np
+    from popnet_b200.decode import retrieve_depth_weighted, retrieve_depth_heat_max
+    rng = np.random.default_rng(3)
+    heat = (rng.random((28, 28), dtype=np.float32) - 0.2).astype(np.float32)        # some negative cells: clamp path
+    heat[10:13, 4:7] = 0.5                                                            # a plateau: first maximum wins
+    depth = (rng.random((28, 28), dtype=np.float32) * 4 + 1).astype(np.float32)
+    for c in [(0, 0), (27, 27), (0, 13), (5, 27), (12, 9), (5, 11), (26, 1)]:
+        assert retrieve_depth_weighted(c, depth, radius=1) == decode_np.retrieve_depth_weighted(c, depth, 1), c
+        assert retrieve_depth_heat_max(c, depth, heat.copy(), radius=1) == decode_np.retrieve_depth_heat_max(c, depth, heat, 1), c
+    # batched, all cells of a plane, against the restatement
+    q = np.array([[0, x, y] for y in range(28) for x in range(28)], np.int32)
+    for mode, fn in ((1, lambda c: decode_np.retrieve_depth_weighted(c, depth, 1)),
+                     (2, lambda c: decode_np.retrieve_depth_heat_max(c, depth, heat, 1))):
+        got = cuda_backend.lift_depth(heat[None], depth[None], q, mode=mode)
+        want = np.array([fn((int(x), int(y))) for _, x, y in q], np.float32)
+        assert np.array_equal(got, want), mode
+
+
+def test_decode_coco_topology_vs_oracle(cuda_backend, oracle_lib):
+    """The decode kernels take the skeleton as data: COCO's 18 keypoints / 19 limbs (pafprocess.h:21-24), byte-for-byte
+    against the C oracle (which tests/test_refcheck.py pins to the reference with the same topology)."""
+    from popnet_b200 import _abi, synth, topology
+    heat, paf, depth, _ = synth.map_batch(48, seed=31, persons=(1, 7), noise=0.01, limbs=topology.COCO_LIMBS,
+                                          template=synth._TEMPLATE_COCO)
+    params = _abi.make_decode_params(topology.coco_config(), topology.MP3DHP)
+    dev = cuda_backend.decode(heat, paf, depth, params)
+    ora = oracle_lib.decode(heat, paf, depth, params)
+    assert helpers.records_equal(dev, ora) == []
+    assert int(dev["n_person"].sum()) >= 48 and not dev["flags"].any()

@@ -105,3 +105,55 @@ def test_decode_fresh_frames_match_reference(oracle_lib):
             assert ok, (f, why)
     finally:
         cv2.ipp.setUseIPP(prev)
+
+
+def test_decode_coco_topology_matches_reference(oracle_lib, monkeypatch):
+    """SURVEY.md 8(f) row 4: the reference's paf_to_pose binds its skeleton as module globals (paf_to_pose.py:28-30);
+    rebinding them to COCO's 18 keypoints / 19 limbs (pafprocess.h:21-24) must give what the oracle computes from the same
+    topology passed as data."""
+    cv2 = pytest.importorskip("cv2")
+    import helpers
+    from popnet_b200 import _abi, synth, topology
+    ref = refshim.load()
+    g = ref.paf_to_pose.__globals__
+    limbs = [list(l) for l in topology.COCO_LIMBS]
+    monkeypatch.setitem(g, "joint_to_limb_heatmap_relationship", limbs)
+    monkeypatch.setitem(g, "paf_xy_coords_per_limb", np.arange(2 * len(limbs)).reshape(-1, 2))
+    monkeypatch.setitem(g, "NUM_LIMBS", len(limbs))
+    monkeypatch.setattr(ref.cfg.MODEL, "NUM_KEYPOINTS", 18)
+    K = 18
+    heat, paf, depth, _ = synth.map_batch(8, seed=99, persons=(1, 6), noise=0.01, limbs=topology.COCO_LIMBS,
+                                          template=synth._TEMPLATE_COCO)
+    out = oracle_lib.decode(heat, paf, depth, _abi.make_decode_params(topology.coco_config(), topology.MP3DHP))
+    prev = cv2.ipp.useIPP()
+    try:
+        cv2.ipp.setUseIPP(False)
+        for f in range(8):
+            r = refshim.reference_decode_frame(ref, heat[f], paf[f], depth[f], topology.MP3DHP)
+            n = len(r["humans_2d"])
+            gold = {"k/joint_list": r["joint_list"], "k/assoc": r["assoc"],
+                    "k/humans_2d": np.asarray(r["humans_2d"], np.float64).reshape(n, K, 2),
+                    "k/humans_3d": np.asarray(r["humans_3d"], np.float64).reshape(n, K, 3),
+                    "k/conf": np.asarray(r["conf"], np.float64).reshape(n, K)}
+            ok, why = helpers.compare_to_golden(out, f, gold, "k/", K=K, exact=True)
+            assert ok, (f, why)
+    finally:
+        cv2.ipp.setUseIPP(prev)
+
+
+def test_depth_read_variants_match_reference():
+    """oracle/decode_np.py restatements of retrieve_depth_weighted / retrieve_depth_heat_max vs lib/utils/common.py:251-318."""
+    from oracle import decode_np
+    ref = refshim.load()
+    common = sys.modules[ref.paf_to_human_list.__module__]
+    rng = np.random.default_rng(5)
+    heat = (rng.random((28, 28), dtype=np.float32) - 0.2).astype(np.float32)
+    heat[10:13, 4:7] = 0.5
+    depth = (rng.random((28, 28), dtype=np.float32) * 4 + 1).astype(np.float32)
+    for y in range(28):
+        for x in range(28):
+            a = common.retrieve_depth_weighted((x, y), depth, radius=1)
+            b = decode_np.retrieve_depth_weighted((x, y), depth, 1)
+            assert np.float32(a) == b and np.asarray(a).dtype == np.float32, (x, y, a, b)
+            a = common.retrieve_depth_heat_max((x, y), depth, heat.copy(), radius=1)
+            assert np.float32(a) == decode_np.retrieve_depth_heat_max((x, y), depth, heat, 1), (x, y)

@@ -146,6 +146,33 @@ def eval_human_dataset_2d_PCKh(humans_pred_set, humans_gt_set, head_id, neck_id,
     return _summarise(out, vis_all, n, num_joints, use_vis)
 
 
+def _head_sizes_from_rect(head_sz_set, humans_gt_set=None, SC_BIAS=0.6):
+    """compute_head_size_from_rect (eval_pck.py:249-263 / eval_mAP.py:43-57) with the reference's expression on the caller's
+    number types; frames without GT humans are skipped when `humans_gt_set` is given (eval_pck.py:199-203)."""
+    out = []
+    for i, rects in enumerate(head_sz_set):
+        if humans_gt_set is not None and len(humans_gt_set[i]) == 0:
+            continue
+        for rect in rects:
+            out.append(np.sqrt((rect[2] - rect[0]) ** 2 + (rect[3] - rect[1]) ** 2) * SC_BIAS)
+    return out
+
+
+def eval_human_dataset_2d_PCKh_rect(humans_pred_set, humans_gt_set, head_sz_set, num_joints=15, h_th=0.5, iou_th=0.5,
+                                    human_gt_set_visibility=None):
+    """util/eval_pck.py:157-229: PCKh with the head size taken from annotated head rectangles (x1, y1, x2, y2),
+    hsz = 0.6 * diagonal."""
+    assert len(humans_gt_set) == len(humans_pred_set)
+    if human_gt_set_visibility is None:
+        human_gt_set_visibility = [np.ones((len(g), num_joints)).tolist() for g in humans_gt_set]
+    hsz = _head_sizes_from_rect(head_sz_set, humans_gt_set)
+    gt_thresh = [h * h_th for h in hsz]
+    out, vis_all, n = _run_pck(humans_pred_set, humans_gt_set, None, None, num_joints, 0.0, iou_th,
+                               human_gt_set_visibility, gt_thresh)
+    use_vis = vis_all.shape[0] != 0
+    return _summarise(out, vis_all, n, num_joints, use_vis)
+
+
 def eval_human_dataset_3d(humans_pred_set_2d, humans_gt_set_2d, humans_pred_set_3d, humans_gt_set_3d,
                           num_joints=15, dist_th=0.1, iou_th=0.5, human_gt_set_visibility=None):
     """util/eval_pck.py:313-374."""
@@ -239,6 +266,19 @@ def eval_ap_mpii_v2(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility
     assert len(humans_gt_set) == len(humans_pred_set)
     K = len(joint_names)
     ref_dist_set = [_head_sizes([g], head_id, neck_id) for g in humans_gt_set]
+    _fill_defaults(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, K)
+    out, conf = _assign(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, ref_dist_set, K, 2, thresh)
+    ap = _ap_from_labels(out, conf, joint_names)
+    return (ap, out) if _return_counts else ap
+
+
+def eval_ap_mpii(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, head_sz_set, joint_names, thresh=0.5,
+                 _return_counts=False):
+    """util/eval_mAP.py:210-269: 2D AP under the PCKh rule with the head size from annotated head rectangles."""
+    print('2D evaluation in AP evaluation under PCKh-{:01f} rule ...'.format(thresh))
+    assert len(humans_gt_set) == len(humans_pred_set)
+    K = len(joint_names)
+    ref_dist_set = [_head_sizes_from_rect([head_sz_set[i]]) for i in range(len(humans_gt_set))]
     _fill_defaults(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, K)
     out, conf = _assign(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, ref_dist_set, K, 2, thresh)
     ap = _ap_from_labels(out, conf, joint_names)

@@ -143,3 +143,22 @@ def test_evaluator_edge_cases_gpu(eval_on_cuda):
     assert (m["dists"][3] == -1).all() and m["dists"][4][3] == 0.0
     with pytest.raises(IndexError):
         E.eval_human_dataset_2d([[base.tolist()]], [[allmiss]], K, 10.0, 0.5)
+
+
+def test_head_rectangle_variants_cuda_vs_oracle(cuda_backend, monkeypatch):
+    """eval_human_dataset_2d_PCKh_rect / eval_ap_mpii (eval_pck.py:157-229, eval_mAP.py:210-269): same numbers from the
+    CUDA backend and the C oracle (tests/test_refcheck.py pins the oracle path to the reference)."""
+    from oracle.backend import OracleBackend
+    ds = synth.eval_set(600, seed=21)
+    rng = np.random.default_rng(4)
+    rects = [[[float(x), float(y), float(x + w), float(y + h)] for x, y, w, h in rng.uniform(5, 60, (len(g), 4))] for g in ds["gt2d"]]
+    names = list(JOINT_NAMES)
+    res = []
+    for be in (cuda_backend, OracleBackend()):
+        monkeypatch.setattr(E, "_backend", be)
+        a = _quiet(E.eval_human_dataset_2d_PCKh_rect, ds["pred2d"], ds["gt2d"], rects, 15, 0.5, 0.5)
+        b = _quiet(E.eval_ap_mpii, ds["pred2d"], copy.deepcopy(ds["conf"]), ds["gt2d"], [], rects, names, 0.5)
+        res.append((np.asarray(a[0]), np.asarray(a[1]), np.asarray(b)))
+    for x, y in zip(*res):
+        assert np.array_equal(x, y, equal_nan=True)
+    assert res[0][2][-1] > 10.0          # a meaningful AP, not an all-zero agreement

@@ -80,6 +80,15 @@ def test_evaluator_edge_cases_match_reference(seed, on_oracle):
     a = _quiet(ref.eval_mAP.eval_ap_3D, pred3, copy.deepcopy(conf), gt3, [], names, 0.1)
     b = _quiet(E.eval_ap_3D, pred3, copy.deepcopy(conf), gt3, [], names, 0.1)
     assert np.array_equal(a, b, equal_nan=True)
+    # head-rectangle variants: eval_pck.py:157-229, eval_mAP.py:210-269
+    rects = [[[float(x), float(y), float(x + w), float(y + h)] for x, y, w, h in rng.uniform(5, 60, (len(g), 4))] for g in gt2]
+    a = _quiet(ref.eval_pck.eval_human_dataset_2d_PCKh_rect, pred2, gt2, rects, 15, 0.5, 0.5)
+    b = _quiet(E.eval_human_dataset_2d_PCKh_rect, pred2, gt2, rects, 15, 0.5, 0.5)
+    for x, y in zip(a, b):
+        assert np.array_equal(np.asarray(x, np.float64), np.asarray(y, np.float64), equal_nan=True)
+    a = _quiet(ref.eval_mAP.eval_ap_mpii, pred2, copy.deepcopy(conf), gt2, [], rects, names, 0.5)
+    b = _quiet(E.eval_ap_mpii, pred2, copy.deepcopy(conf), gt2, [], rects, names, 0.5)
+    assert np.array_equal(a, b, equal_nan=True)
 
 
 def test_decode_fresh_frames_match_reference(oracle_lib):

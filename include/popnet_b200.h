@@ -191,6 +191,30 @@ typedef struct PopnetMapArgs {
 POPNET_API int popnet_eval_map_assign(const PopnetMapArgs* args_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * AP tail on the device.  Replaces, per joint,
+ *   getRPC      util/eval_mAP.py:160-191   sort the scores of ALL predictions descending, cumulative precision / recall
+ *   VOCap       util/eval_mAP.py:194-207   monotone precision envelope, area under the recall steps
+ * and the `ap[j] = VOCap(...) * 100; ap[-1] = mean` lines of eval_ap_mpii / eval_ap_mpii_v2 / eval_ap_3D (:262-265).
+ * Tie order: the reference sorts with np.argsort (introsort, order of equal scores unspecified); here equal scores keep
+ * their input order (stable by prediction index), which is one of the orders the reference can produce.  AP is a float64:
+ * compared with a tolerance (summation order differs from NumPy's pairwise sum), see tests/test_gpu_eval.py.
+ * conf / labels are the [SP][K] arrays of the assignment step (labels = PopnetMapArgs.labels, n_gt = PopnetMapArgs.n_gt).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct PopnetApArgs {
+  const double* conf;          /* [SP][K] prediction scores                                        */
+  const uint8_t* labels;       /* [SP][K] 1 = true positive                                        */
+  const long long* n_gt;       /* [K] annotated GT joints (recall denominator)                     */
+  int32_t num_preds;           /* SP                                                               */
+  int32_t num_joints;          /* K <= 32                                                          */
+  double* ap;                  /* out [K+1]: AP * 100 per joint, their mean last                   */
+  void* workspace;             /* popnet_eval_ap_workspace_bytes(SP, K) bytes of device memory     */
+  size_t workspace_bytes;
+} PopnetApArgs;
+
+POPNET_API size_t popnet_eval_ap_workspace_bytes(int num_preds, int num_joints);
+POPNET_API int popnet_eval_ap(const PopnetApArgs* args_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Network forward.  Replaces rtpose_light3d.forward   third_party_methods/lib/network/rtpose_light3d.py:326-356
  * (ResPreprocessNet :201-216, BasicBlock :56-72, make_stages :222-246) for num_stages = 2.
  * Weights are folded (eval-mode BatchNorm into scale/shift, then bf16) and packed once by

@@ -64,6 +64,14 @@ class MapArgs(C.Structure):
     ]
 
 
+class ApArgs(C.Structure):
+    _fields_ = [
+        ("conf", vp), ("labels", vp), ("n_gt", vp),
+        ("num_preds", C.c_int32), ("num_joints", C.c_int32),
+        ("ap", vp), ("workspace", vp), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 class NetConfig(C.Structure):
     _fields_ = [("num_parts", C.c_int32), ("num_limbs", C.c_int32), ("input_dim", C.c_int32),
                 ("height", C.c_int32), ("width", C.c_int32), ("operand_dtype", C.c_int32)]
@@ -80,6 +88,8 @@ PROTOTYPES = {
     "popnet_last_cuda_error": (C.c_int, []),
     "popnet_launch_count": (C.c_longlong, []),
     "popnet_decode": (C.c_int, [vp, vp, vp, C.c_int, C.POINTER(DecodeParams), C.POINTER(DecodeOut), vp]),
+    "popnet_eval_ap_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "popnet_eval_ap": (C.c_int, [C.POINTER(ApArgs), vp]),
     "popnet_lift_depth": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp]),
     "popnet_lift_depth_mode": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, vp, vp]),
     "popnet_eval_pck": (C.c_int, [C.POINTER(PckArgs), vp]),

@@ -136,6 +136,25 @@ class CudaBackend:
         d = {k: _to_dev(v) for k, v in arrs.items()}
         return {k: v.cpu().numpy() for k, v in self.map_assign_device(d, thresh=thresh, K=K, D=D).items()}
 
+    def ap_tail_device(self, conf, labels, n_gt):
+        """popnet_eval_ap on device tensors: conf [SP,K] f64, labels [SP,K] u8, n_gt [K] i64 -> ap [K+1] f64 (device)."""
+        SP, K = conf.shape
+        nbytes = self.lib.popnet_eval_ap_workspace_bytes(SP, K)
+        ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device="cuda")
+        ap = torch.empty((K + 1,), dtype=torch.float64, device="cuda")
+        a = _abi.ApArgs(conf=_ptr(conf), labels=_ptr(labels), n_gt=_ptr(n_gt), num_preds=SP, num_joints=K, ap=_ptr(ap),
+                        workspace=_ptr(ws), workspace_bytes=nbytes)
+        _lib.check(self.lib.popnet_eval_ap(C.byref(a), _stream()), "popnet_eval_ap")
+        ws.record_stream(torch.cuda.current_stream())
+        return ap
+
+    def ap_tail(self, conf, labels, n_gt):
+        """Host arrays in, ap [K+1] (NumPy) out."""
+        c = _to_dev(np.ascontiguousarray(conf, np.float64))
+        l = _to_dev(np.ascontiguousarray(labels, np.uint8))
+        g = _to_dev(np.ascontiguousarray(n_gt, np.int64))
+        return self.ap_tail_device(c, l, g).cpu().numpy()
+
     # ------------------------------------------------------------------ decode
     def decode_device(self, heat, paf, depth, params, out=None):
         """Device tensors in, device tensors out (no synchronisation); `out` buffers may be reused."""

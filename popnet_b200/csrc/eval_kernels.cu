@@ -248,6 +248,156 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) map_assign_kernel(PopnetM
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// AP tail: per joint a bitonic sort of (score descending, prediction index ascending), then one CTA per joint scans
+// the sorted labels (cumulative true positives -> precision / recall), takes the suffix maximum of the precision
+// (VOC envelope) and sums the recall steps.
+// Workspace per joint: keys f64 [N2], idx i32 [N2] with N2 = SP rounded up to a power of two (>= 2048).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSortBlock = 2048;          // elements sorted inside one CTA's shared memory (1024 threads)
+
+__device__ __forceinline__ bool ap_before(double ka, int ia, double kb, int ib) {   // a sorts before b
+  return ka > kb || (ka == kb && ia < ib);
+}
+__device__ __forceinline__ void ap_cmpswap(double& ka, int& ia, double& kb, int& ib, bool ascending_block) {
+  // within an "ascending" bitonic block the smaller position must hold the element that sorts first
+  const bool swap = ascending_block ? ap_before(kb, ib, ka, ia) : ap_before(ka, ia, kb, ib);
+  if (swap) { const double tk = ka; ka = kb; kb = tk; const int ti = ia; ia = ib; ib = ti; }
+}
+
+__global__ void ap_init_kernel(const double* __restrict__ conf, int SP, int K, int N2, double* __restrict__ keys, int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= N2) return;
+  // padding sorts last: -inf score and indices beyond every real prediction
+  keys[(size_t)j * N2 + i] = i < SP ? conf[(size_t)i * K + j] : -INFINITY;
+  idx[(size_t)j * N2 + i] = i;
+}
+
+// all (k, j) stages with j < kSortBlock for k in [k_lo, k_hi] on one 2048-element block held in shared memory
+__global__ void __launch_bounds__(kSortBlock / 2) ap_sort_smem_kernel(double* __restrict__ keys, int* __restrict__ idx, int N2, int k_lo, int k_hi) {
+  __shared__ double sk[kSortBlock];
+  __shared__ int si[kSortBlock];
+  const int jn = blockIdx.y;
+  const size_t base = (size_t)jn * N2 + (size_t)blockIdx.x * kSortBlock;
+  for (int t = threadIdx.x; t < kSortBlock; t += blockDim.x) { sk[t] = keys[base + t]; si[t] = idx[base + t]; }
+  __syncthreads();
+  for (int k = k_lo; k <= k_hi; k <<= 1) {
+    for (int j = (k >> 1) < kSortBlock ? (k >> 1) : (kSortBlock >> 1); j > 0; j >>= 1) {
+      const int t = threadIdx.x;
+      const int lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;               // pair (lo, lo + j) inside the block
+      const size_t glo = (size_t)blockIdx.x * kSortBlock + lo;
+      const bool asc = (glo & (size_t)k) == 0;
+      ap_cmpswap(sk[lo], si[lo], sk[hi], si[hi], asc);
+      __syncthreads();
+    }
+  }
+  for (int t = threadIdx.x; t < kSortBlock; t += blockDim.x) { keys[base + t] = sk[t]; idx[base + t] = si[t]; }
+}
+
+// one (k, j) stage with j >= kSortBlock: partners live in different blocks
+__global__ void ap_sort_global_kernel(double* __restrict__ keys, int* __restrict__ idx, int N2, int k, int j) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, jn = blockIdx.y;
+  if (t >= N2 / 2) return;
+  const int lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+  double* kk = keys + (size_t)jn * N2;
+  int* ii = idx + (size_t)jn * N2;
+  double ka = kk[lo], kb = kk[hi];
+  int ia = ii[lo], ib = ii[hi];
+  const bool asc = (lo & k) == 0;
+  const double oa = ka;
+  const int oi = ia;
+  ap_cmpswap(ka, ia, kb, ib, asc);
+  if (ia != oi || ka != oa) { kk[lo] = ka; kk[hi] = kb; ii[lo] = ia; ii[hi] = ib; }
+}
+
+constexpr int kApThreads = 1024;
+// one CTA per joint over the sorted order; every thread owns one contiguous chunk of positions
+__global__ void __launch_bounds__(kApThreads) ap_scan_kernel(PopnetApArgs a, const int* __restrict__ idx, int N2) {
+  __shared__ long long s_cnt[kApThreads];
+  __shared__ double s_max[kApThreads];
+  __shared__ double s_sum[kApThreads];
+  const int j = blockIdx.x, t = threadIdx.x, SP = a.num_preds, K = a.num_joints;
+  const int* order = idx + (size_t)j * N2;
+  const int chunk = (SP + kApThreads - 1) / kApThreads;
+  const int i0 = min(t * chunk, SP), i1 = min(i0 + chunk, SP);
+  // pass 1: true positives per chunk -> exclusive prefix
+  long long c = 0;
+  for (int i = i0; i < i1; ++i) c += a.labels[(size_t)order[i] * K + j];
+  s_cnt[t] = c;
+  __syncthreads();
+  if (t == 0) {
+    long long run = 0;
+    for (int q = 0; q < kApThreads; ++q) { const long long v = s_cnt[q]; s_cnt[q] = run; run += v; }
+  }
+  __syncthreads();
+  const long long before = s_cnt[t];
+  // pass 2: suffix maximum of the precision, chunk-local then across chunks (precision[i] = npos_i / (i + 1))
+  double m = 0.0;                                   // mpre[-1] = 0 (eval_mAP.py:201)
+  {
+    long long np = before + c;
+    for (int i = i1 - 1; i >= i0; --i) {
+      const double prec = (double)np / (double)(i + 1);
+      m = fmax(m, prec);
+      np -= a.labels[(size_t)order[i] * K + j];
+    }
+  }
+  s_max[t] = m;
+  __syncthreads();
+  if (t == 0) {
+    double run = 0.0;
+    for (int q = kApThreads - 1; q >= 0; --q) { const double v = s_max[q]; s_max[q] = run; run = fmax(run, v); }   // max over LATER chunks
+  }
+  __syncthreads();
+  // pass 3: sum over the recall steps (true positives) of (recall_i - recall_{i-1}) * envelope_i
+  const double T = (double)a.n_gt[j];
+  double acc = 0.0;
+  {
+    // envelope inside the chunk needs the running suffix max from the right: walk backwards again
+    double env = s_max[t];
+    long long np = before + c;
+    for (int i = i1 - 1; i >= i0; --i) {
+      const double prec = (double)np / (double)(i + 1);
+      env = fmax(env, prec);
+      if (a.labels[(size_t)order[i] * K + j]) {
+        const double step = (double)np / T - (double)(np - 1) / T;
+        if (step > 0) acc += step * env;
+        --np;
+      }
+    }
+  }
+  s_sum[t] = acc;
+  __syncthreads();
+  if (t == 0) {
+    double tot = 0.0;
+    for (int q = 0; q < kApThreads; ++q) tot += s_sum[q];
+    a.ap[j] = tot * 100;
+  }
+}
+
+__global__ void ap_mean_kernel(double* ap, int K) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    // np.mean of K doubles: pairwise sum (K < 128: 8-way unrolled order) divided by K
+    double r;
+    if (K < 8) { r = 0.0; for (int i = 0; i < K; ++i) r += ap[i]; }
+    else {
+      double q[8];
+      for (int i = 0; i < 8; ++i) q[i] = ap[i];
+      int i = 8;
+      for (; i < K - (K % 8); i += 8) for (int u = 0; u < 8; ++u) q[u] += ap[i + u];
+      r = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+      for (; i < K; ++i) r += ap[i];
+    }
+    ap[K] = r / (double)K;
+  }
+}
+
+int ap_pow2(int n) {
+  int p = kSortBlock;
+  while (p < n) p <<= 1;
+  return p;
+}
+
 int grid_for(int frames) {
   int blocks = (frames + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int cap = 148 * 16;   // B200: 148 SMs x 16 resident 128-thread CTAs
@@ -280,6 +430,41 @@ extern "C" int popnet_eval_map_assign(const PopnetMapArgs* args, void* stream) {
   POPNET_CUDA_TRY(cudaMemsetAsync(args->n_pos, 0, sizeof(long long) * args->num_joints, st));
   if (args->num_frames == 0) return POPNET_OK;
   map_assign_kernel<<<grid_for(args->num_frames), kWarpsPerBlock * 32, 0, st>>>(*args);
+  POPNET_AFTER_LAUNCH();
+  return POPNET_OK;
+}
+
+extern "C" size_t popnet_eval_ap_workspace_bytes(int num_preds, int num_joints) {
+  if (num_preds < 0 || num_joints < 1 || num_joints > 32 || num_preds > (1 << 28)) return 0;
+  const size_t N2 = (size_t)ap_pow2(num_preds);
+  return (size_t)num_joints * N2 * (sizeof(double) + sizeof(int));
+}
+
+extern "C" int popnet_eval_ap(const PopnetApArgs* args, void* stream) {
+  if (!args || !args->n_gt || !args->ap || !args->workspace || args->num_preds < 0 || args->num_preds > (1 << 28) ||
+      args->num_joints < 1 || args->num_joints > 32 || (args->num_preds > 0 && (!args->conf || !args->labels)))
+    return POPNET_ERR_INVALID_ARG;
+  if (args->workspace_bytes < popnet_eval_ap_workspace_bytes(args->num_preds, args->num_joints)) return POPNET_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K = args->num_joints, SP = args->num_preds, N2 = ap_pow2(SP);
+  double* keys = static_cast<double*>(args->workspace);
+  int* idx = reinterpret_cast<int*>(keys + (size_t)K * N2);
+  ap_init_kernel<<<dim3((N2 + 255) / 256, K), 256, 0, st>>>(args->conf, SP, K, N2, keys, idx);
+  POPNET_AFTER_LAUNCH();
+  // k = 2 .. kSortBlock entirely in shared memory, then per k: the global stages j >= kSortBlock, the rest in shared memory
+  ap_sort_smem_kernel<<<dim3(N2 / kSortBlock, K), kSortBlock / 2, 0, st>>>(keys, idx, N2, 2, kSortBlock);
+  POPNET_AFTER_LAUNCH();
+  for (int k = kSortBlock * 2; k <= N2; k <<= 1) {
+    for (int j = k >> 1; j >= kSortBlock; j >>= 1) {
+      ap_sort_global_kernel<<<dim3((N2 / 2 + 255) / 256, K), 256, 0, st>>>(keys, idx, N2, k, j);
+      POPNET_AFTER_LAUNCH();
+    }
+    ap_sort_smem_kernel<<<dim3(N2 / kSortBlock, K), kSortBlock / 2, 0, st>>>(keys, idx, N2, k, k);
+    POPNET_AFTER_LAUNCH();
+  }
+  ap_scan_kernel<<<K, kApThreads, 0, st>>>(*args, idx, N2);
+  POPNET_AFTER_LAUNCH();
+  ap_mean_kernel<<<1, 32, 0, st>>>(args->ap, K);
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }

@@ -234,15 +234,23 @@ def _assign(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, re
     return out, conf
 
 
+#: "numpy" = the reference's own NumPy calls for the sort / scan / envelope (bit-identical to util/eval_mAP.py:160-207);
+#: "device" = popnet_eval_ap (stable tie order, float64 sums in a different order: agrees to ~1e-12)
+AP_TAIL = "numpy"
+
+
 def _ap_from_labels(out, conf, joint_names):
     K = len(joint_names)
-    ap = np.zeros(K + 1)
-    for j in range(K):
-        scores = conf[:, j]
-        labels = out["labels"][:, j].astype(np.int64)
-        precision, recall = _get_rpc(scores, labels, np.float64(out["n_gt"][j]))
-        ap[j] = _voc_ap(recall, precision) * 100
-    ap[-1] = np.mean(ap[:-1])
+    if AP_TAIL == "device":
+        ap = np.asarray(_get_backend().ap_tail(conf, out["labels"], out["n_gt"]), np.float64)
+    else:
+        ap = np.zeros(K + 1)
+        for j in range(K):
+            scores = conf[:, j]
+            labels = out["labels"][:, j].astype(np.int64)
+            precision, recall = _get_rpc(scores, labels, np.float64(out["n_gt"][j]))
+            ap[j] = _voc_ap(recall, precision) * 100
+        ap[-1] = np.mean(ap[:-1])
     for j, name in enumerate(joint_names):
         print('    {},  AP: {:03f}'.format(name, ap[j]))
     print('\n     Overall: AP: {:03f}\n'.format(ap[-1]))

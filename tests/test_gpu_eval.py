@@ -162,3 +162,51 @@ def test_head_rectangle_variants_cuda_vs_oracle(cuda_backend, monkeypatch):
     for x, y in zip(*res):
         assert np.array_equal(x, y, equal_nan=True)
     assert res[0][2][-1] > 10.0          # a meaningful AP, not an all-zero agreement
+
+
+@pytest.mark.parametrize("N,seed", [(400, 7), (4000, 0)], ids=["small", "c3"])
+def test_ap_tail_on_device(N, seed, cuda_backend, monkeypatch):
+    """popnet_eval_ap (sort + precision/recall scan + VOC envelope on the device) against the NumPy tail that is
+    bit-identical to util/eval_mAP.py:160-207; float64 sums in a different order -> 1e-9 on the 0..100 scale."""
+    monkeypatch.setattr(E, "_backend", cuda_backend)
+    ds = synth.eval_set(N, seed=seed)
+    names = list(JOINT_NAMES)
+    res = {}
+    for tail in ("numpy", "device"):
+        monkeypatch.setattr(E, "AP_TAIL", tail)
+        res[tail] = (_quiet(E.eval_ap_3D, ds["pred3d"], copy.deepcopy(ds["conf"]), ds["gt3d"], [], names, 0.1),
+                     _quiet(E.eval_ap_mpii_v2, ds["pred2d"], copy.deepcopy(ds["conf"]), ds["gt2d"], [], 0, 1, names, 0.5))
+    for a, b in zip(res["numpy"], res["device"]):
+        assert a.shape == b.shape == (16,)
+        assert np.allclose(a, b, rtol=0, atol=1e-9), np.abs(a - b).max()
+        assert a[-1] > 10
+
+
+def test_ap_tail_sort_sizes_and_ties(cuda_backend):
+    """Sizes around the shared-memory / global bitonic boundaries, duplicate scores with equal labels (order-free),
+    zero-score missing joints, joints without any GT."""
+    rng = np.random.default_rng(11)
+    for SP in (0, 1, 5, 2047, 2048, 2049, 5000, 70000):
+        K = 15
+        conf = rng.uniform(0.05, 1.0, (SP, K))
+        labels = (rng.random((SP, K)) < 0.6).astype(np.uint8)
+        if SP:
+            dup = rng.integers(0, SP, SP // 3)
+            conf[dup] = np.round(conf[dup], 2)                  # many ties ...
+            labels[dup] = 1                                     # ... whose labels agree, so any tie order gives one AP
+            same = np.isin(conf, np.round(conf[dup], 2))
+            labels[same] = 1
+            miss = rng.random((SP, K)) < 0.1
+            conf[miss] = 0.0
+            labels[miss] = 0
+        n_gt = labels.sum(0).astype(np.int64) + rng.integers(0, 50, K)
+        n_gt[3] = 0 if SP == 0 else n_gt[3]
+        labels[:, 7] = 0                                        # a joint that is never right
+        got = cuda_backend.ap_tail(conf, labels, n_gt)
+        want = np.zeros(K + 1)
+        with np.errstate(all="ignore"):
+            for j in range(K):
+                pr, rc = E._get_rpc(conf[:, j], labels[:, j].astype(np.int64), np.float64(n_gt[j]))
+                want[j] = E._voc_ap(rc, pr) * 100
+        want[-1] = np.mean(want[:-1])
+        assert np.allclose(got, want, rtol=0, atol=1e-9, equal_nan=True), (SP, np.abs(got - want).max())

@@ -343,7 +343,7 @@ def run_ours(args, rank, local_rank, world):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (37 launches) + stem_kernel = the forward",
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (35 launches) + stem_kernel = the forward",
                      "achieved": tflops, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tflops / pk["tflops"],
                      "frac_of_burst_peak": tflops / pk["tflops_burst"], "peak_source": pk["src"], "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_flop_per_step": B * FLOP_PER_FRAME,

@@ -32,7 +32,8 @@ struct Buf {
   int P;                  // (2 + N * (H+1)) * (W+1)
 };
 
-enum BufId { A112, B112, C112, D56, E56, F56, G56, S2IN, LA, LB, LC, SA, SB_, DA, DB, DC, kNumBufs };
+// (DA directly behind SA: the fused first layer of the heat-map + depth branches writes 32 consecutive planes)
+enum BufId { A112, B112, C112, D56, E56, F56, G56, S2IN, LA, LB, LC, SA, DA, SB_, DB, DC, kNumBufs };
 
 struct Layer {
   int cin, cout, k;          // logical
@@ -45,6 +46,8 @@ struct Layer {
   int remap_s2;              // input channels follow the S2IN layout
   int fuse_layer;            // index of a 1x1 layer whose weights are K-concatenated here (-1 = none); its input is in2_buf
   int in2_buf;
+  int nfuse_layer;           // index of a layer with the SAME input whose output channels are N-concatenated behind this
+                             // layer's (-1 = none): one launch computes both, its planes continue into the next buffer
   size_t w_off, shift_off;   // bytes in the packed blob
 };
 
@@ -91,7 +94,7 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
     l.cout_pad = (int)align_up(cout, nt);
     l.nt = nt; l.nacc = nacc; l.act = act;
     l.in_buf = in_buf; l.in_plane0 = in_plane0; l.out_buf = out_buf; l.out_plane0 = out_plane0; l.res_buf = res_buf;
-    l.head = head; l.stage = stage; l.remap_s2 = remap; l.fuse_layer = -1; l.in2_buf = -1;
+    l.head = head; l.stage = stage; l.remap_s2 = remap; l.fuse_layer = -1; l.in2_buf = -1; l.nfuse_layer = -1;
     p.layers.push_back(l);
   };
   p.layers.clear();
@@ -110,6 +113,8 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   // 28x28 stage layers: 512-position tiles.  At batch 64 the 53,882 positions make 106 tiles (72 % of the 148 SMs), 384-position
   // tiles (POPNET_STAGE_NACC=3) make 141 (95 %); measured identical (1.065 vs 1.067 ms per forward) because the three concurrent
   // branches already fill each other's idle SMs.
+  const bool kFuseFirst = p.bufs[DA].off == p.bufs[SA].off + (size_t)(p.bufs[SA].C / 8) * p.bufs[SA].plane_stride &&
+                          p.bufs[DA].plane_stride == p.bufs[SA].plane_stride;
   int kStageNacc = 4;
   if (const char* e = getenv("POPNET_STAGE_NACC")) { const int v = atoi(e); if (v >= 2 && v <= 4) kStageNacc = v; }
   for (int s = 1; s <= 2; ++s) {
@@ -124,6 +129,13 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
     add(128, L2, 1, 32, kStageNacc, kActHeadPaf, LC, 0, (s == 1) ? S2IN : -1, 0, -1, 1, s, 0);
     // heat-map branch: 3x3 -> 128 x4, 3x3 -> K+1
     add(cin, 128, 3, 128, kStageNacc, kActLeaky, S2IN, in0, SA, 0, -1, 0, s, remap);
+    // the first convs of the heat-map and the depth branch read the same input: ONE N = 256 launch (full-rate MMAs, the
+    // input tile staged once) whose output planes 0-15 are SA and 16-31 are DA (the buffer right behind it)
+    if (kFuseFirst) {
+      Layer& f = p.layers.back();
+      f.nfuse_layer = (int)p.layers.size() + 4;       // the depth branch's first conv (weights only; never launched)
+      f.nt = 256; f.nacc = 2; f.cout_pad = 256;
+    }
     add(128, 128, 3, 128, kStageNacc, kActLeaky, SA, 0, SB_, 0, -1, 0, s, 0);
     add(128, 128, 3, 128, kStageNacc, kActLeaky, SB_, 0, SA, 0, -1, 0, s, 0);
     add(128, 128, 3, 128, kStageNacc, kActLeaky, SA, 0, SB_, 0, -1, 0, s, 0);
@@ -199,6 +211,14 @@ extern "C" int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvH
       return POPNET_ERR_INVALID_ARG;
     float* shift = reinterpret_cast<float*>(blob.data() + l.shift_off);
     for (int n = 0; n < l.cout; ++n) shift[n] = h.shift_host[n];
+    const PopnetConvHost* h2 = nullptr;                  // N-concatenated sibling layer (same input)
+    if (l.nfuse_layer >= 0) {
+      const Layer& f = p.layers[l.nfuse_layer];
+      h2 = &layers[l.nfuse_layer];
+      if (f.cin != l.cin || f.k != l.k || f.remap_s2 != l.remap_s2 || l.cout + f.cout > l.cout_pad || !h2->weight_host)
+        return POPNET_ERR_UNSUPPORTED;
+      for (int n = 0; n < f.cout; ++n) shift[l.cout + n] = h2->shift_host[n];
+    }
     if (l.k == 7) {                                      // stem: [k8 = kernel row (8th is zero)][cout][8 = column slot]
       h16* w = reinterpret_cast<h16*>(blob.data() + l.w_off);
       for (int n = 0; n < 64; ++n)
@@ -220,6 +240,8 @@ extern "C" int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvH
               const int cref = l.remap_s2 ? s2_to_ref(p, ci) : (ci < l.cin ? ci : -1);
               float v = 0.f;
               if (n < l.cout && cref >= 0) v = h.weight_host[((size_t)n * l.cin + cref) * taps + t] * h.scale_host[n];
+              else if (h2 && n >= l.cout && n - l.cout < p.layers[l.nfuse_layer].cout && cref >= 0)
+                v = h2->weight_host[((size_t)(n - l.cout) * l.cin + cref) * taps + t] * h2->scale_host[n - l.cout];
               w[((((size_t)ti * taps + t) * k8 + g) * l.nt + nn) * 8 + j] = f2h16(v, cfg->operand_dtype);
             }
     if (l.fuse_layer >= 0) {                             // K-concatenated projection shortcut (cin 64, 1x1, own BN scale)
@@ -250,7 +272,7 @@ namespace {
 struct AuxStreams {
   cudaStream_t owner;
   cudaStream_t s[2];
-  cudaEvent_t fork, join[2];
+  cudaEvent_t fork, join[2], nfused;
 };
 AuxStreams* aux_streams(cudaStream_t owner) {
   static std::mutex mu;
@@ -267,6 +289,7 @@ AuxStreams* aux_streams(cudaStream_t owner) {
   for (int i = 0; i < 2; ++i) ok &= cudaStreamCreateWithFlags(&aux->s[i], cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaEventCreateWithFlags(&aux->fork, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < 2; ++i) ok &= cudaEventCreateWithFlags(&aux->join[i], cudaEventDisableTiming) == cudaSuccess;
+  ok &= cudaEventCreateWithFlags(&aux->nfused, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { delete aux; return nullptr; }
   sets.push_back(aux);
   return aux;
@@ -313,7 +336,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
       a.chunks2 = 1;
     }
     a.a_stages = 2;                       // double-buffered across chunks AND across tiles (persistent kernel)
-    a.act = l.act; a.cout = l.cout; a.cout_pad = l.cout_pad; a.nt = l.nt; a.taps = l.k * l.k;
+    a.act = l.act; a.cout = l.nfuse_layer >= 0 ? l.cout_pad : l.cout; a.cout_pad = l.cout_pad; a.nt = l.nt; a.taps = l.k * l.k;
     a.fmt = cfg->operand_dtype;
     if (impl == POPNET_FWD_IMPL_SIMT) return launch_conv_simt(a, st);
     // shrink the A staging if the tile does not fit next to two B stages
@@ -359,9 +382,17 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     POPNET_CUDA_TRY(cudaEventRecord(aux->fork, st));
     for (int b = 0; b < 2; ++b) POPNET_CUDA_TRY(cudaStreamWaitEvent(aux->s[b], aux->fork, 0));
     cudaStream_t main_st = st;
+    const bool fused_first = p.layers[base + 5].nfuse_layer >= 0;
     for (int b = 0; b < 3; ++b) {
       st = (b == 0) ? main_st : aux->s[b - 1];
-      for (int i = 0; i < 5; ++i) POPNET_TRY(run_conv(base + 5 * b + i));
+      for (int i = 0; i < 5; ++i) {
+        if (b == 2 && i == 0 && fused_first) {           // computed by the heat-map branch's fused first launch
+          POPNET_CUDA_TRY(cudaStreamWaitEvent(st, aux->nfused, 0));
+          continue;
+        }
+        POPNET_TRY(run_conv(base + 5 * b + i));
+        if (b == 1 && i == 0 && fused_first) POPNET_CUDA_TRY(cudaEventRecord(aux->nfused, st));
+      }
     }
     st = main_st;
     for (int b = 0; b < 2; ++b) {

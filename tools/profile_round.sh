@@ -6,8 +6,8 @@ python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null
 python tools/forward_timeline.py > gpurun_out/forward_timeline.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"conv_tc|stem_kernel|pool_kernel" -s 120 -c 40 --csv --log-file gpurun_out/forward_dram.csv python tools/time_forward.py --batch 64 --iters 1 > /dev/null 2>&1
-# 38 conv_tc/stem launches per forward: 114 = start of the 4th forward (stem, layers 1-6, 8); 124 = its stage-1 branches
-ncu --set full --clock-control none --import-source on -k regex:"conv_tc|stem_kernel" -s 114 -c 8 -o gpurun_out/prof_conv_block python tools/time_forward.py --batch 64 --iters 1 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"conv_tc|stem_kernel" -s 122 -c 13 -o gpurun_out/prof_conv python tools/time_forward.py --batch 64 --iters 1 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"conv_tc|stem_kernel|pool_kernel" -s 114 -c 38 --csv --log-file gpurun_out/forward_dram.csv python tools/time_forward.py --batch 64 --iters 1 > /dev/null 2>&1
+# 36 conv_tc/stem launches per forward: 108 = start of the 4th forward (stem, layers 1-6, 8); 116 = its stage-1 branches
+ncu --set full --clock-control none --import-source on -k regex:"conv_tc|stem_kernel" -s 108 -c 8 -o gpurun_out/prof_conv_block python tools/time_forward.py --batch 64 --iters 1 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"conv_tc|stem_kernel" -s 116 -c 12 -o gpurun_out/prof_conv python tools/time_forward.py --batch 64 --iters 1 > /dev/null 2>&1
 ls -la gpurun_out

@@ -65,12 +65,12 @@ subprocess.run(["cp", os.path.join(OUT, "launches_bench.csv"), os.path.join(PROF
 
 # ---- 2. DRAM traffic of one forward
 k = read_ncu_csv(os.path.join(OUT, "forward_dram.csv"))
-assert short(k[0]["name"]).startswith("stem_kernel") and len(k) == 40, (k[0]["name"], len(k))
+assert short(k[0]["name"]).startswith("stem_kernel") and len(k) == 38, (k[0]["name"], len(k))
 rd = sum(d.get("dram__bytes_read.sum", 0) for d in k)
 wr = sum(d.get("dram__bytes_write.sum", 0) for d in k)
 out = {"command": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-                  "-k regex:'conv_tc|stem_kernel|pool_kernel' -s 120 -c 40 python tools/time_forward.py --batch 64 --iters 1",
-       "what": "one forward at batch 64 (40 kernels: stem, 2 pools, 37 conv_tc_kernel launches), B200",
+                  "-k regex:'conv_tc|stem_kernel|pool_kernel' -s 114 -c 38 python tools/time_forward.py --batch 64 --iters 1",
+       "what": "one forward at batch 64 (38 kernels: stem, 2 pools, 35 conv_tc_kernel launches), B200",
        "kernels": len(k), "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_total": rd + wr,
        "sum_kernel_time_us_serialised": sum(d["gpu__time_duration.sum"] for d in k),
        "per_kernel": [{"kernel": short(d["name"])[:48], "us": round(d["gpu__time_duration.sum"], 1),

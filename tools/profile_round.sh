@@ -10,4 +10,8 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
 # 36 conv_tc/stem launches per forward: 108 = start of the 4th forward (stem, layers 1-6, 8); 116 = its stage-1 branches
 ncu --set full --clock-control none --import-source on -k regex:"conv_tc|stem_kernel" -s 108 -c 8 -o gpurun_out/prof_conv_block python tools/time_forward.py --batch 64 --iters 1 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"conv_tc|stem_kernel" -s 116 -c 12 -o gpurun_out/prof_conv python tools/time_forward.py --batch 64 --iters 1 > /dev/null 2>&1
+# the .ncu-rep files are ~40 MB each and gpurun only brings back 64 MiB: keep the raw-page CSVs instead
+for r in prof_conv_block prof_conv; do
+  ncu -i gpurun_out/$r.ncu-rep --page raw --csv > gpurun_out/$r.raw.csv 2>/dev/null && rm -f gpurun_out/$r.ncu-rep
+done
 ls -la gpurun_out

@@ -78,7 +78,7 @@ out = {"command": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dra
 json.dump(out, open(os.path.join(PROF, tag + "_forward_dram_traffic.json"), "w"), indent=1)
 
 # ---- 3. ncu --set full detail of the forward's first 13 tensor-core launches
-reps = [r for r in (os.path.join(OUT, "prof_conv_block.ncu-rep"), os.path.join(OUT, "prof_conv.ncu-rep")) if os.path.exists(r)]
+reps = [r for r in (os.path.join(OUT, "prof_conv_block.raw.csv"), os.path.join(OUT, "prof_conv.raw.csv")) if os.path.exists(r)]
 if reps:
     METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
                "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.sum",
@@ -87,13 +87,12 @@ if reps:
                "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
                "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
     with open(os.path.join(PROF, tag + "_conv_tc_ncu_summary.txt"), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:'conv_tc|stem_kernel' -s 114 -c 8 / -s 122 -c 13 python tools/time_forward.py --batch 64 --iters 1\n")
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:'conv_tc|stem_kernel' -s 108 -c 8 / -s 116 -c 12 python tools/time_forward.py --batch 64 --iters 1\n")
         f.write("# B200, forward at batch 64, bf16 operands: stem + layers 1-6 and 8 (first capture, if present), then the stage-1 branch convs.\n")
         f.write("# conv_tc_kernel template arguments: <NT, NACC, TAPS, B stages, B resident, debug>.  The .ncu-rep files are scratch (not committed).\n\n")
         allrows = []
         for rep in reps:
-            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-            rows = list(csv.reader(raw.splitlines()))
+            rows = list(csv.reader(open(rep)))
             hdr, units = rows[0], rows[1]
             allrows += rows[2:]
         for r in allrows:

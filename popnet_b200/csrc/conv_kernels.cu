@@ -677,8 +677,14 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvArgs a) {
 // same TMEM epilogue; the input image is read through L1 (every pixel feeds ~12 taps).
 // ------------------------------------------------------------------------------------------------
 constexpr int kStemThreads = 128;
+#ifndef POPNET_STEM_BATCHES
+#define POPNET_STEM_BATCHES 2
+#endif
+constexpr int kStemBatches = POPNET_STEM_BATCHES;   // 2: 16 loads in flight per thread, 64 registers, 8 CTAs per SM (30.7 us);
+                                                    // 1: 32 loads, 72 registers, 6 CTAs per SM (32.5 us, same box)
+constexpr int kStemCtasPerSm = kStemBatches == 1 ? 6 : 8;
 
-__global__ void __launch_bounds__(kStemThreads, 8) stem_kernel(const StemArgs a) {
+__global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(const StemArgs a) {
   __shared__ __align__(128) h16 sA[8 * 128 * 8];          // [k8][row][8]
   __shared__ __align__(128) h16 sB[8 * 64 * 8];           // [k8][cout][8]
   __shared__ float s_shift[64];
@@ -727,14 +733,14 @@ __global__ void __launch_bounds__(kStemThreads, 8) stem_kernel(const StemArgs a)
       bool cok[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) cok[j] = interior && (unsigned)(ix0 + 2 * j) < (unsigned)a.W;   // even: the pair is in or out together
-      // two batches of four rows: 16 loads in flight per thread (the 6-8 co-resident CTAs supply the rest of the
-      // memory-level parallelism) and half the registers of a single 32-load batch
+      // kStemBatches batches of rows: all loads of a batch are issued before their first use
+      constexpr int RB = 8 / kStemBatches;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float2 v[4][4];
+      for (int half = 0; half < kStemBatches; ++half) {
+        float2 v[RB][4];
 #pragma unroll
-        for (int r4 = 0; r4 < 4; ++r4) {
-          const int ry = half * 4 + r4;
+        for (int r4 = 0; r4 < RB; ++r4) {
+          const int ry = half * RB + r4;
           const bool rok = (unsigned)(iy0 + ry) < (unsigned)a.H;
           const float* row = p0 + ry * a.W;
 #pragma unroll
@@ -742,8 +748,8 @@ __global__ void __launch_bounds__(kStemThreads, 8) stem_kernel(const StemArgs a)
             v[r4][j] = (rok && cok[j]) ? __ldg(reinterpret_cast<const float2*>(row + 2 * j)) : make_float2(0.f, 0.f);
         }
 #pragma unroll
-        for (int r4 = 0; r4 < 4; ++r4)
-          reinterpret_cast<uint4*>(sA)[(half * 4 + r4) * 128 + tid] =
+        for (int r4 = 0; r4 < RB; ++r4)
+          reinterpret_cast<uint4*>(sA)[(half * RB + r4) * 128 + tid] =
               make_uint4(pack2(v[r4][0].x, v[r4][0].y, a.fmt), pack2(v[r4][1].x, v[r4][1].y, a.fmt),
                          pack2(v[r4][2].x, v[r4][2].y, a.fmt), pack2(v[r4][3].x, v[r4][3].y, a.fmt));
       }
@@ -944,7 +950,7 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
 int launch_stem(const StemArgs& a, cudaStream_t st) {
   const int P = (int)c8p_positions(a.N, a.H / 2, a.W / 2);
   const int tiles = (P + 127) / 128;
-  const int cps = 8;                    // CTAs per SM (TMEM: 8 x 64 columns; registers: 8 x 128 x 64); 4 / 6 / 8 measured equal
+  const int cps = kStemCtasPerSm;       // CTAs per SM (TMEM: 8 x 64 columns; registers: 8 x 128 x 64)
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(stem_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); once = true; }
   const int grid = tiles < 148 * cps ? tiles : 148 * cps;      // persistent: `cps` CTAs per SM walk the tiles

@@ -240,32 +240,38 @@ __device__ __forceinline__ void finish8(const ConvArgs& a, int pos, const PosInf
         *reinterpret_cast<const uint4*>(ob);
 }
 
-// hot-path epilogue of the hidden layers: 8 channels (one C8P vector) of one interior position.
-// activation as a slope: ReLU = 0, LeakyReLU = 0.1, none = 1
+// hot-path epilogue of the hidden layers: 8 channels (one C8P vector) of one position.
+// FMT (operand format) and MODE (0 = ReLU, 1 = slope multiply: LeakyReLU 0.1 / identity 1) are compile-time so that the
+// warp-uniform choices cost no predicated-off instructions; adds and multiplies run as packed f32x2 operations
+// (add.rn.f32x2 / mul.rn.f32x2, sm_100): same fp32 results, half the issue slots.
+template <int FMT, int MODE>
 __device__ __forceinline__ uint4 finish8_fast(const uint32_t* acc, const float* s_shift8, bool has_res, uint4 res,
-                                              float slope, bool interior, int fmt) {
-  float x[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[i]) + s_shift8[i];
+                                              float slope, bool interior) {
+  const float4 s0 = *reinterpret_cast<const float4*>(s_shift8), s1 = *reinterpret_cast<const float4*>(s_shift8 + 4);
+  float2 x[4];
+  x[0] = __fadd2_rn(make_float2(__uint_as_float(acc[0]), __uint_as_float(acc[1])), make_float2(s0.x, s0.y));
+  x[1] = __fadd2_rn(make_float2(__uint_as_float(acc[2]), __uint_as_float(acc[3])), make_float2(s0.z, s0.w));
+  x[2] = __fadd2_rn(make_float2(__uint_as_float(acc[4]), __uint_as_float(acc[5])), make_float2(s1.x, s1.y));
+  x[3] = __fadd2_rn(make_float2(__uint_as_float(acc[6]), __uint_as_float(acc[7])), make_float2(s1.z, s1.w));
   if (has_res) {
     const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
 #pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = __fadd2_rn(x[i], unpack2(rw[i], FMT));
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = make_float2(fmaxf(x[i].x, 0.f), fmaxf(x[i].y, 0.f));
+  } else {
+    const float2 sl = make_float2(slope, slope);
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack2(rw[i], fmt);
-      x[2 * i] += f.x;
-      x[2 * i + 1] += f.y;
+      const float2 y = __fmul2_rn(x[i], sl);                          // slope in (0,1]: LeakyReLU 0.1, identity 1
+      x[i] = make_float2(fmaxf(x[i].x, y.x), fmaxf(x[i].y, y.y));
     }
   }
-  if (slope == 0.f) {                                                // warp-uniform: ReLU without the multiply
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], slope * x[i]);    // slope in (0,1]: LeakyReLU 0.1, identity 1
-  }
   uint4 o;
-  o.x = pack2(x[0], x[1], fmt); o.y = pack2(x[2], x[3], fmt); o.z = pack2(x[4], x[5], fmt); o.w = pack2(x[6], x[7], fmt);
-  if (!interior) o = make_uint4(0u, 0u, 0u, 0u);                     // padding ring stays zero
+  o.x = pack2(x[0].x, x[0].y, FMT); o.y = pack2(x[1].x, x[1].y, FMT); o.z = pack2(x[2].x, x[2].y, FMT); o.w = pack2(x[3].x, x[3].y, FMT);
+  if (!interior) o = make_uint4(0u, 0u, 0u, 0u);                     // zero cells stay zero
   return o;
 }
 
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   uint8_t* sB = smem + (((size_t)ast * a_stage_bytes + 127) & ~(size_t)127);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)kBSlots * kBStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
-  float* s_shift = reinterpret_cast<float*>(bars + kNumBars + 1);         // [NT]
+  float* s_shift = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + kNumBars + 1) + 15) & ~(uintptr_t)15);   // [NT], 16 B aligned
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8u * s; };
   auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -522,6 +528,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
     const bool head = a.act == kActHeadPaf || a.act == kActHeadHeat;
     const float slope = a.act == kActRelu ? 0.f : (a.act == kActLeaky ? 0.1f : 1.f);
     const uint32_t mHs = div_magic(a.Hs), mWp = div_magic(a.Wp);
+    const int epi_variant = (a.fmt != 0 ? 2 : 0) + (slope == 0.f ? 0 : 1);
     long long wait_full = 0, busy = 0;
     int ti = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
@@ -586,10 +593,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
           }
           tmem_ld_wait();
           if (pi.in_range && !(dbg & 2)) {
+            auto store4 = [&](auto fmt_c, auto mode_c) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint4 o = finish8_fast(r + g * 8, s_shift + j * 32 + g * 8, has_res, rs[g], slope, pi.interior, a.fmt);
-              *reinterpret_cast<uint4*>(a.out + (long long)(plane + g) * a.out_plane_stride + (long long)pos * 8) = o;
+              for (int g = 0; g < 4; ++g) {
+                const uint4 o = finish8_fast<decltype(fmt_c)::value, decltype(mode_c)::value>(
+                    r + g * 8, s_shift + j * 32 + g * 8, has_res, rs[g], slope, pi.interior);
+                *reinterpret_cast<uint4*>(a.out + (long long)(plane + g) * a.out_plane_stride + (long long)pos * 8) = o;
+              }
+            };
+            using std::integral_constant;
+            switch (epi_variant) {                    // warp-uniform: (operand format, ReLU | slope)
+              case 0: store4(integral_constant<int, 0>{}, integral_constant<int, 0>{}); break;
+              case 1: store4(integral_constant<int, 0>{}, integral_constant<int, 1>{}); break;
+              case 2: store4(integral_constant<int, 1>{}, integral_constant<int, 0>{}); break;
+              default: store4(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
             }
           }
         }
@@ -671,7 +688,7 @@ constexpr int kStemCtasPerSm = kStemBatches == 1 ? 6 : 8;
 __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(const StemArgs a) {
   __shared__ __align__(128) h16 sA[8 * 128 * 8];          // [k8][row][8]
   __shared__ __align__(128) h16 sB[8 * 64 * 8];           // [k8][cout][8]
-  __shared__ float s_shift[64];
+  __shared__ __align__(16) float s_shift[64];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -763,7 +780,9 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
       if (pos < P) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const uint4 o = finish8_fast(r + g * 8, s_shift + j * 32 + g * 8, false, make_uint4(0, 0, 0, 0), 0.f, interior, a.fmt);
+          const uint4 o = a.fmt == 0
+              ? finish8_fast<0, 0>(r + g * 8, s_shift + j * 32 + g * 8, false, make_uint4(0, 0, 0, 0), 0.f, interior)
+              : finish8_fast<1, 0>(r + g * 8, s_shift + j * 32 + g * 8, false, make_uint4(0, 0, 0, 0), 0.f, interior);
           *reinterpret_cast<uint4*>(a.out + (long long)(j * 4 + g) * a.out_plane_stride + (long long)pos * 8) = o;
         }
       }

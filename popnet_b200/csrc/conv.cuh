@@ -68,6 +68,7 @@ struct ConvArgs {
   int fmt;                      // 0 = bf16, 1 = fp16 operands
   long long* probe;             // optional [gridDim.x][16] clock64 stamps (bring-up / tuning), else nullptr
   int dbg;                      // bring-up switches: 1 = skip MMA issue, 2 = skip epilogue stores
+  int mc;                       // 1 = cluster-of-two kernel with multicast weight stages (conv_kernels.cu, "MC")
   unsigned long long* trace;    // optional [3] globaltimer stamps {first CTA in, first CTA past griddepcontrol.wait, last CTA out}
 };
 

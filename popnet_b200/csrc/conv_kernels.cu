@@ -76,6 +76,22 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// ---- thread-block cluster of two CTAs (MC kernels): B (weight) stages are loaded half by each CTA and multicast to both
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy delivered to the same shared-memory offset (and signalled on the same mbarrier offset) of every CTA in `mask`
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
 // One lane of a fully converged warp.  Unlike `lane == 0`, the compiler knows the elected region runs on exactly one
 // thread and issues the uniform-datapath tcgen05 instructions directly; behind a plain lane test it wraps EVERY
 // tcgen05.mma / commit in an ELECT + BRA.U.ANY serialisation loop (4 extra dependent instructions per MMA).
@@ -146,6 +162,12 @@ __device__ __forceinline__ void static_for(F&& f) {
 // mbarrier arrive when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// the same arrive delivered to the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -320,8 +342,15 @@ constexpr int acc_stages() { return (2 * NACC * NT <= 512) ? 2 : 1; }
 //         because the tensor core's instruction queue is shallow -- every instruction the issuing thread
 //         spends between two MMAs is exposed (measured: tools/umma_bench.cu).
 //   DBG:  bring-up instantiation with clock64 probes and debug switches; the product path compiles them out.
-template <int NT, int NACC, int TAPS, int BST, bool BRES, bool DBG>
+//   MC:   clusters of two CTAs share the weight stream: each CTA loads half of every B stage and multicasts it to both, a
+//         stage is released when BOTH CTAs' MMAs have consumed it (commit multicast to both b_empty barriers).  Halves
+//         the L2 weight traffic per output, which is what limits how small a tile may be: with it the N = 256 layers
+//         run 128-position tiles with double-buffered accumulators (epilogue hidden) instead of 256-position tiles
+//         whose two accumulators fill the TMEM.  Both CTAs walk the same number of tiles (the last may be a dummy
+//         that only keeps the B ring in step).
+template <int NT, int NACC, int TAPS, int BST, bool BRES, bool DBG, bool MC = false>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a) {
+  static_assert(!(MC && BRES), "multicast applies to the B ring");
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int MT = NACC * 128;
   constexpr int AS = acc_stages<NT, NACC>();
@@ -352,6 +381,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (a.P + MT - 1) / MT;
+  // MC: every CTA walks the same number of tile slots (the B ring of a cluster must stay in step); slots past the last
+  // tile are dummies: their B stages are loaded and released, nothing else happens
+  const int tile_end = MC ? (int)((num_tiles + gridDim.x - 1) / gridDim.x * gridDim.x) : num_tiles;
+  const uint32_t cta_rank = MC ? cluster_ctarank() : 0u;
   long long* probe = (DBG && a.probe) ? a.probe + (long long)blockIdx.x * 16 : nullptr;
   const int dbg = DBG ? a.dbg : 0;
   if (probe && threadIdx.x == 0) probe[0] = clock64();
@@ -362,9 +395,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNumBars; ++i) mbar_init(bar0 + 8u * i, (i >= 4 + 2 * BST + AS) ? (uint32_t)kEpiWarps : 1u);   // acc_empty: one arrive per epilogue warp
+    for (int i = 0; i < kNumBars; ++i) {
+      uint32_t cnt = 1u;
+      if (i >= 4 + 2 * BST + AS) cnt = (uint32_t)kEpiWarps;                    // acc_empty: one arrive per epilogue warp
+      else if (MC && i >= 4 + BST && i < 4 + 2 * BST) cnt = 2u;                // b_empty: the MMA threads of both CTAs
+      mbar_init(bar0 + 8u * i, cnt);
+    }
     fence_mbar_init();
   }
+  if (MC) cluster_sync_all();       // the peer's multicast copies / commits may reach this CTA's barriers from here on
   for (int i = threadIdx.x; i < NT; i += kTcThreads) s_shift[i] = a.shift[i];
   if (warp == 2) {
     tmem_alloc(smem_u32(tmem_slot), kCols);
@@ -387,21 +426,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
         for (int t = 0; t < TAPS; ++t)
           bulk_g2s(smem_u32(sB + (size_t)t * kBStageBytes), a.w + (long long)t * k8_total * NT * 8, kBStageBytes, b_full(0));
       }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         const int t0 = tile * MT;
-        for (int c = 0; c < chunks_all; ++c, ++ia) {
+        const bool live = tile < num_tiles;                 // (always true without MC)
+        for (int c = 0; c < chunks_all; ++c) {
           const bool ex = c >= chunks;                      // extra 1x1 chunk of the fused shortcut
-          const h16* src = ex ? a.in2 + (long long)((c - chunks) * 8) * a.in2_plane_stride
-                              : a.in + (long long)(c * 8) * a.in_plane_stride;
-          const long long pstride = ex ? a.in2_plane_stride : a.in_plane_stride;
-          const int as = ia % ast;
-          if (ia >= ast) mbar_wait_relaxed(a_empty(as), ((ia / ast) - 1) & 1);
-          if ((dbg & 16) && ia >= ast) mbar_arrive(a_full(as));      // tuning: no copy traffic after the first fill
-          else {
-            mbar_expect_tx(a_full(as), a_stage_bytes);
-            for (int g = 0; g < 8; ++g)
-              bulk_g2s(smem_u32(sA + (size_t)as * a_stage_bytes + (size_t)g * a_plane_bytes),
-                       src + (long long)g * pstride + (long long)(t0 - halo) * 8, a_plane_bytes, a_full(as));
+          if (live) {
+            const h16* src = ex ? a.in2 + (long long)((c - chunks) * 8) * a.in2_plane_stride
+                                : a.in + (long long)(c * 8) * a.in_plane_stride;
+            const long long pstride = ex ? a.in2_plane_stride : a.in_plane_stride;
+            const int as = ia % ast;
+            if (ia >= ast) mbar_wait_relaxed(a_empty(as), ((ia / ast) - 1) & 1);
+            if ((dbg & 16) && ia >= ast) mbar_arrive(a_full(as));      // tuning: no copy traffic after the first fill
+            else {
+              mbar_expect_tx(a_full(as), a_stage_bytes);
+              for (int g = 0; g < 8; ++g)
+                bulk_g2s(smem_u32(sA + (size_t)as * a_stage_bytes + (size_t)g * a_plane_bytes),
+                         src + (long long)g * pstride + (long long)(t0 - halo) * 8, a_plane_bytes, a_full(as));
+            }
+            ++ia;
           }
           const int ntap = ex ? 1 : TAPS;
           for (int t = 0; t < ntap && !BRES; ++t, ++ib) {
@@ -412,7 +455,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
               const long long woff = ex ? ((long long)TAPS * k8_total + (c - chunks) * 8) * NT * 8
                                         : ((long long)t * k8_total + c * 8) * NT * 8;
               mbar_expect_tx(b_full(bs), kBStageBytes);
-              bulk_g2s(smem_u32(sB + (size_t)bs * kBStageBytes), a.w + woff, kBStageBytes, b_full(bs));
+              if (MC) {     // this CTA's half (input-channel groups 4*rank .. 4*rank+3) to both CTAs; the peer sends the other
+                bulk_g2s_mc(smem_u32(sB + (size_t)bs * kBStageBytes) + cta_rank * (kBStageBytes / 2),
+                            a.w + woff + (long long)cta_rank * (kBStageBytes / 4), kBStageBytes / 2, b_full(bs), (uint16_t)3);
+              } else {
+                bulk_g2s(smem_u32(sB + (size_t)bs * kBStageBytes), a.w + woff, kBStageBytes, b_full(bs));
+              }
             }
           }
         }
@@ -439,7 +487,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
       uint32_t aph = 0, bph = 0;
       bool b_ready = false;                       // b_full(bs) already observed
       if (BRES) { mbar_wait(b_full(0), 0); b_ready = true; }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      // B stage consumed: arrive on its empty barrier when the MMAs issued so far retire (MC: in both CTAs of the cluster)
+      auto release_b = [&](int stage) {
+        if (MC) umma_commit_mc(b_empty(stage), (uint16_t)3);
+        else umma_commit(b_empty(stage));
+      };
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        if (MC && tile >= num_tiles) {
+          // dummy slot: keep the shared B ring in step with the peer -- take every stage and release it again
+          for (int c = 0; c < chunks_all; ++c) {
+            const int ntap = c >= chunks ? 1 : TAPS;
+            for (int t = 0; t < ntap; ++t) {
+              if (!b_ready) mbar_wait(b_full(bs), bph);
+              b_ready = false;
+              release_b(bs);
+              if (++bs == BST) { bs = 0; bph ^= 1; }
+            }
+          }
+          continue;
+        }
         const int s = ti % AS;
         if (ti >= AS) {
           long long tw = probe ? clock64() : 0;
@@ -483,7 +549,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
                   constexpr int acc = decltype(acc_c)::value;
                   umma_off<acc * 128, kk * (int)b_kstep, acc * NT>(tmem_acc, a_lo_k, desc_hi, b_lo_tap, desc_hi, idesc,
                                                                    (kk == 0) ? accumulate : 1u);
-                  if (!BRES && kk == 0 && acc == 0 && prev_bs >= 0) umma_commit(b_empty(prev_bs));   // (also covers the MMA above)
+                  if (!BRES && kk == 0 && acc == 0 && prev_bs >= 0) release_b(prev_bs);   // (also covers the MMA above)
                   if (!BRES && (NACC > 1 ? (kk == 0 && acc == 1) : (kk == 1))) {
                     // look ahead: next B stage (also across chunk / tile boundaries); one probe only -- if it is not there
                     // yet, block at the top of the next tap.  Deadlock-free: that slot was released by a tap already issued
@@ -493,7 +559,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
                 });
               });
             } else if (!BRES) {
-              if (prev_bs >= 0) umma_commit(b_empty(prev_bs));
+              if (prev_bs >= 0) release_b(prev_bs);
               b_ready = mbar_try_wait(b_full(nbs), nbph);
             }
             accumulate = 1u;
@@ -512,11 +578,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
               for (int d = 0; d < 3; ++d) tap_body(row0 + d - 1, r * 3 + d);
             }
           }
-          if (!BRES) umma_commit(b_empty(prev_bs));      // last tap of the chunk
+          if (!BRES) release_b(prev_bs);                 // last tap of the chunk
           umma_commit(a_empty(as));
           if (++as == ast) { as = 0; aph ^= 1; }
         }
         umma_commit(acc_full(s));
+        ++ti;
       }
       if (probe) { probe[3] = wait_a; probe[4] = wait_b; probe[5] = clock64(); probe[10] = wait_acc; probe[9] = ti; }
     }
@@ -621,6 +688,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();        // the peer may still multicast into this CTA's shared memory / barriers until it is done too
   if (probe && threadIdx.x == 0) probe[8] = clock64();
   trace_max(a.trace, 2);
   if (warp == 2) {
@@ -847,6 +915,8 @@ unsigned long long* next_trace_slot(int tag) {
   return g_trace_buf + 4 * (size_t)i;
 }
 
+constexpr size_t kSmemLimit = 227 * 1024;
+
 // launch configuration with programmatic stream serialization (PDL) enabled
 cudaLaunchAttribute g_pdl_attr[1];
 cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
@@ -893,7 +963,6 @@ int launch_tc_bst(const ConvArgs& a, int bst, size_t smem, cudaStream_t st) {
 
 }  // namespace
 
-constexpr size_t kSmemLimit = 227 * 1024;
 
 size_t conv_tc_smem_bytes(int nt, int nacc, int taps, int a_stages, int Wp, int* b_stages_out, bool b_resident) {
   const int halo = taps == 9 ? Wp + 1 : 0;
@@ -910,7 +979,43 @@ size_t conv_tc_smem_bytes(int nt, int nacc, int taps, int a_stages, int Wp, int*
   return a_bytes + bst * b_stage + misc;
 }
 
+namespace {
+// cluster-of-two launch of the multicast variant (programmatic dependent launch + cluster dimension)
+template <int NT, int NACC, int TAPS, int BST>
+int launch_tc_mc(const ConvArgs& a, cudaStream_t st) {
+  auto kern = conv_tc_kernel<NT, NACC, TAPS, BST, false, false, true>;
+  const int halo = TAPS == 9 ? a.Wp + 1 : 0;
+  const size_t a_bytes = (((size_t)a.a_stages * 8 * (NACC * 128 + 2 * halo) * 16) + 127) & ~(size_t)127;
+  const size_t smem = a_bytes + (size_t)BST * 8 * NT * 16 + 256 + (size_t)NT * 4;
+  if (smem > kSmemLimit || a.cout_pad != NT || a.chunks2 != 0) return POPNET_ERR_UNSUPPORTED;
+  POPNET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  POPNET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  const int tiles = (a.P + NACC * 128 - 1) / (NACC * 128);
+  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  grid = (grid + 1) & ~1;                                      // whole clusters (148 is even)
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = 2; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = attrs; cfg.numAttrs = 2;
+  ConvArgs at = a;
+  at.trace = next_trace_slot(NT * 1000 + NACC * 100 + TAPS * 10 + 5);
+  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, at));
+  POPNET_AFTER_LAUNCH();
+  return POPNET_OK;
+}
+}  // namespace
+
 int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st) {
+  if (a.mc) {
+    if (a.probe != nullptr || a.dbg != 0) return POPNET_ERR_UNSUPPORTED;
+    if (a.nt == 256 && nacc == 1 && a.taps == 9) return launch_tc_mc<256, 1, 9, 5>(a, st);
+    if (a.nt == 128 && nacc == 2 && a.taps == 9) return launch_tc_mc<128, 2, 9, 6>(a, st);
+    return POPNET_ERR_UNSUPPORTED;
+  }
   int bst = 0;
   // weights resident in shared memory whenever the layer is a single chunk and everything fits
   const bool bres = a.chunks == 1 && a.taps == 9 && a.nt == 64 &&

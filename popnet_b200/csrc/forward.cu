@@ -46,6 +46,7 @@ struct Layer {
   int remap_s2;              // input channels follow the S2IN layout
   int fuse_layer;            // index of a 1x1 layer whose weights are K-concatenated here (-1 = none); its input is in2_buf
   int in2_buf;
+  int mc;                    // launch the cluster-of-two multicast kernel
   int nfuse_layer;           // index of a layer with the SAME input whose output channels are N-concatenated behind this
                              // layer's (-1 = none): one launch computes both, its planes continue into the next buffer
   size_t w_off, shift_off;   // bytes in the packed blob
@@ -94,7 +95,7 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
     l.cout_pad = (int)align_up(cout, nt);
     l.nt = nt; l.nacc = nacc; l.act = act;
     l.in_buf = in_buf; l.in_plane0 = in_plane0; l.out_buf = out_buf; l.out_plane0 = out_plane0; l.res_buf = res_buf;
-    l.head = head; l.stage = stage; l.remap_s2 = remap; l.fuse_layer = -1; l.in2_buf = -1; l.nfuse_layer = -1;
+    l.head = head; l.stage = stage; l.remap_s2 = remap; l.fuse_layer = -1; l.in2_buf = -1; l.nfuse_layer = -1; l.mc = 0;
     p.layers.push_back(l);
   };
   p.layers.clear();
@@ -115,6 +116,12 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   // branches already fill each other's idle SMs.
   const bool kFuseFirst = p.bufs[DA].off == p.bufs[SA].off + (size_t)(p.bufs[SA].C / 8) * p.bufs[SA].plane_stride &&
                           p.bufs[DA].plane_stride == p.bufs[SA].plane_stride;
+  // POPNET_MC=1: the N = 256 stage layers as cluster-of-two multicast kernels with 128-position tiles and double-buffered
+  // accumulators.  Validated (tests/test_forward.py) and 20-25 % faster per layer (#11: 56.6 -> 43.5 us in the timeline), but
+  // the forward as a whole does not gain (0.980 vs 0.971 ms, same box): the stage is then bounded by the serial heat-map chain
+  // and the power cap.  Off by default; kept as the basis for cta_group::2 pairs.
+  int kMc = 0;
+  if (const char* e = getenv("POPNET_MC")) kMc = atoi(e);
   int kStageNacc = 4;
   if (const char* e = getenv("POPNET_STAGE_NACC")) { const int v = atoi(e); if (v >= 2 && v <= 4) kStageNacc = v; }
   for (int s = 1; s <= 2; ++s) {
@@ -122,9 +129,9 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
     const int cin = (s == 1) ? 128 : 128 + L2 + K1 + L1;
     const int remap = (s == 2);
     // paf branch: 3x3 -> 256, 256, 256, 1x1 -> 128, 1x1 -> 2L
-    add(cin, 256, 3, 256, 2, kActLeaky, S2IN, in0, LA, 0, -1, 0, s, remap);
-    add(256, 256, 3, 256, 2, kActLeaky, LA, 0, LB, 0, -1, 0, s, 0);
-    add(256, 256, 3, 256, 2, kActLeaky, LB, 0, LA, 0, -1, 0, s, 0);
+    add(cin, 256, 3, 256, kMc ? 1 : 2, kActLeaky, S2IN, in0, LA, 0, -1, 0, s, remap); p.layers.back().mc = kMc ? 1 : 0;
+    add(256, 256, 3, 256, kMc ? 1 : 2, kActLeaky, LA, 0, LB, 0, -1, 0, s, 0);         p.layers.back().mc = kMc ? 1 : 0;
+    add(256, 256, 3, 256, kMc ? 1 : 2, kActLeaky, LB, 0, LA, 0, -1, 0, s, 0);         p.layers.back().mc = kMc ? 1 : 0;
     add(256, 128, 1, 128, kStageNacc, kActLeaky, LA, 0, LC, 0, -1, 0, s, 0);
     add(128, L2, 1, 32, kStageNacc, kActHeadPaf, LC, 0, (s == 1) ? S2IN : -1, 0, -1, 1, s, 0);
     // heat-map branch: 3x3 -> 128 x4, 3x3 -> K+1
@@ -134,7 +141,7 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
     if (kFuseFirst) {
       Layer& f = p.layers.back();
       f.nfuse_layer = (int)p.layers.size() + 4;       // the depth branch's first conv (weights only; never launched)
-      f.nt = 256; f.nacc = 2; f.cout_pad = 256;
+      f.nt = 256; f.nacc = kMc ? 1 : 2; f.cout_pad = 256; f.mc = kMc ? 1 : 0;
     }
     add(128, 128, 3, 128, kStageNacc, kActLeaky, SA, 0, SB_, 0, -1, 0, s, 0);
     add(128, 128, 3, 128, kStageNacc, kActLeaky, SB_, 0, SA, 0, -1, 0, s, 0);
@@ -338,6 +345,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     a.a_stages = 2;                       // double-buffered across chunks AND across tiles (persistent kernel)
     a.act = l.act; a.cout = l.nfuse_layer >= 0 ? l.cout_pad : l.cout; a.cout_pad = l.cout_pad; a.nt = l.nt; a.taps = l.k * l.k;
     a.fmt = cfg->operand_dtype;
+    a.mc = l.mc;
     if (impl == POPNET_FWD_IMPL_SIMT) return launch_conv_simt(a, st);
     // shrink the A staging if the tile does not fit next to two B stages
     int bst = 0;
@@ -383,6 +391,8 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     for (int b = 0; b < 2; ++b) POPNET_CUDA_TRY(cudaStreamWaitEvent(aux->s[b], aux->fork, 0));
     cudaStream_t main_st = st;
     const bool fused_first = p.layers[base + 5].nfuse_layer >= 0;
+    // (enqueue order PAF, heat-map, depth; heat-map / depth first, or the auxiliary streams at high priority, measured
+    //  0.5 - 4 % slower)
     for (int b = 0; b < 3; ++b) {
       st = (b == 0) ? main_st : aux->s[b - 1];
       for (int i = 0; i < 5; ++i) {

@@ -104,3 +104,26 @@ def test_cuda_forward_batch_invariance(cuda_backend):
     torch.cuda.synchronize()
     assert torch.equal(p9[4:5], p1) and torch.equal(h9[4:5], h1) and torch.equal(d9[4:5], d1)
     assert torch.equal(p9[3:6], p3) and torch.equal(h9[3:6], h3) and torch.equal(d9[3:6], d3)
+
+
+@pytest.mark.gpu
+def test_cuda_forward_multicast_variant_identical(cuda_backend, monkeypatch):
+    """POPNET_MC=1 runs the N = 256 stage layers as cluster-of-two kernels whose weight stages are multicast (128-position
+    tiles, dummy tile slots, cross-CTA stage release).  Same K order per output, so the maps must be bit-identical to the
+    default path -- at a batch with dummy slots (odd tile counts) and at the bench batch."""
+    from popnet_b200 import synth
+    sd = network.synth_state_dict(seed=11, style="trained_like")
+    outs = {}
+    for mc in ("0", "1"):
+        monkeypatch.setenv("POPNET_MC", mc)
+        m = network.rtpose_light3d(15, 14, 2, input_dim=1)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        res = []
+        for B, seed in ((3, 5), (64, 6)):
+            x = torch.from_numpy(synth.depth_frames(B, seed=seed)).cuda()
+            (p, h, d), saved = m(x)
+            torch.cuda.synchronize()
+            res += [p.clone(), h.clone(), d.clone()] + [t.clone() for t in saved[:3]]
+        outs[mc] = res
+    for a, b in zip(outs["0"], outs["1"]):
+        assert torch.equal(a, b)

@@ -1013,7 +1013,6 @@ int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st) {
   if (a.mc) {
     if (a.probe != nullptr || a.dbg != 0) return POPNET_ERR_UNSUPPORTED;
     if (a.nt == 256 && nacc == 1 && a.taps == 9) return launch_tc_mc<256, 1, 9, 5>(a, st);
-    if (a.nt == 128 && nacc == 2 && a.taps == 9) return launch_tc_mc<128, 2, 9, 6>(a, st);
     return POPNET_ERR_UNSUPPORTED;
   }
   int bst = 0;

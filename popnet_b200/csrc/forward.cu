@@ -119,7 +119,8 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   // POPNET_MC=1: the N = 256 stage layers as cluster-of-two multicast kernels with 128-position tiles and double-buffered
   // accumulators.  Validated (tests/test_forward.py) and 20-25 % faster per layer (#11: 56.6 -> 43.5 us in the timeline), but
   // the forward as a whole does not gain (0.980 vs 0.971 ms, same box): the stage is then bounded by the serial heat-map chain
-  // and the power cap.  Off by default; kept as the basis for cta_group::2 pairs.
+  // and the power cap (the heat-map chain's 128 -> 128 convs as multicast kernels with 256-position tiles: 1.01 ms).
+  // Off by default; kept as the basis for cta_group::2 pairs.
   int kMc = 0;
   if (const char* e = getenv("POPNET_MC")) kMc = atoi(e);
   int kStageNacc = 4;

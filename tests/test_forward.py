@@ -127,3 +127,25 @@ def test_cuda_forward_multicast_variant_identical(cuda_backend, monkeypatch):
         outs[mc] = res
     for a, b in zip(outs["0"], outs["1"]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hw", [(160, 192), (224, 96), (64, 64)], ids=lambda v: "%dx%d" % v)
+def test_cuda_forward_other_input_sizes(hw, cuda_backend):
+    """The layer plan is generic in the input size (multiples of 8, non-square included): rows / columns / image pitch
+    all differ here, so any place that confuses H with W or Hs with Wp fails against the fp32 oracle."""
+    from oracle import forward_torch
+    from popnet_b200 import _abi
+    sd = network.synth_state_dict(seed=11, style="trained_like")
+    rng = np.random.default_rng(hw[0] * 1000 + hw[1])
+    x = rng.normal(0.0, 1.0, (3, 1, hw[0], hw[1])).astype(np.float32)
+    m = network.rtpose_light3d(15, 14, 2, input_dim=1)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m.operand_dtype = _abi.OPERAND_FP16
+    (paf, heat, depth), saved = m(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    (opaf, oheat, odepth), osaved = forward_torch.forward(sd, x)
+    assert tuple(paf.shape) == (3, 28, hw[0] // 8, hw[1] // 8)
+    for name, a, b in (("paf", paf, opaf), ("heat", heat, oheat), ("depth", depth, odepth), ("paf1", saved[0], osaved[0])):
+        err = float((a.cpu() - b).abs().max())
+        assert np.isfinite(err) and err <= TOL, (name, err)

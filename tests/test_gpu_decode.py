@@ -75,3 +75,17 @@ def test_paf_to_pose_signature(cuda_backend):
         assert np.array_equal(np.asarray(assoc).reshape(-1, 17), g["mp/native/%d/assoc" % f])
         humans, vis, conf = paf_to_human_list(jl, assoc)
         assert len(humans) == len(g["mp/native/%d/assoc" % f])
+
+
+@pytest.mark.parametrize("size", [160, 320], ids=["grid20", "grid40"])
+def test_decode_other_grid_sizes_vs_oracle(size, cuda_backend, oracle_lib):
+    """The decode takes the grid size as data (up to 64 x 64 cells): 20 x 20 and 40 x 40 grids, byte-for-byte vs the oracle."""
+    from popnet_b200 import _abi
+    from popnet_b200.topology import DecodeConfig, MP3DHP
+    heat, paf, depth, _ = synth.map_batch(24, seed=5 + size, persons=(1, 5), noise=0.01, size=size)
+    assert heat.shape[-1] == size // 8
+    params = _abi.make_decode_params(DecodeConfig(), MP3DHP, input_size=size)
+    dev = cuda_backend.decode(heat, paf, depth, params)
+    ora = oracle_lib.decode(heat, paf, depth, params)
+    assert helpers.records_equal(dev, ora) == []
+    assert int(dev["n_person"].sum()) >= 24 * 0.5

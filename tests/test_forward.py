@@ -130,6 +130,34 @@ def test_cuda_forward_multicast_variant_identical(cuda_backend, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_cuda_forward_pair_kernel_identical(cuda_backend, monkeypatch):
+    """The cta_group::2 pair kernel (default for the non-residual 64 -> 64 layers at 112 x 112) against the single-CTA kernel
+    (POPNET_PAIR=0), and with the residual layers included / 384-position tiles: same K order per output -> bit-identical.
+    Batch 3 gives odd tile counts (dummy tile slots), batch 64 is the bench shape."""
+    from popnet_b200 import synth
+    sd = network.synth_state_dict(seed=11, style="trained_like")
+    outs = {}
+    for tag, env in (("off", {"POPNET_PAIR": "0"}), ("default", {}), ("res3", {"POPNET_PAIR": "3", "POPNET_PAIR_RES": "1"}),
+                     ("res4", {"POPNET_PAIR": "4", "POPNET_PAIR_RES": "1"})):
+        monkeypatch.delenv("POPNET_PAIR", raising=False)
+        monkeypatch.delenv("POPNET_PAIR_RES", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = network.rtpose_light3d(15, 14, 2, input_dim=1)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        res = []
+        for B, seed in ((3, 5), (64, 6)):
+            x = torch.from_numpy(synth.depth_frames(B, seed=seed)).cuda()
+            (p, h, d), saved = m(x)
+            torch.cuda.synchronize()
+            res += [p.clone(), h.clone(), d.clone()]
+        outs[tag] = res
+    for tag in ("default", "res3", "res4"):
+        for a, b in zip(outs["off"], outs[tag]):
+            assert torch.equal(a, b), tag
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("hw", [(160, 192), (224, 96), (64, 64)], ids=lambda v: "%dx%d" % v)
 def test_cuda_forward_other_input_sizes(hw, cuda_backend):
     """The layer plan is generic in the input size (multiples of 8, non-square included): rows / columns / image pitch

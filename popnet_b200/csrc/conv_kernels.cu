@@ -1304,13 +1304,15 @@ int launch_pair64(const ConvArgs& a, cudaStream_t st) {
 }  // namespace
 
 int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st) {
-  // CTA-pair kernel (cta_group::2) for the large single-chunk 64 -> 64 3x3 layers without a residual input: 512-position
-  // tiles per CTA.  Measured (same box, A/B/A/B): 0.984 vs 0.994 ms per forward; the two layers it applies to go from 57 to
-  // 51 us.  The residual layers stay on the single-CTA kernel: they are HBM-bound (210 MB read + 105 MB written in 66 us --
-  // the 105 MB tensors do not survive in the L2 from one layer to the next) and the pair's coupled accumulator release makes
-  // them 4 us slower.  POPNET_PAIR=0 disables, 3 selects 384-position tiles, POPNET_PAIR_RES=1 includes the residual layers.
+  // CTA-pair kernel (cta_group::2) for the large single-chunk 64 -> 64 3x3 layers: opt-in with POPNET_PAIR=4 (512-position
+  // tiles) or 3 (384).  Measured, same box, A/B/A/B: the two non-residual layers go from 57 to 51 us and the forward ALONE
+  // from 0.994 to 0.984 ms -- but inside the pipelined step, where the decode of the previous batch shares the SMs, the
+  // step gets 1.6 % SLOWER (1.035 vs 1.019 ms: a cluster needs both SMs of a pair free at once), so it is off by default.
+  // The residual layers are HBM-bound (210 MB read + 105 MB written in 66 us -- the 105 MB tensors do not survive in the
+  // L2 from one layer to the next) and the pair's coupled accumulator release makes them 4 us slower
+  // (POPNET_PAIR_RES=1 includes them).
   const char* pe = getenv("POPNET_PAIR");
-  const int pair = pe ? atoi(pe) : 4;
+  const int pair = pe ? atoi(pe) : 0;
   const char* pr = getenv("POPNET_PAIR_RES");
   const bool pair_res = pr && atoi(pr) != 0;
   if (pair && !a.mc && a.nt == 64 && a.taps == 9 && a.chunks == 1 && a.chunks2 == 0 && a.head_out == nullptr &&

@@ -131,13 +131,13 @@ def test_cuda_forward_multicast_variant_identical(cuda_backend, monkeypatch):
 
 @pytest.mark.gpu
 def test_cuda_forward_pair_kernel_identical(cuda_backend, monkeypatch):
-    """The cta_group::2 pair kernel (default for the non-residual 64 -> 64 layers at 112 x 112) against the single-CTA kernel
-    (POPNET_PAIR=0), and with the residual layers included / 384-position tiles: same K order per output -> bit-identical.
+    """The cta_group::2 pair kernel (opt-in, POPNET_PAIR=4|3) for the 64 -> 64 layers at 112 x 112 against the single-CTA
+    kernel, without and with the residual layers, 512- and 384-position tiles: same K order per output -> bit-identical.
     Batch 3 gives odd tile counts (dummy tile slots), batch 64 is the bench shape."""
     from popnet_b200 import synth
     sd = network.synth_state_dict(seed=11, style="trained_like")
     outs = {}
-    for tag, env in (("off", {"POPNET_PAIR": "0"}), ("default", {}), ("res3", {"POPNET_PAIR": "3", "POPNET_PAIR_RES": "1"}),
+    for tag, env in (("off", {"POPNET_PAIR": "0"}), ("default", {"POPNET_PAIR": "4"}), ("res3", {"POPNET_PAIR": "3", "POPNET_PAIR_RES": "1"}),
                      ("res4", {"POPNET_PAIR": "4", "POPNET_PAIR_RES": "1"})):
         monkeypatch.delenv("POPNET_PAIR", raising=False)
         monkeypatch.delenv("POPNET_PAIR_RES", raising=False)

@@ -68,6 +68,8 @@ struct ConvArgs {
   int fmt;                      // 0 = bf16, 1 = fp16 operands
   long long* probe;             // optional [gridDim.x][16] clock64 stamps (bring-up / tuning), else nullptr
   int dbg;                      // bring-up switches: 1 = skip MMA issue, 2 = skip epilogue stores
+  int reverse;                  // 1 = walk the tiles from the last to the first (zig-zag between consecutive layers: a layer then
+                                //   starts on the positions its producer wrote last, which are the ones still in the L2)
   int mc;                       // 1 = cluster-of-two kernel with multicast weight stages (conv_kernels.cu, "MC")
   unsigned long long* trace;    // optional [3] globaltimer stamps {first CTA in, first CTA past griddepcontrol.wait, last CTA out}
 };
@@ -80,6 +82,7 @@ struct StemArgs {
   long long out_plane_stride;
   int N, H, W;                  // input size
   int fmt;
+  int reverse;
   unsigned long long* trace;
 };
 
@@ -91,6 +94,7 @@ struct PoolArgs {
   int planes;
   int N, H, W;                  // input spatial size (output is H/2 x W/2)
   int fmt;
+  int reverse;
   unsigned long long* trace;
 };
 

@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
           bulk_g2s(smem_u32(sB + (size_t)t * kBStageBytes), a.w + (long long)t * k8_total * NT * 8, kBStageBytes, b_full(0));
       }
       for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
-        const int t0 = tile * MT;
+        const int t0 = ((a.reverse && tile < num_tiles) ? num_tiles - 1 - tile : tile) * MT;
         const bool live = tile < num_tiles;                 // (always true without MC)
         for (int c = 0; c < chunks_all; ++c) {
           const bool ex = c >= chunks;                      // extra 1x1 chunk of the fused shortcut
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
     int ti = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
       const int s = ti % AS;
-      const int t0 = tile * MT;
+      const int t0 = ((a.reverse && tile < num_tiles) ? num_tiles - 1 - tile : tile) * MT;
       long long tw = probe ? clock64() : 0;
       mbar_wait_relaxed(acc_full(s), (ti / AS) & 1);
       tc_fence_after();
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
         // 8 lanes), one epilogue ahead of their use -- the residual tensor was written two layers ago and has left the
         // L2; without this the epilogue of the 64-channel residual layers waits on DRAM and outlasts the MMA phase.
         if (a.res != nullptr && tile + (int)gridDim.x < num_tiles && (lane & 7) == 0) {
-          const int tn0 = (tile + (int)gridDim.x) * MT;
+          const int tn0 = (a.reverse ? num_tiles - 1 - (tile + (int)gridDim.x) : tile + (int)gridDim.x) * MT;
 #pragma unroll 1
           for (int it = sub; it < kItems; it += 4) {
             const int acc = it / (NT / 32), j = it - acc * (NT / 32);
@@ -1052,7 +1052,7 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
   pdl_wait();
   trace_min(a.trace, 1);
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int pos = tile * 128 + tid;
+    const int pos = (a.reverse ? tiles - 1 - tile : tile) * 128 + tid;
     const PosInfo pi = c8p_locate_fast(pos, P, Hs, Wp, mHs, mWp);
     const int n = pi.n;
     const bool interior = pi.interior;
@@ -1135,7 +1135,7 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
 __global__ void __launch_bounds__(128) pool_kernel(const PoolArgs a) {
   const int Ho = a.H / 2, Wo = a.W / 2, Wpi = a.W + 1, Hsi = a.H + 1;
   const int P = (int)c8p_positions(a.N, Ho, Wo);
-  const int pos = blockIdx.x * 128 + threadIdx.x;
+  const int pos = (a.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * 128 + threadIdx.x;
   trace_min(a.trace, 0);
   pdl_launch_dependents();
   pdl_wait();

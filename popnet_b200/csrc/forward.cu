@@ -315,6 +315,11 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned char* blob = static_cast<const unsigned char*>(packed_dev);
 
+  // Zig-zag tile order through the 112 x 112 block (stem forward, layer 1 backward, layer 2 forward, ...): a layer starts on
+  // the positions its producer wrote last, the only part of the 105 MB tensor that is still in the 126 MB L2.  Measured in the
+  // bench, same box, A/B/A/B: 62.39 k vs 61.77 k frames/s; each 64 -> 64 layer 3 us shorter.  POPNET_ZIGZAG=0 disables.
+  const char* zz = getenv("POPNET_ZIGZAG");
+  const int zigzag = zz ? atoi(zz) : 1;
   auto run_conv = [&](int li) -> int {
     const Layer& l = p.layers[li];
     const Buf& bi = p.bufs[l.in_buf];
@@ -347,6 +352,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     a.act = l.act; a.cout = l.nfuse_layer >= 0 ? l.cout_pad : l.cout; a.cout_pad = l.cout_pad; a.nt = l.nt; a.taps = l.k * l.k;
     a.fmt = cfg->operand_dtype;
     a.mc = l.mc;
+    a.reverse = (zigzag && li >= 1 && li <= 4) ? (li & 1) : 0;
     if (impl == POPNET_FWD_IMPL_SIMT) return launch_conv_simt(a, st);
     // shrink the A staging if the tile does not fit next to two B stages
     int bst = 0;
@@ -361,6 +367,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     a.in = buf_ptr(workspace, bi, 0); a.in_plane_stride = bi.plane_stride;
     a.out = buf_ptr(workspace, p.bufs[out_buf], out_plane0); a.out_plane_stride = p.bufs[out_buf].plane_stride;
     a.planes = bi.C / 8; a.N = batch; a.H = bi.H; a.W = bi.W; a.fmt = cfg->operand_dtype;
+    a.reverse = (zigzag && in_buf == A112) ? 1 : 0;
     return launch_pool(a, st);
   };
 #define POPNET_TRY(expr) do { int _rc = (expr); if (_rc != POPNET_OK) return _rc; } while (0)

@@ -87,7 +87,8 @@ typedef struct PopnetDecodeParams {
   int32_t flip_y;                           /* ITOP: Y3 negated (evaluation_rtpose_light3d_itop.py:206) */
   int32_t max_peaks;                        /* <= POPNET_MAX_PEAKS                                 */
   int32_t max_persons;                      /* <= POPNET_MAX_PERSONS                               */
-  int32_t reserved;
+  int32_t depth_channels;                   /* planes per frame in `depth`: the network's third head has L + 1
+                                               (rtpose_light3d.py:299-309), joint j reads plane j; 0 means K        */
 } PopnetDecodeParams;
 
 /* Output buffers (see popnet_decode for which may be NULL).
@@ -109,7 +110,7 @@ typedef struct PopnetDecodeOut {
   uint32_t* flags;         /* [B]            POPNET_FLAG_*                                         */
 } PopnetDecodeOut;
 
-/* heat [B][K+1][gh][gw], paf [B][2L][gh][gw], depth [B][K][gh][gw]: fp32, channel-major (the layout
+/* heat [B][K+1][gh][gw], paf [B][2L][gh][gw], depth [B][depth_channels][gh][gw]: fp32, channel-major (the layout
  * the network writes; the reference transposes to HWC on the host, ...mpreal_ablation.py:176-178).
  * depth may be NULL (2D only: pose3d / Z are then not written).
  * peak_* and conn_* double as the stage-to-stage storage of the three decode kernels and are
@@ -135,6 +136,13 @@ POPNET_API int popnet_lift_depth(const float* heat, const float* depth, const in
 #define POPNET_LIFT_HEAT_MAX 2
 POPNET_API int popnet_lift_depth_mode(const float* heat, const float* depth, const int32_t* queries, int n, int grid_h,
                                       int grid_w, float depth_mean, float depth_std, int mode, float* out_z, void* stream);
+/* The same three reads with the helpers' `radius` argument (lib/utils/common.py:251,272,296): window
+ * [c - radius, c + radius] clipped to the grid, 0 <= radius <= 5 (up to 121 cells: NumPy's pairwise sum is reproduced for
+ * one 128-element block; larger windows return POPNET_ERR_UNSUPPORTED).  radius = 1 is what every reference call site
+ * passes and what popnet_decode uses for the assembled joints. */
+POPNET_API int popnet_lift_depth_window(const float* heat, const float* depth, const int32_t* queries, int n, int grid_h,
+                                        int grid_w, float depth_mean, float depth_std, int mode, int radius, float* out_z,
+                                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Evaluator.  Ragged lists-of-lists are CSR-packed by the host: humans of frame f are rows

@@ -93,6 +93,10 @@ def decode(heat, paf, depth, params):
     paf = np.ascontiguousarray(paf, np.float32)
     depth = None if depth is None else np.ascontiguousarray(depth, np.float32)
     B = heat.shape[0]
+    g = (params.grid_h, params.grid_w)
+    dc = params.depth_channels if params.depth_channels > 0 else params.num_joints
+    assert heat.shape == (B, params.num_joints + 1) + g and paf.shape == (B, 2 * params.num_limbs) + g, (heat.shape, paf.shape, g)
+    assert depth is None or depth.shape == (B, dc) + g, (depth.shape, dc, g)
     bufs = alloc_decode_out(B, params)
     out = _abi.DecodeOut(**{k: _p(v) for k, v in bufs.items()})
     rc = lib().oracle_decode(_p(heat), _p(paf), _p(depth), B, C.byref(params), C.byref(out))

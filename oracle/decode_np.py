@@ -301,16 +301,24 @@ def paf_to_human_list(joint_list: np.ndarray, assoc: np.ndarray):
 
 
 def _np_sum_f32(a: np.ndarray) -> f32:
-    """np.sum of a contiguous fp32 array of n <= 9 elements (numpy pairwise_sum)."""
+    """np.sum of a contiguous fp32 array of n <= 128 elements (numpy pairwise_sum, loops_utils.h): a plain loop below 8;
+    else eight running sums over whole blocks of 8, combined as a tree, then the tail in order."""
     a = a.ravel()
     n = len(a)
+    assert n <= 128
     if n < 8:
         r = f32(0.0)
         for v in a:
             r = f32(r + v)
         return r
-    r = f32(f32(f32(a[0] + a[1]) + f32(a[2] + a[3])) + f32(f32(a[4] + a[5]) + f32(a[6] + a[7])))
-    for v in a[8:]:
+    r8 = [f32(a[j]) for j in range(8)]
+    i = 8
+    while i < n - (n % 8):
+        for j in range(8):
+            r8[j] = f32(r8[j] + a[i + j])
+        i += 8
+    r = f32(f32(f32(r8[0] + r8[1]) + f32(r8[2] + r8[3])) + f32(f32(r8[4] + r8[5]) + f32(r8[6] + r8[7])))
+    for v in a[i:]:
         r = f32(r + v)
     return r
 

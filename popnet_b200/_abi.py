@@ -35,7 +35,7 @@ class DecodeParams(C.Structure):
         ("w_org", C.c_double), ("h_org", C.c_double),
         ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
         ("flip_y", C.c_int32), ("max_peaks", C.c_int32), ("max_persons", C.c_int32),
-        ("reserved", C.c_int32),
+        ("depth_channels", C.c_int32),
     ]
 
 
@@ -92,6 +92,8 @@ PROTOTYPES = {
     "popnet_eval_ap": (C.c_int, [C.POINTER(ApArgs), vp]),
     "popnet_lift_depth": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp]),
     "popnet_lift_depth_mode": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, vp, vp]),
+    "popnet_lift_depth_window": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                           vp, vp]),
     "popnet_eval_pck": (C.c_int, [C.POINTER(PckArgs), vp]),
     "popnet_eval_map_assign": (C.c_int, [C.POINTER(MapArgs), vp]),
     "popnet_num_conv_layers": (C.c_int, [C.POINTER(NetConfig)]),
@@ -114,16 +116,21 @@ def bind(lib):
     return lib
 
 
-def make_decode_params(cfg, cam, *, input_size=224, max_peaks=MAX_PEAKS, max_persons=MAX_PERSONS):
-    """DecodeParams from a topology.DecodeConfig and a topology.Camera."""
+def make_decode_params(cfg, cam, *, input_size=224, grid_hw=None, depth_channels=0, max_peaks=MAX_PEAKS,
+                       max_persons=MAX_PERSONS):
+    """DecodeParams from a topology.DecodeConfig and a topology.Camera.  ``grid_hw``: (rows, columns) of the maps --
+    default: the square grid of a square ``input_size`` network input; ``depth_channels``: planes per frame of the
+    depth tensor handed to the decode (0 = num_keypoints; the network's third head emits num_limbs + 1)."""
     p = DecodeParams()
     p.num_joints = cfg.num_keypoints
     p.num_limbs = len(cfg.limbs)
     for l, (a, b) in enumerate(cfg.limbs):
         p.limbs[l][0] = a
         p.limbs[l][1] = b
-    g = input_size // cfg.downsample
-    p.grid_h = p.grid_w = g
+    if grid_hw is None:
+        grid_hw = (input_size // cfg.downsample, input_size // cfg.downsample)
+    p.grid_h, p.grid_w = int(grid_hw[0]), int(grid_hw[1])
+    p.depth_channels = int(depth_channels)
     p.stride = cfg.downsample
     p.num_intermed_pts = cfg.num_intermed_pts
     p.thresh_heat = cfg.thresh_heatmap

@@ -80,6 +80,25 @@ def alloc_decode_out(B, params, device="cuda"):
     return out
 
 
+def check_decode_shapes(heat, paf, depth, params):
+    """The C ABI takes raw pointers: the map shapes must agree with the DecodeParams block or the kernels would index
+    with the wrong pitch / plane stride.  Raises (like POPNET_ERR_INVALID_ARG) instead of decoding garbage."""
+    B, K, L = heat.shape[0], params.num_joints, params.num_limbs
+    g = (params.grid_h, params.grid_w)
+    dc = params.depth_channels if params.depth_channels > 0 else K
+    want = {"heat": (B, K + 1) + g, "paf": (B, 2 * L) + g}
+    got = {"heat": tuple(heat.shape), "paf": tuple(paf.shape)}
+    if depth is not None:
+        want["depth"], got["depth"] = (B, dc) + g, tuple(depth.shape)
+    for k in want:
+        if want[k] != got[k]:
+            raise _lib.PopnetError("popnet_decode: %s has shape %s but the decode parameters (K=%d, L=%d, grid %dx%d, "
+                                   "depth_channels=%d) need %s" % (k, got[k], K, L, g[0], g[1], dc, want[k]))
+    for k, t in (("heat", heat), ("paf", paf), ("depth", depth)):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda):
+            raise _lib.PopnetError("popnet_decode: %s must be a contiguous fp32 CUDA tensor" % k)
+
+
 class CudaBackend:
     name = "cuda-sm100a"
 
@@ -159,6 +178,7 @@ class CudaBackend:
     def decode_device(self, heat, paf, depth, params, out=None):
         """Device tensors in, device tensors out (no synchronisation); `out` buffers may be reused."""
         B = heat.shape[0]
+        check_decode_shapes(heat, paf, depth, params)
         if out is None:
             out = alloc_decode_out(B, params)
         o = _abi.DecodeOut(**{k: _ptr(v) for k, v in out.items() if not k.startswith("_")})
@@ -174,16 +194,17 @@ class CudaBackend:
         res["flags"] = res["flags"].view(np.uint32)
         return res
 
-    def lift_depth(self, heat, depth, queries, depth_mean=0.0, depth_std=1.0, mode=_abi.LIFT_HEAT_WEIGHTED):
+    def lift_depth(self, heat, depth, queries, depth_mean=0.0, depth_std=1.0, mode=_abi.LIFT_HEAT_WEIGHTED, radius=1):
         """heat/depth: [planes, gh, gw] fp32 (heat may be None for LIFT_MEAN); queries [n,3] int32 (plane, cx, cy)
-        -> fp32 [n] (NumPy)."""
+        -> fp32 [n] (NumPy).  radius: half-width of the clipped window (0..5)."""
         d = _to_dev(depth, torch.float32)
         h = _to_dev(heat, torch.float32) if heat is not None else None
         q = _to_dev(np.ascontiguousarray(queries, np.int32))
         n = q.shape[0]
         out = torch.empty((n,), dtype=torch.float32, device="cuda")
-        _lib.check(self.lib.popnet_lift_depth_mode(_ptr(h), _ptr(d), _ptr(q), n, d.shape[-2], d.shape[-1], float(depth_mean),
-                                                   float(depth_std), int(mode), _ptr(out), _stream()), "popnet_lift_depth_mode")
+        _lib.check(self.lib.popnet_lift_depth_window(_ptr(h), _ptr(d), _ptr(q), n, d.shape[-2], d.shape[-1], float(depth_mean),
+                                                     float(depth_std), int(mode), int(radius), _ptr(out), _stream()),
+                   "popnet_lift_depth_window")
         return out.cpu().numpy()
 
     def preprocess_depth(self, frames, dst_hw, depth_max, depth_mean, depth_std):

@@ -1182,16 +1182,18 @@ unsigned long long* next_trace_slot(int tag) {
 
 constexpr size_t kSmemLimit = 227 * 1024;
 
-// launch configuration with programmatic stream serialization (PDL) enabled
-cudaLaunchAttribute g_pdl_attr[1];
-cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
-  g_pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  g_pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cfg.attrs = g_pdl_attr; cfg.numAttrs = 1;
-  return cfg;
-}
+// launch configuration with programmatic stream serialization (PDL) enabled; the attribute lives in the caller's frame
+struct PdlConfig {
+  cudaLaunchAttribute attr[1];
+  cudaLaunchConfig_t cfg;
+  PdlConfig(dim3 grid, dim3 block, size_t smem, cudaStream_t st) : cfg{} {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  PdlConfig(const PdlConfig&) = delete;
+};
 
 template <int NT, int NACC, int TAPS, int BST, bool BRES, bool DBG>
 int launch_tc_inst(const ConvArgs& a, size_t smem, cudaStream_t st) {
@@ -1203,10 +1205,10 @@ int launch_tc_inst(const ConvArgs& a, size_t smem, cudaStream_t st) {
   if (a.cout_pad != NT) return POPNET_ERR_UNSUPPORTED;     // one N tile per layer (true for every rtpose layer)
   const int tiles = (a.P + MT - 1) / MT;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;        // persistent: one CTA per SM walks the tiles
-  cudaLaunchConfig_t cfg = pdl_config(dim3(grid), dim3(kTcThreads), smem, st);
+  PdlConfig pc(dim3(grid), dim3(kTcThreads), smem, st);
   ConvArgs at = a;
   at.trace = next_trace_slot(NT * 1000 + NACC * 100 + TAPS * 10);
-  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, at));
+  POPNET_CUDA_TRY(cudaLaunchKernelEx(&pc.cfg, kern, at));
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }
@@ -1369,13 +1371,13 @@ int launch_stem(const StemArgs& a, cudaStream_t st) {
   const int P = (int)c8p_positions(a.N, a.H / 2, a.W / 2);
   const int tiles = (P + 127) / 128;
   const int cps = kStemCtasPerSm;       // CTAs per SM (TMEM: 8 x 64 columns; registers: 8 x 128 x 64)
-  static bool once = false;
-  if (!once) { cudaFuncSetAttribute(stem_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); once = true; }
+  // (a function attribute is per device context: set on every call, it is a host-side table write)
+  POPNET_CUDA_TRY(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int grid = tiles < 148 * cps ? tiles : 148 * cps;      // persistent: `cps` CTAs per SM walk the tiles
-  cudaLaunchConfig_t cfg = pdl_config(dim3(grid), dim3(kStemThreads), 0, st);
+  PdlConfig pc(dim3(grid), dim3(kStemThreads), 0, st);
   StemArgs at = a;
   at.trace = next_trace_slot(1);
-  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, stem_kernel, at));
+  POPNET_CUDA_TRY(cudaLaunchKernelEx(&pc.cfg, stem_kernel, at));
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }
@@ -1383,10 +1385,10 @@ int launch_stem(const StemArgs& a, cudaStream_t st) {
 int launch_pool(const PoolArgs& a, cudaStream_t st) {
   const int P = (int)c8p_positions(a.N, a.H / 2, a.W / 2);
   dim3 grid((P + 127) / 128, a.planes);
-  cudaLaunchConfig_t cfg = pdl_config(grid, dim3(128), 0, st);
+  PdlConfig pc(grid, dim3(128), 0, st);
   PoolArgs at = a;
   at.trace = next_trace_slot(2);
-  POPNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, pool_kernel, at));
+  POPNET_CUDA_TRY(cudaLaunchKernelEx(&pc.cfg, pool_kernel, at));
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }

@@ -30,9 +30,21 @@ constexpr int kThreads = 128;
 constexpr int kMaxCells = 64 * 64;      // largest supported grid_h * grid_w
 
 // OpenCV INTER_CUBIC at scale 8: phase r = dst % 8 -> first-tap offset and the four Keys(A=-0.75)
-// weights; all values are dyadic rationals, exact in fp32 (oracle/decode_np.py::phase_table).
-__constant__ int c_ofs[8];
-__constant__ float c_coef[8][4];
+// weights, cv::interpolateCubic evaluated in fp32 at x = frac((r + 0.5) / 8 - 0.5).  All sixteen distinct values are
+// integers / 2^14, exact in fp32 (oracle/decode_np.py::phase_table computes them; tests compare).  Statically
+// initialised __constant__ data: present on every device of the process from module load, no upload call, no state.
+#define POPNET_Q14(n) ((float)(n) / 16384.0f)
+__constant__ int c_ofs[8] = {-1, -1, -1, -1, 0, 0, 0, 0};
+__constant__ float c_coef[8][4] = {
+    {POPNET_Q14(-1323), POPNET_Q14(8365), POPNET_Q14(11043), POPNET_Q14(-1701)},
+    {POPNET_Q14(-825), POPNET_Q14(5615), POPNET_Q14(13409), POPNET_Q14(-1815)},
+    {POPNET_Q14(-351), POPNET_Q14(3033), POPNET_Q14(15223), POPNET_Q14(-1521)},
+    {POPNET_Q14(-45), POPNET_Q14(859), POPNET_Q14(16245), POPNET_Q14(-675)},
+    {POPNET_Q14(-675), POPNET_Q14(16245), POPNET_Q14(859), POPNET_Q14(-45)},
+    {POPNET_Q14(-1521), POPNET_Q14(15223), POPNET_Q14(3033), POPNET_Q14(-351)},
+    {POPNET_Q14(-1815), POPNET_Q14(13409), POPNET_Q14(5615), POPNET_Q14(-825)},
+    {POPNET_Q14(-1701), POPNET_Q14(11043), POPNET_Q14(8365), POPNET_Q14(-1323)}};
+#undef POPNET_Q14
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -453,7 +465,7 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const float* __re
         const int x0 = clampi(cx - 1, 0, W - 1), x1 = clampi(cx + 1, 0, W - 1);
         const int y0 = clampi(cy - 1, 0, H - 1), y1 = clampi(cy + 1, 0, H - 1);
         const float* hm = heat + ((size_t)b * (K + 1) + k) * cells;
-        const float* dm = depth + ((size_t)b * K + k) * cells;
+        const float* dm = depth + ((size_t)b * (p.depth_channels > 0 ? p.depth_channels : K) + k) * cells;
         float wv[9], dv[9];
         int n = 0;
         for (int yy = y0; yy <= y1; ++yy)
@@ -481,18 +493,44 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const float* __re
   }
 }
 
-// retrieve_depth_heat_weighted (lib/utils/common.py:272-293) for arbitrary query points: one thread per query
+// NumPy's pairwise summation of n <= 128 contiguous fp32 values (numpy/core/src/umath/loops_utils.h, pairwise_sum):
+// below 8 a plain loop from 0; else eight running sums over whole blocks of 8, combined as a tree, then the tail in order
+__device__ float sum_pairwise_f32_n(const float* a, int n) {
+  if (n < 8) {
+    float r = 0.f;
+    for (int i = 0; i < n; ++i) r += a[i];
+    return r;
+  }
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+  float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  for (; i < n; ++i) res += a[i];
+  return res;
+}
+
+constexpr int kMaxLiftRadius = 5;                                   // (2*5+1)^2 = 121 <= 128: one pairwise block
+constexpr int kMaxLiftWin = (2 * kMaxLiftRadius + 1) * (2 * kMaxLiftRadius + 1);
+
+// retrieve_depth_heat_weighted / retrieve_depth_weighted / retrieve_depth_heat_max (lib/utils/common.py:251-318) for
+// arbitrary query points and window radius: one thread per query
 __global__ void __launch_bounds__(128) lift_points_kernel(const float* __restrict__ heat, const float* __restrict__ depth,
                                                           const int32_t* __restrict__ queries, int n, int H, int W,
-                                                          float depth_mean, float depth_std, int mode, float* __restrict__ out) {
+                                                          float depth_mean, float depth_std, int mode, int radius,
+                                                          float* __restrict__ out) {
   const int i = blockIdx.x * 128 + threadIdx.x;
   if (i >= n) return;
   const int plane = queries[3 * i], cx = queries[3 * i + 1], cy = queries[3 * i + 2];
-  const int x0 = clampi(cx - 1, 0, W - 1), x1 = clampi(cx + 1, 0, W - 1);
-  const int y0 = clampi(cy - 1, 0, H - 1), y1 = clampi(cy + 1, 0, H - 1);
+  // min(max(c - r, 0), g - 1) .. max(min(c + r, g - 1), 0)   (common.py:279-282)
+  const int x0 = clampi(cx - radius, 0, W - 1), x1 = clampi(cx + radius, 0, W - 1);
+  const int y0 = clampi(cy - radius, 0, H - 1), y1 = clampi(cy + radius, 0, H - 1);
   const float* hm = heat ? heat + (size_t)plane * H * W : nullptr;
   const float* dm = depth + (size_t)plane * H * W;
-  float wv[9], dv[9];
+  float wv[kMaxLiftWin], dv[kMaxLiftWin];
   int m = 0;
   float best_w = 0.f, best_d = 0.f;
   for (int yy = y0; yy <= y1; ++yy)
@@ -510,30 +548,9 @@ __global__ void __launch_bounds__(128) lift_points_kernel(const float* __restric
       }
       ++m;
     }
-  if (mode == POPNET_LIFT_HEAT_WEIGHTED) out[i] = sum_pairwise_f32(dv, m) / sum_pairwise_f32(wv, m);
-  else if (mode == POPNET_LIFT_MEAN) out[i] = sum_pairwise_f32(dv, m) / (float)m;     // np.mean of an fp32 window
+  if (mode == POPNET_LIFT_HEAT_WEIGHTED) out[i] = sum_pairwise_f32_n(dv, m) / sum_pairwise_f32_n(wv, m);
+  else if (mode == POPNET_LIFT_MEAN) out[i] = sum_pairwise_f32_n(dv, m) / (float)m;     // np.mean of an fp32 window
   else out[i] = best_d;
-}
-
-bool g_tables_uploaded = false;
-
-int upload_tables() {
-  // OpenCV interpolateCubic in fp32 (exact: all operands are small dyadic rationals)
-  int ofs[8];
-  float coef[8][4];
-  for (int r = 0; r < 8; ++r) {
-    const float fx = (float)((r + 0.5) * 0.125 - 0.5);
-    const int s = (int)floorf(fx);
-    const float x = fx - (float)s, A = -0.75f;
-    ofs[r] = s;
-    coef[r][0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
-    coef[r][1] = ((A + 2) * x - (A + 3)) * x * x + 1;
-    coef[r][2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
-    coef[r][3] = 1.f - coef[r][0] - coef[r][1] - coef[r][2];
-  }
-  POPNET_CUDA_TRY(cudaMemcpyToSymbol(c_ofs, ofs, sizeof(ofs)));
-  POPNET_CUDA_TRY(cudaMemcpyToSymbol(c_coef, coef, sizeof(coef)));
-  return POPNET_OK;
 }
 
 }  // namespace
@@ -550,16 +567,12 @@ extern "C" int popnet_decode(const float* heat, const float* paf, const float* d
       p->max_persons > POPNET_MAX_PERSONS || p->grid_h < 1 || p->grid_w < 1 || p->grid_h * p->grid_w > kMaxCells ||
       p->num_intermed_pts < 1 || p->num_intermed_pts > 32 || p->num_joints > 32)
     return POPNET_ERR_UNSUPPORTED;
+  if (p->depth_channels != 0 && p->depth_channels < p->num_joints) return POPNET_ERR_INVALID_ARG;
   for (int l = 0; l < p->num_limbs; ++l)
     if (p->limbs[l][0] < 0 || p->limbs[l][0] >= p->num_joints || p->limbs[l][1] < 0 || p->limbs[l][1] >= p->num_joints)
       return POPNET_ERR_INVALID_ARG;
   if (batch == 0) return POPNET_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!g_tables_uploaded) {      // idempotent constant upload (same bytes every time)
-    int rc = upload_tables();
-    if (rc != POPNET_OK) return rc;
-    g_tables_uploaded = true;
-  }
   POPNET_CUDA_TRY(cudaMemsetAsync(o->flags, 0, sizeof(uint32_t) * batch, st));
   const int cells = p->grid_h * p->grid_w;
   const size_t smem_peaks = sizeof(float) * cells;
@@ -575,20 +588,27 @@ extern "C" int popnet_decode(const float* heat, const float* paf, const float* d
   return POPNET_OK;
 }
 
-extern "C" int popnet_lift_depth_mode(const float* heat, const float* depth, const int32_t* queries, int n, int grid_h,
-                                      int grid_w, float depth_mean, float depth_std, int mode, float* out_z, void* stream) {
+extern "C" int popnet_lift_depth_window(const float* heat, const float* depth, const int32_t* queries, int n, int grid_h,
+                                        int grid_w, float depth_mean, float depth_std, int mode, int radius, float* out_z,
+                                        void* stream) {
   if (mode < POPNET_LIFT_HEAT_WEIGHTED || mode > POPNET_LIFT_HEAT_MAX) return POPNET_ERR_INVALID_ARG;
-  if ((!heat && mode != POPNET_LIFT_MEAN) || !depth || !queries || !out_z || n < 0 || grid_h < 1 || grid_w < 1)
+  if ((!heat && mode != POPNET_LIFT_MEAN) || !depth || !queries || !out_z || n < 0 || grid_h < 1 || grid_w < 1 || radius < 0)
     return POPNET_ERR_INVALID_ARG;
+  if (radius > kMaxLiftRadius) return POPNET_ERR_UNSUPPORTED;
   if (n == 0) return POPNET_OK;
   lift_points_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(heat, depth, queries, n, grid_h, grid_w,
-                                                                                    depth_mean, depth_std, mode, out_z);
+                                                                                    depth_mean, depth_std, mode, radius, out_z);
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }
 
+extern "C" int popnet_lift_depth_mode(const float* heat, const float* depth, const int32_t* queries, int n, int grid_h,
+                                      int grid_w, float depth_mean, float depth_std, int mode, float* out_z, void* stream) {
+  return popnet_lift_depth_window(heat, depth, queries, n, grid_h, grid_w, depth_mean, depth_std, mode, 1, out_z, stream);
+}
+
 extern "C" int popnet_lift_depth(const float* heat, const float* depth, const int32_t* queries, int n, int grid_h, int grid_w,
                                  float depth_mean, float depth_std, float* out_z, void* stream) {
-  return popnet_lift_depth_mode(heat, depth, queries, n, grid_h, grid_w, depth_mean, depth_std, POPNET_LIFT_HEAT_WEIGHTED, out_z,
-                                stream);
+  return popnet_lift_depth_window(heat, depth, queries, n, grid_h, grid_w, depth_mean, depth_std, POPNET_LIFT_HEAT_WEIGHTED, 1,
+                                  out_z, stream);
 }

@@ -274,10 +274,11 @@ extern "C" int popnet_pack_weights(const PopnetNetConfig* cfg, const PopnetConvH
 }
 
 namespace {
-// Two auxiliary streams + fork/join events per CALLER stream, created on first use and kept for the life of the
+// Two auxiliary streams + fork/join events per (device, CALLER stream), created on first use and kept for the life of the
 // process (plumbing state; no results live here).  Keyed by the caller's stream so that forwards issued on different
 // streams (two batches in flight) do not serialise on each other's branch streams.
 struct AuxStreams {
+  int device;
   cudaStream_t owner;
   cudaStream_t s[2];
   cudaEvent_t fork, join[2], nfused;
@@ -285,11 +286,22 @@ struct AuxStreams {
 AuxStreams* aux_streams(cudaStream_t owner) {
   static std::mutex mu;
   static std::vector<AuxStreams*> sets;
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lock(mu);
-  for (AuxStreams* a : sets)
+  // streams and events belong to a device: the key is (device, caller's stream) -- the default stream handle is the
+  // same value on every device
+  int on_device = 0;
+  AuxStreams* any = nullptr;
+  for (AuxStreams* a : sets) {
+    if (a->device != device) continue;
     if (a->owner == owner) return a;
-  if (sets.size() >= 16) return sets[reinterpret_cast<uintptr_t>(owner) / 64 % 16];     // bounded: share beyond 16 streams
+    ++on_device;
+    any = a;
+  }
+  if (on_device >= 16) return any;                                 // bounded: share beyond 16 caller streams per device
   AuxStreams* aux = new AuxStreams();
+  aux->device = device;
   aux->owner = owner;
   bool ok = true;
   // default priority on purpose: giving the forward's streams the highest priority (so that the overlapped decode of the

@@ -57,7 +57,8 @@ def paf_to_pose(heatmaps, pafs, config):
     cfg = DecodeConfig.from_cfg(config)
     heat = np.ascontiguousarray(np.transpose(np.asarray(heatmaps, np.float32), (2, 0, 1)))[None]
     paf = np.ascontiguousarray(np.transpose(np.asarray(pafs, np.float32), (2, 0, 1)))[None]
-    params = _abi.make_decode_params(cfg, MP3DHP, input_size=heat.shape[2] * cfg.downsample)
+    # any H x W like the reference: the grid comes from the maps themselves (rows, columns)
+    params = _abi.make_decode_params(cfg, MP3DHP, input_size=heat.shape[2] * cfg.downsample, grid_hw=heat.shape[2:4])
     out = _get_backend().decode(heat, paf, None, params)
     _raise_on_overflow(out["flags"])
     return records_to_reference(out, 0, cfg.num_keypoints)
@@ -74,34 +75,39 @@ def paf_to_human_list(joint_list, person_to_joint_assoc):
     return humans, visibility, conf_vec
 
 
+def _radius(radius):
+    """The reference takes any number and truncates `center -/+ radius` (common.py:279-282); integral radii 0..5 run on
+    the device (windows of up to 121 cells), anything else is rejected loudly."""
+    r = int(radius)
+    if r != radius or not 0 <= r <= 5:
+        raise ValueError("radius must be an integer in 0..5 (got %r)" % (radius,))
+    return r
+
+
 def retrieve_depth_heat_weighted(center, depthmap, heatmap, radius=1):
-    """lib/utils/common.py:272-293: heat-weighted depth in the clipped 3x3 window around ``center`` = (x, y) grid cell.
+    """lib/utils/common.py:272-293: heat-weighted depth in the clipped (2*radius+1)^2 window around ``center`` = (x, y) grid cell.
     ``depthmap`` / ``heatmap`` are single [gh, gw] fp32 maps (already de-normalised depth, as at the reference's call
     site, ...mpreal_ablation.py:212-215).  Returns np.float32.  (The batched decode does this on the device for every
     assembled joint; this entry point exists for callers that use the helper on its own.)"""
-    if radius != 1:
-        raise NotImplementedError("only radius=1 (the value every reference call site uses) is implemented on the device")
     z = _get_backend().lift_depth(np.asarray(heatmap, np.float32)[None], np.asarray(depthmap, np.float32)[None],
-                                  np.array([[0, int(center[0]), int(center[1])]], np.int32))
+                                  np.array([[0, int(center[0]), int(center[1])]], np.int32), radius=_radius(radius))
     return np.float32(z[0])
 
 
 def retrieve_depth_weighted(center, depthmap, radius=1):
     """lib/utils/common.py:251-269: plain mean of the clipped 3x3 depth window (np.mean of an fp32 window)."""
-    if radius != 1:
-        raise NotImplementedError("only radius=1 is implemented on the device")
     z = _get_backend().lift_depth(None, np.asarray(depthmap, np.float32)[None],
-                                  np.array([[0, int(center[0]), int(center[1])]], np.int32), mode=_abi.LIFT_MEAN)
+                                  np.array([[0, int(center[0]), int(center[1])]], np.int32), mode=_abi.LIFT_MEAN,
+                                  radius=_radius(radius))
     return np.float32(z[0])
 
 
 def retrieve_depth_heat_max(center, depthmap, heatmap, radius=1):
     """lib/utils/common.py:296-318: depth at the (first, row-major) maximum of the heat-map inside the clipped 3x3
     window; like the reference, negative heat values count as 0."""
-    if radius != 1:
-        raise NotImplementedError("only radius=1 is implemented on the device")
     z = _get_backend().lift_depth(np.asarray(heatmap, np.float32)[None], np.asarray(depthmap, np.float32)[None],
-                                  np.array([[0, int(center[0]), int(center[1])]], np.int32), mode=_abi.LIFT_HEAT_MAX)
+                                  np.array([[0, int(center[0]), int(center[1])]], np.int32), mode=_abi.LIFT_HEAT_MAX,
+                                  radius=_radius(radius))
     return np.float32(z[0])
 
 
@@ -133,7 +139,8 @@ def decode_frames(heat, paf, depth, config=None, camera: Camera = MP3DHP, *, inp
     """Batched decode + lift of channel-major maps (NumPy or CUDA tensors):
     heat [B,K+1,g,g], paf [B,2L,g,g], depth [B,K,g,g] -> dict of flat records (NumPy)."""
     cfg = DecodeConfig.from_cfg(config) if config is not None else DecodeConfig()
-    params = _abi.make_decode_params(cfg, camera, input_size=input_size)
+    params = _abi.make_decode_params(cfg, camera, input_size=input_size, grid_hw=tuple(heat.shape[2:4]),
+                                     depth_channels=0 if depth is None else int(depth.shape[1]))
     out = _get_backend().decode(heat, paf, depth, params)
     if strict:
         _raise_on_overflow(out["flags"])

@@ -77,6 +77,13 @@ class rtpose_light3d(nn.Module):
         super().__init__()
         if num_stages != 2:
             raise ValueError("the reference hard-wires two stages (rtpose_light3d.py:314-322)")
+        # The reference's own defaults (18 parts, 19 limbs, 3 input channels: the COCO RGB configuration) are accepted by
+        # its constructor but are not on the depth path this package replaces; the compiled layer plan (csrc/forward.cu,
+        # make_plan) takes one depth channel and up to 15 parts / 15 limbs.  Fail here, not at the first forward.
+        if input_dim != 1 or not 1 <= num_parts <= 15 or not 1 <= num_limbs <= 15:
+            raise ValueError("popnet_b200 compiles the depth configuration only: input_dim=1, num_parts<=15, num_limbs<=15 "
+                             "(got input_dim=%d, num_parts=%d, num_limbs=%d); the depth path uses "
+                             "rtpose_light3d(15, 14, 2, input_dim=1)" % (input_dim, num_parts, num_limbs))
         self.num_parts = num_parts
         self.num_stages = num_stages
         self.num_limbs = num_limbs
@@ -169,7 +176,25 @@ class rtpose_light3d(nn.Module):
         _lib.check(rc, "popnet_pack_weights")
         self._packed = blob
         self._packed_dtype = int(self.operand_dtype)
+        self._packed_version = self._param_version()
         return blob
+
+    def _param_version(self):
+        """Changes whenever a parameter or BatchNorm statistic is modified in place (copy_, per-module loads, .to())
+        or replaced: sum of the tensors' autograd version counters plus their identities."""
+        ts = self.__dict__.get("_version_tensors")
+        if ts is None or len(ts) != 234:
+            ts = self.__dict__["_version_tensors"] = list(self.parameters()) + list(self.buffers())
+        live = self._parameters_and_buffers_ids()
+        if live != self.__dict__.get("_version_ids"):
+            ts = self.__dict__["_version_tensors"] = list(self.parameters()) + list(self.buffers())
+            self.__dict__["_version_ids"] = live
+        return sum(t._version for t in ts) + live
+
+    def _parameters_and_buffers_ids(self):
+        # replaced tensors (model.float(), .to(), per-module load with assign=True) change identity, not version; the
+        # first conv's weight and the last BatchNorm's statistics are representative and cheap to look at
+        return id(self.model0.conv1.weight) ^ id(self.model2_3[12].weight) ^ id(self.model0.bn1.running_var)
 
     def forward(self, x):
         """x [B, 1, H, W] fp32 CUDA tensor -> ((paf, heat, depth), [paf1, heat1, depth1, paf2, heat2, depth2])."""
@@ -180,7 +205,8 @@ class rtpose_light3d(nn.Module):
             raise ValueError("expected [B, %d, H, W], got %s" % (self.input_dim, tuple(x.shape)))
         x = x.contiguous().float()
         B, _, H, W = x.shape
-        if self._packed is None or self._packed_dtype != int(self.operand_dtype):
+        if (self._packed is None or self._packed_dtype != int(self.operand_dtype)
+                or self._packed_version != self._param_version()):
             self.pack(H, W)
         cfg = self._net_config(H, W)
         ws_bytes = lib.popnet_workspace_bytes(C.byref(cfg), B)

@@ -25,15 +25,20 @@ RECORD_KEYS = ("n_person", "flags", "person_peak", "person_score", "person_njoin
 
 class PoseEstimator:
     def __init__(self, model, camera: Camera = MP3DHP, config: DecodeConfig | None = None, *, input_size: int = 224,
-                 max_persons: int = 32, max_peaks: int = _abi.MAX_PEAKS):
+                 max_persons: int = 32, max_peaks: int = _abi.MAX_PEAKS, strict: bool = True):
         from ._cuda_backend import CudaBackend          # raises without CUDA / the library
         self.backend = CudaBackend()
         self.model = model
         self.camera = camera
         self.config = config or DecodeConfig()
         self.input_size = input_size
+        # the network's third head has num_limbs + 1 planes; joint j reads plane j (...mpreal_ablation.py:212-215)
         self.params = _abi.make_decode_params(self.config, camera, input_size=input_size, max_peaks=max_peaks,
-                                              max_persons=max_persons)
+                                              max_persons=max_persons, depth_channels=model.num_limbs + 1)
+        #: the reference's lists are unbounded; max_peaks / max_persons are device capacities.  strict: collect() raises
+        #: OverflowError when a frame hit one of them (its poses would differ from the reference's); strict=False
+        #: leaves the check of out["flags"] to the caller.
+        self.strict = strict
         self._out = None
         self._x_dev = None
         self._slots = None
@@ -127,7 +132,11 @@ class PoseEstimator:
         slot, B = ticket
         slot["done"].synchronize()
         slot["busy"] = False
-        return unpack_records(slot["host"], slot["out"]["_layout"], B)
+        rec = unpack_records(slot["host"], slot["out"]["_layout"], B)
+        if self.strict and rec["flags"].any():
+            from .decode import _raise_on_overflow
+            _raise_on_overflow(rec["flags"])
+        return rec
 
     def infer(self, frames):
         """The user-facing call: ``frames`` [B,1,H,W] fp32 on the HOST (NumPy array or, to avoid a staging copy,
@@ -179,7 +188,10 @@ def gather_records(out, group=None, unpack=True):
     world = dist.get_world_size(group)
     rec = out["_records"]
     rec = rec if isinstance(rec, torch.Tensor) else torch.from_numpy(rec)
-    full = torch.empty((world * rec.shape[0],), dtype=torch.uint8, device=rec.device)
+    full = out.get("_gathered")
+    if full is None or full.shape[0] != world * rec.shape[0] or full.device != rec.device:
+        # one buffer per output slot, reused every step (all ranks must hold equal-sized shards: see shard())
+        full = out["_gathered"] = torch.empty((world * rec.shape[0],), dtype=torch.uint8, device=rec.device)
     dist.all_gather_into_tensor(full, rec, group=group)
     if not unpack:
         return full
@@ -200,6 +212,26 @@ def reduce_counts(counts, group=None):
 
 
 def shard(n_items: int, rank: int, world: int):
-    """Contiguous batch slice of rank `rank`."""
+    """Contiguous batch slice of rank `rank`.  Every rank gets ceil(n / world) slots; ranks past the
+    end get a shorter (possibly empty) slice -- pad it with ``pad_shard`` before a gather, which needs equal sizes."""
     per = (n_items + world - 1) // world
     return slice(min(rank * per, n_items), min((rank + 1) * per, n_items))
+
+
+def pad_shard(x, n_items: int, world: int):
+    """Pad a rank's shard (NumPy array or tensor, frames on axis 0) with zero frames up to ceil(n / world) so that all
+    ranks run the same batch size and ``gather_records`` sees equal-sized buffers.  Returns (padded, n_valid).  A zero
+    depth frame decodes to no persons; callers drop the padding with ``unpad_gathered``."""
+    per = (n_items + world - 1) // world
+    n = x.shape[0]
+    if n == per:
+        return x, n
+    if isinstance(x, torch.Tensor):
+        pad = torch.zeros((per - n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        return torch.cat([x, pad], 0), n
+    return np.concatenate([x, np.zeros((per - n,) + x.shape[1:], x.dtype)], 0), n
+
+
+def unpad_gathered(rec: dict, n_items: int):
+    """Drop the padding frames of a gathered record dict (rank r's frames sit at [r * per, r * per + n_r))."""
+    return {k: v[:n_items] for k, v in rec.items()}

@@ -89,3 +89,45 @@ def test_decode_other_grid_sizes_vs_oracle(size, cuda_backend, oracle_lib):
     ora = oracle_lib.decode(heat, paf, depth, params)
     assert helpers.records_equal(dev, ora) == []
     assert int(dev["n_person"].sum()) >= 24 * 0.5
+
+
+@pytest.mark.parametrize("rows,cols", [(20, 28), (28, 17), (9, 40)], ids=lambda v: str(v))
+def test_decode_non_square_grid_vs_oracle(rows, cols, cuda_backend, oracle_lib):
+    """Rows != columns (the reference's paf_to_pose takes any H x W, paf_to_pose.py:354-377): crops of rendered maps,
+    byte-for-byte vs the C oracle (pinned to the reference on the same crops by tests/test_refcheck.py), through both the
+    batched entry and the reference-signature paf_to_pose (whose grid comes from the maps, not from a square size)."""
+    from types import SimpleNamespace as NS
+    from popnet_b200 import _abi
+    from popnet_b200.decode import paf_to_pose, records_to_reference
+    from popnet_b200.topology import DecodeConfig, MP3DHP
+    heat, paf, depth, _ = synth.map_batch(12, seed=600 + rows, persons=(2, 6), noise=0.01, size=384)
+    heat, paf, depth = (np.ascontiguousarray(t[:, :, 3:3 + rows, 5:5 + cols]) for t in (heat, paf, depth))
+    params = _abi.make_decode_params(DecodeConfig(), MP3DHP, input_size=224, grid_hw=(rows, cols))
+    dev = cuda_backend.decode(heat, paf, depth, params)
+    ora = oracle_lib.decode(heat, paf, depth, params)
+    assert helpers.records_equal(dev, ora) == []
+    assert int(dev["peak_count"].sum()) > 12 * 10
+    cfg = NS(MODEL=NS(NUM_KEYPOINTS=15, NUM_LIMBS=14, DOWNSAMPLE=8),
+             TEST=NS(THRESH_HEATMAP=0.1, THRESH_PAF=0.05, NUM_INTERMED_PTS_BETWEEN_KEYPOINTS=10))
+    for f in (0, 7):
+        jl, assoc = paf_to_pose(heat[f].transpose(1, 2, 0), paf[f].transpose(1, 2, 0), cfg)
+        ojl, oassoc = records_to_reference(ora, f, 15)
+        assert np.array_equal(jl, ojl) and np.array_equal(np.asarray(assoc), np.asarray(oassoc))
+
+
+def test_decode_rejects_mismatched_shapes(cuda_backend):
+    """The C ABI takes raw pointers; the Python boundary refuses maps whose shape disagrees with the parameter block
+    instead of indexing them with the wrong pitch."""
+    from popnet_b200 import _abi
+    from popnet_b200._lib import PopnetError
+    from popnet_b200.topology import DecodeConfig, MP3DHP
+    heat, paf, depth, _ = synth.map_batch(2, seed=1, persons=(1, 2))
+    params = _abi.make_decode_params(DecodeConfig(), MP3DHP)
+    with pytest.raises(PopnetError):
+        cuda_backend.decode(heat[:, :, :20], paf[:, :, :20], depth[:, :, :20], params)          # 20 x 28 maps, 28 x 28 params
+    with pytest.raises(PopnetError):
+        cuda_backend.decode(heat, paf, np.concatenate([depth, depth[:, :5]], 1), params)          # 20 depth planes, K = 15
+    p20 = _abi.make_decode_params(DecodeConfig(), MP3DHP, depth_channels=20)
+    d20 = np.ascontiguousarray(np.concatenate([depth, depth[:, :5]], 1))
+    a, b = cuda_backend.decode(heat, paf, d20, p20), cuda_backend.decode(heat, paf, depth, params)
+    assert helpers.records_equal(a, b) == []                                                     # joint j reads plane j

@@ -82,6 +82,29 @@ def test_depth_read_variants_match_oracle(cuda_backend):
         assert np.array_equal(got, want), mode
 
 
+@pytest.mark.parametrize("radius", [0, 2, 3, 5])
+def test_depth_reads_other_radii_match_oracle(radius, cuda_backend):
+    """The helpers' `radius` argument (common.py:251,272,296): windows of 1 .. 121 cells, every cell of the grid (clipped
+    windows at the borders), all three reads, bit-exact against the restatement (which test_refcheck pins to the reference)."""
+    from oracle import decode_np
+    from popnet_b200.decode import retrieve_depth_heat_weighted
+    rng = np.random.default_rng(40 + radius)
+    heat = (rng.random((28, 28), dtype=np.float32) - 0.2).astype(np.float32)
+    heat[10:13, 4:7] = 0.5
+    depth = (rng.random((28, 28), dtype=np.float32) * 4 + 1).astype(np.float32)
+    q = np.array([[0, x, y] for y in range(28) for x in range(28)], np.int32)
+    for mode, fn in ((0, lambda c: decode_np.retrieve_depth_heat_weighted(c, depth, heat, radius)),
+                     (1, lambda c: decode_np.retrieve_depth_weighted(c, depth, radius)),
+                     (2, lambda c: decode_np.retrieve_depth_heat_max(c, depth, heat, radius))):
+        got = cuda_backend.lift_depth(heat[None], depth[None], q, mode=mode, radius=radius)
+        want = np.array([fn((int(x), int(y))) for _, x, y in q], np.float32)
+        assert np.array_equal(got, want), (mode, radius)
+    assert retrieve_depth_heat_weighted((3, 4), depth, heat.copy(), radius=radius) == \
+        decode_np.retrieve_depth_heat_weighted((3, 4), depth, heat, radius)
+    with pytest.raises(ValueError):
+        retrieve_depth_heat_weighted((3, 4), depth, heat, radius=6)
+
+
 def test_decode_coco_topology_vs_oracle(cuda_backend, oracle_lib):
     """The decode kernels take the skeleton as data: COCO's 18 keypoints / 19 limbs (pafprocess.h:21-24), byte-for-byte
     against the C oracle (which tests/test_refcheck.py pins to the reference with the same topology)."""

@@ -159,10 +159,41 @@ def test_depth_read_variants_match_reference():
     heat = (rng.random((28, 28), dtype=np.float32) - 0.2).astype(np.float32)
     heat[10:13, 4:7] = 0.5
     depth = (rng.random((28, 28), dtype=np.float32) * 4 + 1).astype(np.float32)
-    for y in range(28):
-        for x in range(28):
-            a = common.retrieve_depth_weighted((x, y), depth, radius=1)
-            b = decode_np.retrieve_depth_weighted((x, y), depth, 1)
-            assert np.float32(a) == b and np.asarray(a).dtype == np.float32, (x, y, a, b)
-            a = common.retrieve_depth_heat_max((x, y), depth, heat.copy(), radius=1)
-            assert np.float32(a) == decode_np.retrieve_depth_heat_max((x, y), depth, heat, 1), (x, y)
+    for radius in (0, 1, 2, 3, 5):                     # windows of 1 .. 121 cells: every branch of NumPy's pairwise sum
+        for y in range(28):
+            for x in range(28):
+                a = common.retrieve_depth_weighted((x, y), depth, radius=radius)
+                b = decode_np.retrieve_depth_weighted((x, y), depth, radius)
+                assert np.float32(a) == b and np.asarray(a).dtype == np.float32, (radius, x, y, a, b)
+                a = common.retrieve_depth_heat_max((x, y), depth, heat.copy(), radius=radius)
+                assert np.float32(a) == decode_np.retrieve_depth_heat_max((x, y), depth, heat, radius), (radius, x, y)
+                a = common.retrieve_depth_heat_weighted((x, y), depth, heat.copy(), radius=radius)
+                b = decode_np.retrieve_depth_heat_weighted((x, y), depth, heat, radius)
+                assert np.float32(a) == b and np.asarray(a).dtype == np.float32, (radius, x, y, a, b)
+
+
+@pytest.mark.parametrize("rows,cols", [(20, 28), (28, 17), (9, 40)], ids=lambda v: str(v))
+def test_decode_non_square_maps_oracle_vs_reference(rows, cols, oracle_lib):
+    """paf_to_pose (paf_to_pose.py:354-377) accepts any H x W: the C oracle on non-square crops of rendered maps is
+    bit-identical to the reference (OpenCV C++ path) -- ids, coordinates, scores, associations."""
+    import cv2
+    import helpers
+    from popnet_b200 import _abi, synth
+    from popnet_b200.decode import records_to_reference
+    from popnet_b200.topology import DecodeConfig, MP3DHP
+    ref = refshim.load()
+    heat, paf, depth, _ = synth.map_batch(6, seed=600 + rows, persons=(2, 6), noise=0.01, size=384)
+    heat, paf, depth = (np.ascontiguousarray(t[:, :, 3:3 + rows, 5:5 + cols]) for t in (heat, paf, depth))
+    params = _abi.make_decode_params(DecodeConfig(), MP3DHP, input_size=224, grid_hw=(rows, cols))
+    out = oracle_lib.decode(heat, paf, depth, params)
+    prev = cv2.ipp.useIPP()
+    try:
+        cv2.ipp.setUseIPP(False)
+        for f in range(6):
+            jl, assoc = ref.paf_to_pose(np.ascontiguousarray(heat[f].transpose(1, 2, 0)),
+                                        np.ascontiguousarray(paf[f].transpose(1, 2, 0)), ref.cfg)
+            ojl, oassoc = records_to_reference(out, f, 15)
+            assert np.array_equal(np.asarray(jl, np.float64).reshape(-1, 5), ojl), f
+            assert np.array_equal(np.asarray(assoc, np.float64).reshape(-1, 17), np.asarray(oassoc, np.float64).reshape(-1, 17)), f
+    finally:
+        cv2.ipp.setUseIPP(prev)

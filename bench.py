@@ -1,22 +1,30 @@
 #!/usr/bin/env python
 """Headline benchmark: depth frames/sec for rtpose_light3d forward + PAF decode + 3D lift (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--dtype bf16|fp16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|c5] [--batch B | --global-batch G] [--dtype bf16|fp16]
 
-N > 1 is launched by the driver through torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
+N > 1 is launched by the driver through torchrun (one rank per GPU); rank 0 prints ONE JSON line.
 A "step" is one pass of the hot path over one batch of synthetic depth frames per GPU:
-    forward (39 convolutions on the tensor cores) -> decode (peaks, limbs, assembly) -> 3D lift
-    [-> all-gather of the pose records when N > 1].
+    forward (39 convolutions on the tensor cores) -> decode of the network's OWN maps (peaks, limbs, assembly) -> 3D lift
+    [-> pose records pushed into every rank's gather buffer over NVLink when N > 1].
+Weights: the fixture checkpoint (tests/golden/fixture_ckpt.npz: the reference module trained with the reference's loss
+on synthetic frames, tools/make_fixture_ckpt.py) -- no trained weights ship with the reference.
 `value`   : inputs already resident in HBM, timed with CUDA events, max over ranks.
-`e2e`     : the same step through the public API (popnet_b200.pipeline.PoseEstimator.infer) with pinned HOST
+`e2e`     : the same step through the public API (popnet_b200.pipeline.PoseEstimator.submit / collect) with pinned HOST
             frames in and pose records copied back to the host every step.
-`--impl reference` times the CPU restatement of the reference's path (oracle/: fp32 torch forward + C decode)
-on all host cores on a bounded sample of the same workload -- the reference itself is Python and cannot
-travel to the GPU box (/root/reference is not there).
+The timed region is at least MIN_TIMED_S seconds whatever --steps is: the K steps are repeated `repeats` times inside it
+(reported; ms_per_step is per step).
+`--impl reference` times the CPU restatement of the reference's path (oracle/: fp32 torch forward + C decode of its maps)
+on all host cores on the same workload -- the reference itself is Python and cannot travel to the GPU box.
+Workloads: c2 = BASELINE.json configs[1] (batch 64 per GPU, 1-6 persons); c5 = configs[4] (crowded, 12-16 persons,
+global batch 256); --global-batch 512 = configs[3] (C4: strong scaling, 512 frames sharded over the ranks).
 """
 import argparse
 import collections
+import hashlib
 import json
+import math
 import os
 import subprocess
 import sys
@@ -31,8 +39,16 @@ sys.path.insert(0, ROOT)
 FLOP_PER_FRAME = 13_343_404_032          # 2 x 6,671,702,016 conv MACs at 224x224, K=15, L=14
 DECODE_BYTES_PER_FRAME = 4 * 784 * (15 + 28 + 15)
 METRIC = "depth frames/sec (fwd+PAF decode+3D lift)"
-WORKLOAD = ("C2: rtpose_light3d inference, batch 64 synthetic 224x224 depth frames per GPU, heatmaps+PAF+depth maps "
-            "and greedy assembly + 3D lift")
+MIN_TIMED_S = 2.0
+WORKLOADS = {
+    "c2": {"persons": (1, 6), "batch": 64, "max_persons": 32,
+           "text": "C2: rtpose_light3d inference, batch 64 synthetic 224x224 depth frames per GPU (1-6 persons), "
+                   "heatmaps+PAF+depth maps, greedy assembly + 3D lift of the network's own maps"},
+    "c5": {"persons": (12, 16), "batch": 256, "max_persons": 64,
+           "text": "C5: crowded scenes, 12-16 synthetic persons per frame with occlusion, global batch 256, "
+                   "rtpose_light3d inference + decode + 3D lift of the network's own maps"},
+}
+FIXTURE = os.path.join(ROOT, "tests", "golden", "fixture_ckpt.npz")
 
 
 def peaks():
@@ -40,14 +56,29 @@ def peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return {"tflops": d.get("bf16_tflops_sustained", 1400.0), "tflops_burst": d.get("bf16_tflops", 1590.0),
-                "hbm": d.get("hbm_gbs", 6650.0), "src": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+                "hbm": d.get("hbm_gbs", 6650.0), "src": "measured (MEASURED_PEAKS.json)"}
     return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
 
 
+def fixture_state_dict():
+    z = np.load(FIXTURE)
+    return {k: (z[k].astype(np.float32) if z[k].dtype != np.int64 else z[k]) for k in z.files}
+
+
+def make_frames(rank, B, persons, rot=0):
+    """Rank `rank`'s batch of input set `rot`: up to 16 distinct seeded synthetic frames tiled to B (tile j offset by
+    1e-3*j so no two frames are equal), rolled and offset per input set."""
+    from popnet_b200 import synth
+    base = synth.depth_frames(min(B, 16), seed=1234 + 1000 * rank, persons=persons)
+    reps = (B + len(base) - 1) // len(base)
+    fr = np.concatenate([base + np.float32(1e-3 * j) for j in range(reps)], 0)[:B]
+    return (np.roll(fr, rot, axis=0) + np.float32(1e-3 * rot)).astype(np.float32)
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
@@ -68,42 +99,45 @@ class ClockSampler:
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        mhz = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        ok = [r for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mhz = [float(r[0]) for r in ok]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = sorted({n for r in ok for n, v in zip(names, r[2:6]) if v == "Active"})
+        mx = [float(r[1]) for r in ok if r[1].replace(".", "").isdigit()]
+        pw = [float(r[6]) for r in ok if len(r) >= 7 and r[6].replace(".", "").isdigit()]
         return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(mhz)}
+                "reasons": reasons, "samples": len(mhz), "power_w_max": max(pw) if pw else None}
 
 
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on the host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_path(sample_frames, repeats, warmup, cores):
-    """Returns (frames/s, seconds per repeat list).  forward: fp32 torch oracle with `cores` threads;
-    decode + lift: C oracle, frames spread over `cores` threads (ctypes releases the GIL)."""
+def cpu_path(frames, repeats, warmup, cores, max_persons):
+    """Returns (frames/s, seconds per repeat list).  forward: fp32 torch oracle with `cores` threads on the fixture
+    checkpoint; decode + lift of ITS maps: C oracle, frames spread over `cores` threads (ctypes releases the GIL)."""
     import torch
     from concurrent.futures import ThreadPoolExecutor
     from oracle import c_oracle, forward_torch
-    from popnet_b200 import _abi, network, synth
+    from popnet_b200 import _abi
     from popnet_b200.topology import MP3DHP, DecodeConfig
     torch.set_num_threads(cores)
-    sd = network.synth_state_dict(seed=0, style="reference")
-    x = torch.from_numpy(synth.depth_frames(sample_frames, seed=1234))
-    heat, paf, depth, _ = synth.map_batch(sample_frames, seed=1234, persons=(1, 6), noise=0.01)
-    params = _abi.make_decode_params(DecodeConfig(), MP3DHP, max_persons=32)
+    sd = {k: torch.from_numpy(v) for k, v in fixture_state_dict().items()}
+    x = torch.from_numpy(frames)
+    n = len(frames)
+    params = _abi.make_decode_params(DecodeConfig(), MP3DHP, max_persons=max_persons)
     c_oracle.lib()
     pool = ThreadPoolExecutor(cores)
 
     def one():
-        forward_torch.forward(sd, x)
-        list(pool.map(lambda f: c_oracle.decode(heat[f:f + 1], paf[f:f + 1], depth[f:f + 1], params), range(sample_frames)))
+        (paf, heat, depth), _ = forward_torch.forward(sd, x)
+        paf, heat, depth = paf.numpy(), heat.numpy(), depth.numpy()
+        return list(pool.map(lambda f: c_oracle.decode(heat[f:f + 1], paf[f:f + 1], depth[f:f + 1], params), range(n)))
 
     for _ in range(warmup):
         one()
@@ -112,26 +146,53 @@ def cpu_path(sample_frames, repeats, warmup, cores):
         t = time.perf_counter()
         one()
         ts.append(time.perf_counter() - t)
-    return sample_frames / float(np.mean(ts)), ts
+    return n / float(np.mean(ts)), ts
+
+
+def workload_config(args, world):
+    wl = WORKLOADS[args.workload]
+    if args.global_batch:
+        B = args.global_batch // world
+        scaling = "strong"
+    elif args.workload == "c5":
+        B = wl["batch"] // world
+        scaling = "strong"
+    else:
+        B = args.batch or wl["batch"]
+        scaling = "weak"
+    return wl, max(B, 1), scaling
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 16
-    steps = min(args.steps, 40)          # bounded: the whole run ends within a few minutes
-    fps, ts = cpu_path(sample, steps, min(args.warmup, 3), cores)
-    desc = "%d frames per step: fp32 torch forward (%d threads) + C-oracle decode/lift over %d threads" % (sample, cores, cores)
+    wl, B, scaling = workload_config(args, 1)
+    # the same frames per step as the GPU arm's rank 0 unless that would run for more than a few minutes
+    est_fps = 60.0
+    budget_s = 150.0
+    n = B
+    while n > 4 and (args.steps + args.warmup) * n / est_fps > budget_s:
+        n //= 2
+    frames = make_frames(0, B, wl["persons"])[:n]
+    fps, ts = cpu_path(frames, args.steps, args.warmup, cores, wl["max_persons"])
+    desc = ("%d of the %d frames of a step, %d steps: fp32 torch forward (%d threads) + C-oracle decode/lift of its maps over "
+            "%d threads; fixture checkpoint" % (n, B, args.steps, cores, cores))
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": float(np.mean(ts)) * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU port of the reference path (oracle/); the Python reference "
-                       "cannot travel to the GPU box"},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(ts)) * 1e3 * B / n,
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": bench_config(args, wl, B, 1, scaling),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def bench_config(args, wl, B, world, scaling):
+    return {"workload": wl["text"], "batch_per_gpu": B, "global_batch": B * world, "input": "224x224x1 fp32",
+            "weights": "fixture checkpoint (reference module + reference loss on synthetic frames, tests/golden/fixture_ckpt.npz)",
+            "decode_input": "the network's own output maps",
+            "parallelism": "dp%d (batch-sharded; pose records pushed to every rank's gather buffer over NVLink)" % world}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -153,6 +214,9 @@ def evaluator_leg(n_frames=4000, iters=20, with_cpu=True):
     be = CudaBackend()
 
     class Tap:                                     # records the packed CSR arrays the public API hands to the backend
+        def __getattr__(self, name):
+            return getattr(be, name)
+
         def pck(self, arrs, **kw):
             captured["pck"] = (arrs, kw)
             return be.pck(arrs, **kw)
@@ -161,12 +225,15 @@ def evaluator_leg(n_frames=4000, iters=20, with_cpu=True):
             captured["map"] = (arrs, kw)
             return be.map_assign(arrs, **kw)
 
+    def public_calls():
+        with contextlib.redirect_stdout(io.StringIO()):
+            evaluate.eval_human_dataset_3d(es["pred2d"], es["gt2d"], es["pred3d"], es["gt3d"], K, 0.1, 0.5)
+            evaluate.eval_ap_3D(es["pred3d"], es["conf"], es["gt3d"], [], names, 0.1)
+
     evaluate._backend = Tap()
-    sink = io.StringIO()
+    public_calls()                                 # warm-up (library load, first-touch allocations)
     t0 = time.perf_counter()
-    with contextlib.redirect_stdout(sink):
-        evaluate.eval_human_dataset_3d(es["pred2d"], es["gt2d"], es["pred3d"], es["gt3d"], K, 0.1, 0.5)
-        evaluate.eval_ap_3D(es["pred3d"], es["conf"], es["gt3d"], [], names, 0.1)
+    public_calls()
     e2e_s = time.perf_counter() - t0
     evaluate._backend = None
     (pa, pkw), (ma, mkw) = captured["pck"], captured["map"]
@@ -190,7 +257,7 @@ def evaluator_leg(n_frames=4000, iters=20, with_cpu=True):
                       "achieved_GBps": alg_bytes / (dev_ms * 1e-3) / 1e9, "algorithmic_bytes": alg_bytes,
                       "bound": "hbm (latency-bound: one warp per frame; the 19 MB of CSR arrays stay in the 126 MB L2 between iterations)"},
            "e2e": {"value": n_frames / e2e_s, "unit": "frames/s", "s": e2e_s,
-                   "note": "public API on ragged Python lists: list->CSR packing and the NumPy AP tail dominate"}}
+                   "note": "public reference-signature calls on ragged Python lists: list->CSR packing, H2D, kernels, AP tail, D2H"}}
     if with_cpu:
         from oracle.backend import OracleBackend          # checker / baseline only
         ob = OracleBackend()
@@ -203,33 +270,41 @@ def evaluator_leg(n_frames=4000, iters=20, with_cpu=True):
     return res
 
 
+def records_digest(rec, B_total):
+    """sha256 over the VALID part of pose records (per frame: count, flags, then the rows of its persons)."""
+    h = hashlib.sha256()
+    n = np.asarray(rec["n_person"]).astype(np.int32)
+    h.update(n.tobytes())
+    h.update(np.asarray(rec["flags"]).astype(np.int32).tobytes())
+    for f in range(B_total):
+        m = int(n[f])
+        for k in ("person_peak", "person_score", "person_njoint", "pose2d", "pose3d", "pose_conf"):
+            h.update(np.ascontiguousarray(np.asarray(rec[k][f, :m])).tobytes())
+    return h.hexdigest()
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
-    from popnet_b200 import _abi, _lib, network, pipeline, synth
+    from popnet_b200 import _abi, _lib, network, pipeline
+    from popnet_b200._cuda_backend import records_layout
+    from popnet_b200.topology import MP3DHP, DecodeConfig
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.get()
-    B = args.batch
-    R = args.rotate
+    wl, B, scaling = workload_config(args, world)
     model = network.rtpose_light3d(15, 14, 2, input_dim=1)
-    sd = network.synth_state_dict(seed=0, style="reference")        # random-init weights of the architecture
-    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in fixture_state_dict().items()})
     model.operand_dtype = _abi.OPERAND_BF16 if args.dtype == "bf16" else _abi.OPERAND_FP16
-    est = pipeline.PoseEstimator(model, max_persons=32)
-    # R rotating input sets so that consecutive steps never find their inputs in the 126 MB L2
-    base = synth.depth_frames(min(B, 16), seed=1234 + 1000 * rank)
-    heat, paf, depth, _ = synth.map_batch(B, seed=1234 + 1000 * rank, persons=(1, 6), noise=0.01)
-    host_frames, dev_frames, dev_maps = [], [], []
-    for r in range(R):
-        fr = np.roll(np.tile(base, ((B + len(base) - 1) // len(base), 1, 1, 1))[:B], r, axis=0).copy()
-        fr += np.float32(1e-3 * r)
-        hf = torch.from_numpy(fr).pin_memory()
-        host_frames.append(hf)
-        dev_frames.append(hf.cuda())
-        roll = lambda a: torch.from_numpy(np.roll(a, r, axis=0).copy()).cuda()
-        dev_maps.append((roll(heat), roll(paf), roll(depth)))
+    peers = None
+    if world > 1:
+        from popnet_b200 import p2p
+        params = _abi.make_decode_params(DecodeConfig(), MP3DHP, max_persons=wl["max_persons"], depth_channels=15)
+        peers = p2p.PeerGather(records_layout(B, params)[0], pipeline.PoseEstimator.NSLOT)
+    est = pipeline.PoseEstimator(model, max_persons=wl["max_persons"], peers=peers, use_graphs=not args.eager, strict=False)
+    NS = est.NSLOT
+    host_frames = [torch.from_numpy(make_frames(rank, B, wl["persons"], rot=r)).pin_memory() for r in range(args.rotate)]
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def barrier():
@@ -238,144 +313,181 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def agree(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=op)
+        return float(t[0])
+
+    # ---- value leg: the NSLOT slot input buffers hold NSLOT different input sets, resident in HBM
+    for i in range(NS):
+        est.slot_input(i, B).copy_(host_frames[i % len(host_frames)])
+    torch.cuda.synchronize()
+
     def step_device(i, evs=None):
-        """One step with inputs resident in HBM.  Forward on the main stream, decode + lift (+ all-gather) on the
-        estimator's decode stream: consecutive steps are software-pipelined (decode of step i under the forward of
-        step i+1), every step still runs the full forward and the full decode."""
-        est.inject = dev_maps[i % R]
-        x = dev_frames[i % R]
-        est._buffers(B)
-        slot = est._slots[i % est.NSLOT]
+        return est.infer_device(est.slot_input(i, B), evs)
 
-        def after(o):
-            if evs is not None:
-                evs[3].record(torch.cuda.current_stream())
-            if world > 1:
-                pipeline.gather_records(o, unpack=False)  # one NCCL all-gather of the packed record bytes
-        out = est.infer_device(x, slot["out"], after=after, _evs=evs)
-        return out
-
-    def submit_e2e(i):
-        est.inject = dev_maps[i % R]
-        # H2D (copy stream) -> forward -> decode -> D2H (-> all-gather of the record bytes), asynchronous
-        gather = (lambda o: pipeline.gather_records(o, unpack=False)) if world > 1 else None
-        return est.submit(host_frames[i % R], after=gather)
-
-    def run_e2e(n):
-        """n steps through the public API, software-pipelined NSLOT deep: the H2D copy of step i+2 and the forward of step
-        i+1 overlap the decode + D2H of step i; every step's records are read back on the host."""
-        rec, q = None, collections.deque()
-        for i in range(n):
-            if len(q) == est.NSLOT:
-                rec = est.collect(q.popleft())
-            q.append(submit_e2e(i))
-        while q:
-            rec = est.collect(q.popleft())
-        return rec
-
-    # ---- value leg
-    for i in range(args.warmup):
+    launches0 = lib.popnet_launch_count()
+    step_device(0)                                   # first use of slot 0: eager warm-up launches, then graph capture
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.popnet_launch_count() - launches0) // (2 if est.use_graphs else 1)
+    for i in range(1, max(args.warmup, NS)):
         step_device(i)
+    barrier()
+    # how long is a step?  (sets `repeats` so that the timed region is >= MIN_TIMED_S on every rank)
+    t0, t1 = ev(), ev()
+    t0.record()
+    for i in range(20):
+        step_device(i)
+    torch.cuda.current_stream().wait_stream(est.decode_stream)
+    t1.record()
+    torch.cuda.synchronize()
+    est_ms = agree(t0.elapsed_time(t1) / 20, dist.ReduceOp.MIN if world > 1 else None)
+    repeats = max(1, int(math.ceil(MIN_TIMED_S * 1e3 / (est_ms * args.steps))))
+    total = args.steps * repeats
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = lib.popnet_launch_count()
-    stage_evs = [[ev(), ev(), ev(), ev()] for _ in range(args.steps)]
+        time.sleep(0.1)
+    barrier()
     t0, t1 = ev(), ev()
     t0.record()
-    for i in range(args.steps):
-        step_device(i, stage_evs[i])
+    for i in range(total):
+        step_device(i)
     torch.cuda.current_stream().wait_stream(est.decode_stream)     # the timed region ends when the last decode has
     t1.record()
     barrier()
-    launches = lib.popnet_launch_count() - launches0
     elapsed_ms = t0.elapsed_time(t1)
-    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in stage_evs]))     # forward, on its (main) stream
-    dec_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in stage_evs]))     # decode + lift, on the decode stream
-    # ---- e2e leg
-    run_e2e(max(3, args.warmup // 2))
+    # forward / decode durations on their own streams (separate short loop: events per step cost host time)
+    stage_evs = [[ev(), ev(), ev(), ev()] for _ in range(30)]
+    for i in range(30):
+        step_device(i, stage_evs[i])
+    barrier()
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in stage_evs[5:]]))
+    dec_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in stage_evs[5:]]))
+
+    # ---- e2e leg: pinned host frames -> H2D -> forward -> decode -> D2H of the records, NSLOT batches in flight
+    def run_e2e(n):
+        rec, q = None, collections.deque()
+        for i in range(n):
+            if len(q) == NS:
+                rec = est.collect(q.popleft())
+            q.append(est.submit(host_frames[i % len(host_frames)]))
+        while q:
+            rec = est.collect(q.popleft())
+        return rec
+
+    run_e2e(max(NS, args.warmup))
     barrier()
     e0, e1 = ev(), ev()
     e0.record()
-    run_e2e(args.steps)
+    run_e2e(total)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = agree(elapsed_ms, dist.ReduceOp.MAX if world > 1 else None)
+    e2e_ms = agree(e2e_ms, dist.ReduceOp.MAX if world > 1 else None)
+
+    # ---- checks: the timed path produced poses; multi-GPU: rank 0's gathered records == its own 1-GPU decode
+    ticket = est.submit(host_frames[0])
+    rec = est.collect(ticket)
+    n_person = int(rec["n_person"].sum())
+    flags = int((rec["flags"] != 0).sum())
+    check = {"persons_decoded_per_step": n_person, "frames_with_overflow_flags": flags}
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms = float(t[0]), float(t[1])
-    # sanity: the timed path produced poses
-    rec = run_e2e(1)
-    n_person = int(np.asarray(rec["n_person"].cpu() if hasattr(rec["n_person"], "cpu") else rec["n_person"]).sum())
-    flags = int(np.asarray(rec["flags"].cpu() if hasattr(rec["flags"], "cpu") else rec["flags"]).astype(np.int64).sum())
+        torch.cuda.synchronize()
+        gathered = {k: v.cpu().numpy() for k, v in est.gathered(ticket).items()}
+        timed_out = peers.timed_out()
+        barrier()
+        if rank == 0:
+            check["gather_sha"] = records_digest(gathered, B * world)
+            solo = pipeline.PoseEstimator(model, max_persons=wl["max_persons"], use_graphs=False, strict=False)
+            parts = [solo.infer(make_frames(r, B, wl["persons"], rot=0)) for r in range(world)]
+            parts = [{k: np.array(v) for k, v in p.items()} for p in parts]
+            cat = {k: np.concatenate([p[k] for p in parts], 0) for k in parts[0]}
+            check["one_gpu_sha"] = records_digest(cat, B * world)
+            check["gather_equals_one_gpu"] = check["gather_sha"] == check["one_gpu_sha"]
+        check["p2p_timed_out"] = bool(timed_out)
+        barrier()
     if rank != 0:
         if world > 1:
+            peers.close()
             dist.destroy_process_group()
         return
     pk = peaks()
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_forward_dram_traffic.json")
-    if os.path.exists(tp) and B == 64:
-        tj = json.load(open(tp))
-        traffic, traffic_src = tj["dram_bytes_total"], "profiles/r1_forward_dram_traffic.json (ncu, one forward at batch 64)"
+    for name in ("r2_forward_dram_traffic.json", "r1_forward_dram_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp) and B == 64:
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj["dram_bytes_total"], "profiles/%s (ncu, one forward at batch 64)" % name
+            break
     frames_per_step = B * world
-    value = frames_per_step * args.steps / (elapsed_ms * 1e-3)
-    e2e = frames_per_step * args.steps / (e2e_ms * 1e-3)
+    value = frames_per_step * total / (elapsed_ms * 1e-3)
+    e2e = frames_per_step * total / (e2e_ms * 1e-3)
     tflops = B * FLOP_PER_FRAME / (fwd_ms * 1e-3) / 1e12
+    sustained = elapsed_ms >= 1000.0
+    peak = pk["tflops"] if sustained else pk["tflops_burst"]
+    cfg = bench_config(args, wl, B, world, scaling)
+    cfg["l2"] = ("%d rotating input sets; one step moves > 1.5 GB through the 126 MB L2 (activation workspace %.0f MB), "
+                 "nothing survives from one step to the next" % (NS, lib.popnet_workspace_bytes(model._net_config(224, 224), B) / 1e6))
+    cfg["cuda_graphs"] = bool(est.use_graphs)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": frames_per_step, "input": "224x224x1 fp32",
-                   "weights": "random init of the architecture (reference init, seed 0)",
-                   "decode_input": "GT-style maps (1-6 persons/frame, reference renderers' formulas) resident in HBM are "
-                                   "decoded in place of the forward's own maps: untrained weights give sigma~0.5 heat-maps "
-                                   "(thousands of plateau peaks), a degenerate decode workload (SURVEY.md 6.2); the forward "
-                                   "still computes and writes all six maps",
-                   "l2": "rotation of %d input sets (%.0f MB frames + %.0f MB maps) > 126 MB L2; activations (%.0f MB) "
-                         "exceed L2 by themselves" % (R, R * B * 224 * 224 * 4 / 1e6, R * B * 46256 * 4 / 1e6,
-                                                      lib.popnet_workspace_bytes(est.model._net_config(224, 224), B) / 1e6),
-                   "parallelism": "dp%d (batch-sharded, all-gather of pose records)" % world},
+        "repeats": repeats, "timed_region_s": elapsed_ms * 1e-3,
+        "ms_per_step": elapsed_ms / total, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic", "config": cfg,
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": est.h2d_bytes(B), "d2h_bytes_per_step": est.d2h_bytes(B),
-                "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches),
+                "ms_per_step": e2e_ms / total, "timed_region_s": e2e_ms * 1e-3},
+        "gpu_launches": int(launches_per_step * total),
+        "gpu_launches_per_step": launches_per_step,
+        "host_launches_per_step": 2 if est.use_graphs else launches_per_step,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (35 launches) + stem_kernel = the forward",
-                     "achieved": tflops, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tflops / pk["tflops"],
-                     "frac_of_burst_peak": tflops / pk["tflops_burst"], "peak_source": pk["src"], "traffic": traffic, "traffic_source": traffic_src,
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + stem_kernel = the forward",
+                     "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
+                     "peak_regime": "sustained (timed region %.1f s)" % (elapsed_ms * 1e-3) if sustained else "burst",
+                     "frac_of_sustained_peak": tflops / pk["tflops"], "frac_of_burst_peak": tflops / pk["tflops_burst"],
+                     "peak_source": pk["src"], "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_flop_per_step": B * FLOP_PER_FRAME,
                      "min_hbm_bytes_per_step": B * (224 * 224 * 4 + 2 * 46256 * 4) + 11_051_628,
                      "forward_ms": fwd_ms, "decode_ms": dec_ms,
                      "decode_hbm": {"bound": "hbm", "achieved": B * DECODE_BYTES_PER_FRAME / (dec_ms * 1e-3) / 1e9,
                                     "peak": pk["hbm"], "unit": "GB/s",
                                     "frac": B * DECODE_BYTES_PER_FRAME / (dec_ms * 1e-3) / 1e9 / pk["hbm"]}},
-        "check": {"persons_decoded_per_step": n_person, "overflow_flags": flags},
+        "check": check,
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        fps, ts = cpu_path(64, 12, 1, cores)
+        n = min(B, 64)
+        reps = 12 if args.workload == "c2" else 4
+        fps, ts = cpu_path(make_frames(0, B, wl["persons"])[:n], reps, 1, cores, wl["max_persons"])
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": "64 frames x 12 repeats: fp32 torch forward (%d threads) + C-oracle decode/lift "
-                                          "over %d threads (%.1f s)" % (cores, cores, sum(ts))}
+                                "sample": "%d frames x %d repeats: fp32 torch forward (%d threads) + C-oracle decode/lift of its maps "
+                                          "over %d threads (%.1f s); fixture checkpoint" % (n, reps, cores, cores, sum(ts))}
     if world == 1 and not args.no_evaluator:
         line["evaluator"] = evaluator_leg(with_cpu=not args.no_cpu_baseline)
     print(json.dumps(line), flush=True)
     if world > 1:
+        peers.close()
         dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
-    ap.add_argument("--rotate", type=int, default=12)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (weak scaling; default: the workload's)")
+    ap.add_argument("--global-batch", type=int, default=0, help="total frames per step, sharded over the ranks (strong scaling; C4: 512)")
+    ap.add_argument("--dtype", default="fp16", choices=["bf16", "fp16"],
+                    help="16-bit operand format (fp32 accumulate); fp16 is the product default, see DESIGN.md section 2")
+    ap.add_argument("--rotate", type=int, default=3)
+    ap.add_argument("--eager", action="store_true", help="issue every launch from the host instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-evaluator", action="store_true", help="skip the secondary evaluator metric")
     args = ap.parse_args()

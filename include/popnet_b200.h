@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define POPNET_ABI_VERSION 1
+#define POPNET_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define POPNET_API __attribute__((visibility("default")))
@@ -117,6 +117,49 @@ typedef struct PopnetDecodeOut {
  * mandatory, as are n_person and flags; person_* and pose* may be NULL. */
 POPNET_API int popnet_decode(const float* heat, const float* paf, const float* depth, int batch,
                   const PopnetDecodeParams* params_host, const PopnetDecodeOut* out_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU record exchange, fused into the decode ("write straight into the registered all-gather
+ * send buffer").  Frames are sharded by batch over the GPUs of one NVSwitch box, one process per GPU; the only data
+ * that crosses GPUs is the pose records of every step.  Instead of an all-gather kernel behind the decode (which holds
+ * SMs while it waits for the slowest rank), the assembly kernel stores every record value it produces into the gather
+ * buffer of EVERY rank (plain stores to peer-mapped memory over NVLink), then publishes a step tag; a one-warp kernel
+ * waits until all ranks' tags of the step have arrived.  The reference has no equivalent (single-GPU DataParallel,
+ * evaluation_rtpose_light3d_kdh3d_mpreal_ablation.py:140-141).
+ *
+ * Memory: each rank owns ONE cudaMalloc block (popnet_p2p_alloc) that it exports with a CUDA IPC handle; peers map it
+ * (popnet_p2p_open).  The host side (popnet_b200/p2p.py) lays it out as, per pipeline slot,
+ *   gather[world][records_bytes]   rank r's records of the step, identical on every rank once the tags have arrived
+ *   arrive[world]                  uint64 step tags, arrive[r] written by rank r
+ * and points PopnetDecodeOut's record fields INTO gather[rank] of its own block, so the local record block and the
+ * rank's chunk of the gathered result are the same bytes.
+ * ---------------------------------------------------------------------------------------------- */
+#define POPNET_MAX_PEERS 8
+typedef struct PopnetPeerPush {
+  int32_t world, rank;
+  void* gather_base[POPNET_MAX_PEERS];            /* rank p's gather buffer of this slot, as mapped in THIS process   */
+  unsigned long long* arrive[POPNET_MAX_PEERS];   /* rank p's arrive[] array of this slot, as mapped in this process  */
+  size_t records_bytes;                           /* size of one rank's record block (chunk stride in gather)         */
+  unsigned long long* step;                       /* local: steps completed on this slot (tag = *step + 1)            */
+  unsigned int* done_counter;                     /* local, zero: CTAs of the assembly kernel that finished pushing   */
+  unsigned int* status;                           /* local: set to 1 by popnet_p2p_wait when a peer's tag timed out   */
+} PopnetPeerPush;
+
+/* popnet_decode whose assembly kernel also pushes the records to the peers.  The record fields of out_host
+ * (n_person, flags, person_*, pose*) must point into gather_base[rank] + rank * records_bytes. */
+POPNET_API int popnet_decode_push(const float* heat, const float* paf, const float* depth, int batch,
+                                  const PopnetDecodeParams* params_host, const PopnetDecodeOut* out_host,
+                                  const PopnetPeerPush* push_host, void* stream);
+/* one warp: returns (in stream order) when arrive[p] >= *step for every rank p of the local arrive array, or sets
+ * *status = 1 after timeout_ms without progress (a dead peer must not hang the GPU) */
+POPNET_API int popnet_p2p_wait(const unsigned long long* local_arrive, int world, const unsigned long long* step,
+                               unsigned int* status, int timeout_ms, void* stream);
+/* peer-visible device memory: cudaMalloc + cudaIpcGetMemHandle (handle_out: 64 bytes, host); popnet_p2p_open maps a
+ * peer's block into this process (cudaIpcOpenMemHandle, peer access enabled lazily) */
+POPNET_API int popnet_p2p_alloc(size_t bytes, void** dev_ptr_out, unsigned char* handle_out);
+POPNET_API int popnet_p2p_open(const unsigned char* handle, void** peer_ptr_out);
+POPNET_API int popnet_p2p_close(void* peer_ptr);
+POPNET_API int popnet_p2p_free(void* dev_ptr);
 
 /* retrieve_depth_heat_weighted(center, depthmap, heatmap, radius=1)   lib/utils/common.py:272-293, for n query points:
  * queries [n][3] = (map plane index, cx, cy) in grid cells; heat / depth are stacks of [grid_h][grid_w] fp32 planes;
@@ -235,9 +278,10 @@ typedef struct PopnetNetConfig {
   int32_t num_limbs;           /* 14                                                               */
   int32_t input_dim;           /* 1 (depth); the only compiled value                               */
   int32_t height, width;       /* 224 x 224; must be multiples of 8                                */
-  int32_t operand_dtype;       /* POPNET_OPERAND_BF16 (default) or POPNET_OPERAND_FP16: storage format of
-                                  weights and inter-layer activations; accumulation is always fp32 and
-                                  the six output maps are always fp32                                 */
+  int32_t operand_dtype;       /* POPNET_OPERAND_FP16 (what the Python mirror defaults to: holds the 1e-2 map tolerance
+                                  on trained weights) or POPNET_OPERAND_BF16: storage format of weights and
+                                  inter-layer activations; accumulation is always fp32 and the six output maps
+                                  are always fp32                                                          */
 } PopnetNetConfig;
 
 #define POPNET_OPERAND_BF16 0

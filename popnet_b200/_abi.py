@@ -9,7 +9,8 @@ MAX_LIMBS = 24
 LIFT_HEAT_WEIGHTED, LIFT_MEAN, LIFT_HEAT_MAX = 0, 1, 2
 MAX_PEAKS = 64
 MAX_PERSONS = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
+MAX_PEERS = 8
 
 OK = 0
 STATUS_NAMES = {0: "POPNET_OK", -1: "POPNET_ERR_INVALID_ARG", -2: "POPNET_ERR_UNSUPPORTED",
@@ -43,6 +44,12 @@ class DecodeOut(C.Structure):
     _fields_ = [(n, vp) for n in (
         "peak_count", "peak_xy", "peak_score", "conn_count", "conn_ij", "conn_score", "n_person",
         "person_peak", "person_score", "person_njoint", "pose2d", "pose3d", "pose_conf", "flags")]
+
+
+class PeerPush(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32),
+                ("gather_base", vp * MAX_PEERS), ("arrive", vp * MAX_PEERS),
+                ("records_bytes", C.c_size_t), ("step", vp), ("done_counter", vp), ("status", vp)]
 
 
 class PckArgs(C.Structure):
@@ -88,6 +95,13 @@ PROTOTYPES = {
     "popnet_last_cuda_error": (C.c_int, []),
     "popnet_launch_count": (C.c_longlong, []),
     "popnet_decode": (C.c_int, [vp, vp, vp, C.c_int, C.POINTER(DecodeParams), C.POINTER(DecodeOut), vp]),
+    "popnet_decode_push": (C.c_int, [vp, vp, vp, C.c_int, C.POINTER(DecodeParams), C.POINTER(DecodeOut),
+                                     C.POINTER(PeerPush), vp]),
+    "popnet_p2p_wait": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp]),
+    "popnet_p2p_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp), C.c_char_p]),
+    "popnet_p2p_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "popnet_p2p_close": (C.c_int, [vp]),
+    "popnet_p2p_free": (C.c_int, [vp]),
     "popnet_eval_ap_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "popnet_eval_ap": (C.c_int, [C.POINTER(ApArgs), vp]),
     "popnet_lift_depth": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp]),

@@ -57,10 +57,33 @@ _FIELDS = (  # name, dtype, shape suffix builder -- 8-byte fields first so every
 RECORD_FIELDS = ("person_score", "pose2d", "pose3d", "pose_conf", "n_person", "person_njoint", "flags", "person_peak")
 
 
-def alloc_decode_out(B, params, device="cuda"):
+def records_layout(B, params):
+    """(byte size, [(name, dtype, shape suffix, offset, nbytes)]) of the pose-record block of a batch."""
+    K, L, P, M = params.num_joints, params.num_limbs, params.max_peaks, params.max_persons
+    off, lay = 0, []
+    for name, dt, shp in _FIELDS:
+        if name in RECORD_FIELDS:
+            n = B * int(np.prod(shp(K, L, P, M), dtype=np.int64)) * torch.empty((), dtype=dt).element_size()
+            lay.append((name, dt, shp(K, L, P, M), off, n))
+            off = (off + n + 7) // 8 * 8
+    return off, lay
+
+
+def alloc_decode_out(B, params, device="cuda", records=None):
     """All decode outputs of a batch live in ONE device buffer (field-major: [field][B][...]); the pose-record fields
-    sit contiguously at its end so that the multi-GPU all-gather (and the D2H copy) is a single transfer of
-    ``out["_records"]`` without any packing kernel."""
+    sit contiguously at its end so that the multi-GPU exchange (and the D2H copy) is a single transfer of
+    ``out["_records"]`` without any packing kernel.  ``records``: optional preallocated uint8 tensor that holds the
+    record block instead (the peer-visible buffer of the multi-GPU path)."""
+    if records is not None:
+        nbytes, lay = records_layout(B, params)
+        assert records.numel() >= nbytes and records.dtype == torch.uint8
+        out = alloc_decode_out(B, params, device)
+        rec = records[:nbytes]
+        rec.zero_()
+        out["_records"], out["_layout"] = rec, lay
+        for name, dt, shp_, o, nb in lay:
+            out[name] = rec[o:o + nb].view(dt).reshape((B,) + tuple(shp_))
+        return out
     K, L, P, M = params.num_joints, params.num_limbs, params.max_peaks, params.max_persons
     order = [f for f in _FIELDS if f[0] not in RECORD_FIELDS] + [f for f in _FIELDS if f[0] in RECORD_FIELDS]
     sizes, off = [], 0
@@ -175,15 +198,20 @@ class CudaBackend:
         return self.ap_tail_device(c, l, g).cpu().numpy()
 
     # ------------------------------------------------------------------ decode
-    def decode_device(self, heat, paf, depth, params, out=None):
-        """Device tensors in, device tensors out (no synchronisation); `out` buffers may be reused."""
+    def decode_device(self, heat, paf, depth, params, out=None, push=None):
+        """Device tensors in, device tensors out (no synchronisation); `out` buffers may be reused.  push: optional
+        _abi.PeerPush block (multi-GPU: the assembly kernel also stores every record value into the peers' gather buffers)."""
         B = heat.shape[0]
         check_decode_shapes(heat, paf, depth, params)
         if out is None:
             out = alloc_decode_out(B, params)
         o = _abi.DecodeOut(**{k: _ptr(v) for k, v in out.items() if not k.startswith("_")})
-        _lib.check(self.lib.popnet_decode(_ptr(heat), _ptr(paf), _ptr(depth), B, C.byref(params), C.byref(o),
-                                          _stream()), "popnet_decode")
+        if push is None:
+            _lib.check(self.lib.popnet_decode(_ptr(heat), _ptr(paf), _ptr(depth), B, C.byref(params), C.byref(o),
+                                              _stream()), "popnet_decode")
+        else:
+            _lib.check(self.lib.popnet_decode_push(_ptr(heat), _ptr(paf), _ptr(depth), B, C.byref(params), C.byref(o),
+                                                   C.byref(push), _stream()), "popnet_decode_push")
         return out
 
     def decode(self, heat, paf, depth, params):

@@ -36,14 +36,30 @@ def _digest():
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(HERE, "..", "include")):
         for name in sorted(os.listdir(root)):
-            if name.endswith((".cu", ".cuh", ".h")):
+            if name.endswith((".cu", ".cuh", ".h")) and name != "packlists.c":
                 with open(os.path.join(root, name), "rb") as f:
                     h.update(name.encode() + b"\0" + f.read())
     h.update(repr(sorted(UNITS.items())).encode())
     return h.hexdigest()
 
 
+PACK_SRC = os.path.join(CSRC, "packlists.c")
+PACK_OUT = os.path.join(HERE, "_packlists.so")
+
+
+def build_packlists(force=False):
+    """gcc -> popnet_b200/_packlists.so: the CPython extension that packs the evaluator's ragged lists (host code)."""
+    import sysconfig
+    if not force and os.path.exists(PACK_OUT) and os.path.getmtime(PACK_OUT) >= os.path.getmtime(PACK_SRC):
+        return PACK_OUT
+    cc = os.environ.get("CC", "gcc")
+    cmd = [cc, "-O2", "-fPIC", "-shared", "-std=c11", "-Wall", "-I", sysconfig.get_paths()["include"], PACK_SRC, "-o", PACK_OUT]
+    subprocess.run(cmd, check=True)
+    return PACK_OUT
+
+
 def build(force=False, verbose=False):
+    build_packlists(force)
     digest = _digest()
     if not force and os.path.exists(OUT) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
         return OUT

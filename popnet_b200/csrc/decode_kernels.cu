@@ -21,6 +21,8 @@
 // so throughput comes from frames in flight (B x 15 / B x 14 / B CTAs), not from any single CTA.
 #include <math_constants.h>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
@@ -318,8 +320,42 @@ __device__ __forceinline__ float sum_pairwise_f32(const float* a, int n) {
 
 constexpr int kAsmThreads = 128;
 
+// Multi-GPU record push (PopnetPeerPush, include/popnet_b200.h): every record value is stored locally AND at the same
+// offset of this rank's chunk in every peer's gather buffer -- plain stores to peer-mapped memory (NVLink).
+struct PushCtx {
+  int world, rank;
+  char* peer_chunk[POPNET_MAX_PEERS];      // gather_base[p] + rank * records_bytes (entry `rank` unused)
+  const char* local_chunk;                 // gather_base[rank] + rank * records_bytes: where the local record fields live
+};
+template <typename T>
+__device__ __forceinline__ void rec_store(const PushCtx& pc, T* ptr, T v) {
+  *ptr = v;
+  if (pc.world > 1) {
+    const size_t off = (size_t)(reinterpret_cast<const char*>(ptr) - pc.local_chunk);
+#pragma unroll 1
+    for (int q = 0; q < pc.world; ++q)
+      if (q != pc.rank) *reinterpret_cast<T*>(pc.peer_chunk[q] + off) = v;
+  }
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const float* __restrict__ heat, const float* __restrict__ depth,
-                                                               PopnetDecodeParams p, PopnetDecodeOut o) {
+                                                               PopnetDecodeParams p, PopnetDecodeOut o, PopnetPeerPush push) {
+  PushCtx pc;
+  pc.world = push.world; pc.rank = push.rank;
+  pc.local_chunk = nullptr;
+  if (push.world > 1) {
+    for (int q = 0; q < push.world; ++q)
+      pc.peer_chunk[q] = static_cast<char*>(push.gather_base[q]) + (size_t)push.rank * push.records_bytes;
+    pc.local_chunk = pc.peer_chunk[push.rank];
+  }
   __shared__ int16_t s_pj[POPNET_MAX_PERSONS][POPNET_MAX_JOINTS];
   __shared__ double s_ps[POPNET_MAX_PERSONS];
   __shared__ int s_pc[POPNET_MAX_PERSONS];
@@ -437,8 +473,10 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const float* __re
     }
     if (lane == 0) {
       s_nout = nout;
-      o.n_person[b] = nout;
-      if (flags) atomicOr(o.flags + b, flags);
+      rec_store(pc, o.n_person + b, nout);
+      // the frame's flag word is complete here (peaks / limbs kernels have finished): fold in this kernel's bits
+      const uint32_t fl = o.flags[b] | flags;
+      rec_store(pc, o.flags + b, fl);
     }
   }
   __syncthreads();
@@ -448,14 +486,14 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const float* __re
   for (int i = tid; i < nout; i += kAsmThreads) {
     const size_t row = (size_t)b * MM + i;
     const int q = s_keep[i];
-    if (o.person_score) o.person_score[row] = s_ps[q];
-    if (o.person_njoint) o.person_njoint[row] = s_pc[q];
+    if (o.person_score) rec_store(pc, o.person_score + row, s_ps[q]);
+    if (o.person_njoint) rec_store(pc, o.person_njoint + row, (int32_t)s_pc[q]);
   }
   for (int i = tid; i < nout * K; i += kAsmThreads) {
     const int pi_ = i / K, k = i - pi_ * K;
     const int q = s_keep[pi_], idx = s_pj[q][k];
     const size_t row = (size_t)b * MM + pi_;
-    if (o.person_peak) o.person_peak[row * K + k] = (int16_t)idx;
+    if (o.person_peak) rec_store(pc, o.person_peak + row * K + k, (int16_t)idx);
     double x2 = -1, y2 = -1, Z = -1, conf = 0;
     if (idx >= 0) {
       const int X = s_xy[k][idx][0], Y = s_xy[k][idx][1];
@@ -482,14 +520,45 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const float* __re
       x2 = (double)X / p.input_size * p.w_org;
       y2 = (double)Y / p.input_size * p.h_org;
     }
-    if (o.pose2d) { o.pose2d[(row * K + k) * 2] = x2; o.pose2d[(row * K + k) * 2 + 1] = y2; }
-    if (o.pose_conf) o.pose_conf[row * K + k] = conf;
+    if (o.pose2d) { rec_store(pc, o.pose2d + (row * K + k) * 2, x2); rec_store(pc, o.pose2d + (row * K + k) * 2 + 1, y2); }
+    if (o.pose_conf) rec_store(pc, o.pose_conf + row * K + k, conf);
     if (o.pose3d && depth) {
       double X3 = (x2 - p.cx) * Z / p.fx, Y3 = (y2 - p.cy) * Z / p.fy;
       if (p.flip_y) Y3 = -Y3;
       double* d3 = o.pose3d + (row * K + k) * 3;
-      d3[0] = X3; d3[1] = Y3; d3[2] = Z;
+      rec_store(pc, d3, X3); rec_store(pc, d3 + 1, Y3); rec_store(pc, d3 + 2, Z);
     }
+  }
+  if (push.world > 1) {
+    // publish: when the LAST CTA of the batch has pushed its frame, tag this rank's slot in every rank's arrive[] array
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int ticket = atomicAdd(push.done_counter, 1u);
+      if (ticket == gridDim.x - 1) {
+        *push.done_counter = 0u;
+        const unsigned long long tag = *push.step + 1ull;
+        *push.step = tag;
+        __threadfence_system();
+        for (int q = 0; q < push.world; ++q) st_release_sys(push.arrive[q] + push.rank, tag);
+      }
+    }
+  }
+}
+
+// one warp: lane q waits for rank q's tag of the current step (bounded: a dead peer sets *status instead of hanging)
+__global__ void __launch_bounds__(32) p2p_wait_kernel(const unsigned long long* arrive, int world, const unsigned long long* step,
+                                                      unsigned int* status, unsigned long long timeout_ns) {
+  const int q = threadIdx.x;
+  if (q >= world) return;
+  const unsigned long long want = *step;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (ld_acquire_sys(arrive + q) < want) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) { atomicExch(status, 1u); return; }
+    __nanosleep(200);
   }
 }
 
@@ -555,9 +624,24 @@ __global__ void __launch_bounds__(128) lift_points_kernel(const float* __restric
 
 }  // namespace
 
-extern "C" int popnet_decode(const float* heat, const float* paf, const float* depth, int batch,
-                             const PopnetDecodeParams* p, const PopnetDecodeOut* o, void* stream) {
+namespace {
+int decode_impl(const float* heat, const float* paf, const float* depth, int batch, const PopnetDecodeParams* p,
+                const PopnetDecodeOut* o, const PopnetPeerPush* push, void* stream) {
   if (!heat || !paf || !p || !o || batch < 0) return POPNET_ERR_INVALID_ARG;
+  PopnetPeerPush pp{};
+  if (push) {
+    pp = *push;
+    if (pp.world < 1 || pp.world > POPNET_MAX_PEERS || pp.rank < 0 || pp.rank >= pp.world || !pp.step || !pp.done_counter)
+      return POPNET_ERR_INVALID_ARG;
+    // every record field must live inside this rank's chunk of its own gather buffer
+    const char* lo = static_cast<const char*>(pp.gather_base[pp.rank]) + (size_t)pp.rank * pp.records_bytes;
+    const char* hi = lo + pp.records_bytes;
+    const void* fields[] = {o->n_person, o->flags, o->person_peak, o->person_score, o->person_njoint, o->pose2d, o->pose3d, o->pose_conf};
+    for (const void* f : fields)
+      if (f && (static_cast<const char*>(f) < lo || static_cast<const char*>(f) >= hi)) return POPNET_ERR_INVALID_ARG;
+    for (int q = 0; q < pp.world; ++q)
+      if (!pp.gather_base[q] || !pp.arrive[q]) return POPNET_ERR_INVALID_ARG;
+  }
   // peak_* and conn_* double as the stage-to-stage storage and are therefore mandatory
   if (!o->peak_count || !o->peak_xy || !o->peak_score || !o->conn_count || !o->conn_ij || !o->conn_score ||
       !o->n_person || !o->flags)
@@ -583,8 +667,64 @@ extern "C" int popnet_decode(const float* heat, const float* paf, const float* d
   POPNET_AFTER_LAUNCH();
   limbs_kernel<<<dim3(p->num_limbs, batch), kThreads, smem_limbs, st>>>(paf, *p, *o);
   POPNET_AFTER_LAUNCH();
-  assemble_kernel<<<batch, kAsmThreads, 0, st>>>(heat, depth, *p, *o);
+  assemble_kernel<<<batch, kAsmThreads, 0, st>>>(heat, depth, *p, *o, pp);
   POPNET_AFTER_LAUNCH();
+  return POPNET_OK;
+}
+}  // namespace
+
+extern "C" int popnet_decode(const float* heat, const float* paf, const float* depth, int batch,
+                             const PopnetDecodeParams* p, const PopnetDecodeOut* o, void* stream) {
+  return decode_impl(heat, paf, depth, batch, p, o, nullptr, stream);
+}
+
+extern "C" int popnet_decode_push(const float* heat, const float* paf, const float* depth, int batch,
+                                  const PopnetDecodeParams* p, const PopnetDecodeOut* o, const PopnetPeerPush* push,
+                                  void* stream) {
+  if (!push) return POPNET_ERR_INVALID_ARG;
+  return decode_impl(heat, paf, depth, batch, p, o, push, stream);
+}
+
+extern "C" int popnet_p2p_wait(const unsigned long long* local_arrive, int world, const unsigned long long* step,
+                               unsigned int* status, int timeout_ms, void* stream) {
+  if (!local_arrive || !step || !status || world < 1 || world > POPNET_MAX_PEERS || timeout_ms < 1) return POPNET_ERR_INVALID_ARG;
+  p2p_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(local_arrive, world, step, status,
+                                                                   (unsigned long long)timeout_ms * 1000000ull);
+  POPNET_AFTER_LAUNCH();
+  return POPNET_OK;
+}
+
+extern "C" int popnet_p2p_alloc(size_t bytes, void** dev_ptr_out, unsigned char* handle_out) {
+  if (!dev_ptr_out || !handle_out || bytes == 0) return POPNET_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* ptr = nullptr;
+  POPNET_CUDA_TRY(cudaMalloc(&ptr, bytes));
+  cudaError_t e = cudaMemset(ptr, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) { cudaFree(ptr); return popnet::record_cuda_error(e); }
+  memcpy(handle_out, &h, sizeof(h));
+  *dev_ptr_out = ptr;
+  return POPNET_OK;
+}
+
+extern "C" int popnet_p2p_open(const unsigned char* handle, void** peer_ptr_out) {
+  if (!handle || !peer_ptr_out) return POPNET_ERR_INVALID_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  POPNET_CUDA_TRY(cudaIpcOpenMemHandle(peer_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return POPNET_OK;
+}
+
+extern "C" int popnet_p2p_close(void* peer_ptr) {
+  if (!peer_ptr) return POPNET_ERR_INVALID_ARG;
+  POPNET_CUDA_TRY(cudaIpcCloseMemHandle(peer_ptr));
+  return POPNET_OK;
+}
+
+extern "C" int popnet_p2p_free(void* dev_ptr) {
+  if (!dev_ptr) return POPNET_ERR_INVALID_ARG;
+  POPNET_CUDA_TRY(cudaFree(dev_ptr));
   return POPNET_OK;
 }
 

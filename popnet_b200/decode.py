@@ -134,6 +134,20 @@ def records_to_lists(out, K: int):
     return p2, p3, vis, conf
 
 
+def records_to_packed(out, K: int):
+    """Flat records of a batch -> (pred2d, pred3d, conf) as ``evaluate.Packed`` CSR arrays: the evaluator's inputs without
+    the detour through Python lists (the reference accumulates lists, ...mpreal_ablation.py:266-274, and dumps them to
+    JSON; ``records_to_lists`` produces those)."""
+    from .evaluate import Packed
+    n = np.asarray(out["n_person"]).astype(np.int64)
+    off = np.zeros(len(n) + 1, np.int32)
+    np.cumsum(n, out=off[1:])
+    M = np.asarray(out["pose2d"]).shape[1]
+    keep = (np.arange(M)[None, :] < n[:, None])                      # [B, M] valid person slots, frame-major order
+    sel = lambda a: np.ascontiguousarray(np.asarray(a)[:, :, :K][keep], np.float64)
+    return Packed(sel(out["pose2d"]), off), Packed(sel(out["pose3d"]), off), Packed(sel(out["pose_conf"]), off)
+
+
 def decode_frames(heat, paf, depth, config=None, camera: Camera = MP3DHP, *, input_size: int = 224,
                   strict: bool = True):
     """Batched decode + lift of channel-major maps (NumPy or CUDA tensors):

@@ -27,7 +27,7 @@ import numpy as np
 from . import _abi
 
 __all__ = ["eval_human_dataset_2d", "eval_human_dataset_2d_PCKh", "eval_human_dataset_3d",
-           "eval_ap_mpii_v2", "eval_ap_3D", "match_counts", "pack_humans"]
+           "eval_ap_mpii_v2", "eval_ap_3D", "match_counts", "pack_humans", "Packed"]
 
 _backend = None   # object with .pck(arrs, dist_th, iou_th, K) and .map_assign(arrs, thresh, K, D)
 
@@ -43,36 +43,71 @@ def _get_backend():
 # ---------------------------------------------------------------------------------------------
 # packing
 # ---------------------------------------------------------------------------------------------
+def _packer():
+    """popnet_b200/_packlists.so (csrc/packlists.c, built by popnet_b200.build): walks the reference's nested lists at
+    list-access speed (np.asarray on them was 85 % of a public evaluate call).  Host code, no fallback."""
+    try:
+        from . import _packlists
+    except ImportError as e:
+        from ._lib import PopnetError
+        raise PopnetError("popnet_b200/_packlists.so is missing: build it with `python -m popnet_b200.build`") from e
+    return _packlists
+
+
+class Packed:
+    """CSR-packed humans (flat [S,K,D] float64, off [N+1] int32): what ``pack_humans`` returns.  Every evaluator entry
+    point also ACCEPTS a Packed in place of a ragged list (``io.load_results`` produces them), which skips the packing."""
+    __slots__ = ("flat", "off")
+
+    def __init__(self, flat, off):
+        self.flat, self.off = flat, off
+
+    def __len__(self):
+        return len(self.off) - 1
+
+    def __getitem__(self, f):              # frame f's humans, like indexing the ragged list
+        if not 0 <= f < len(self):
+            raise IndexError(f)
+        return self.flat[self.off[f]:self.off[f + 1]]
+
+    def __iter__(self):
+        return (self.flat[self.off[f]:self.off[f + 1]] for f in range(len(self)))
+
+
 def pack_humans(human_set, K: int, D: int):
-    """Ragged [N][n_f][K][D] lists -> (flat [S,K,D] float64, off [N+1] int32)."""
-    off = np.zeros(len(human_set) + 1, np.int32)
-    rows = []
-    for f, humans in enumerate(human_set):
-        off[f + 1] = off[f] + len(humans)
-        rows.extend(humans)
-    if rows:
-        flat = np.asarray(rows, dtype=np.float64)
-        if flat.shape[1:] != (K, D):
-            raise ValueError("every human must be a %d x %d list, got %r" % (K, D, flat.shape[1:]))
-    else:
-        flat = np.zeros((0, K, D), np.float64)
-    return np.ascontiguousarray(flat), off
+    """Ragged [N][n_f][K][D] lists (or a Packed) -> (flat [S,K,D] float64, off [N+1] int32)."""
+    if isinstance(human_set, Packed):
+        if human_set.flat.shape[1:] != (K, D):
+            raise ValueError("every human must be a %d x %d list, got %r" % (K, D, human_set.flat.shape[1:]))
+        return human_set.flat, human_set.off
+    flat, off = _packer().pack_humans(human_set, K, D)
+    return np.frombuffer(flat, np.float64).reshape(-1, K, D), np.frombuffer(off, np.int32)
 
 
 def _pack_rows(per_frame_rows, K: int, dtype):
-    rows = []
-    for r in per_frame_rows:
-        rows.extend(r)
-    if not rows:
-        return np.zeros((0, K), dtype)
-    return np.ascontiguousarray(np.asarray(rows, dtype=np.float64).astype(dtype))
+    if isinstance(per_frame_rows, Packed):
+        flat = np.ascontiguousarray(per_frame_rows.flat, np.float64).reshape(-1, K)
+        return flat if dtype == np.float64 else np.ascontiguousarray(flat.astype(dtype))
+    flat = np.frombuffer(_packer().pack_rows(per_frame_rows, K), np.float64).reshape(-1, K)
+    return flat if dtype == np.float64 else np.ascontiguousarray(flat.astype(dtype))
+
+
+def _frame_counts(human_set):
+    if isinstance(human_set, Packed):
+        return np.diff(human_set.off)
+    return np.fromiter((len(h) for h in human_set), np.int64, len(human_set))
+
+
+def _ones_rows(human_set, K):
+    """[np.ones((len(g), K)).tolist() for g in human_set] (eval_pck.py:107-111, eval_mAP.py:298-307), built without NumPy"""
+    return [[[1.0] * K for _ in range(n)] for n in _frame_counts(human_set).tolist()]
 
 
 def _head_sizes(humans_gt_set, ind1: int, ind2: int):
     """compute_head_size (eval_pck.py:232-246) / compute_head_size_from_two_joints (eval_mAP.py:26-40),
     evaluated with the reference's expression on the caller's own number types."""
     out = []
-    for humans in humans_gt_set:
+    for humans in humans_gt_set:                   # (a Packed iterates frame by frame: the same expression on float64 scalars)
         for human in humans:
             out.append(2 * np.sqrt((human[ind1][0] - human[ind2][0]) ** 2 + (human[ind1][1] - human[ind2][1]) ** 2))
     return out
@@ -94,7 +129,7 @@ def _run_pck(pred2d_set, gt2d_set, pred3d_set, gt3d_set, K, dist_th, iou_th, vis
     vis_all = None
     if vis_set is not None:
         # the reference only walks visibility rows of frames that have GT humans (eval_pck.py:50-58)
-        vis_all = _pack_rows([v for v, g in zip(vis_set, gt2d_set) if len(g) > 0], K, np.float64)
+        vis_all = _pack_rows([v for v, n in zip(vis_set, _frame_counts(gt2d_set)) if n > 0], K, np.float64)
         if vis_all.shape[0] != gt2d.shape[0]:
             raise ValueError("visibility rows do not match GT humans")
         arrs["gt_vis"] = np.ascontiguousarray((vis_all != 0).astype(np.uint8))
@@ -137,7 +172,7 @@ def eval_human_dataset_2d_PCKh(humans_pred_set, humans_gt_set, head_id, neck_id,
     """util/eval_pck.py:80-154 (per-GT threshold h_th * head size; default visibility = all ones)."""
     assert len(humans_gt_set) == len(humans_pred_set)
     if human_gt_set_visibility is None:
-        human_gt_set_visibility = [np.ones((len(g), num_joints)).tolist() for g in humans_gt_set]
+        human_gt_set_visibility = _ones_rows(humans_gt_set, num_joints)
     hsz = _head_sizes(humans_gt_set, head_id, neck_id)
     gt_thresh = [h * h_th for h in hsz]
     out, vis_all, n = _run_pck(humans_pred_set, humans_gt_set, None, None, num_joints, 0.0, iou_th,
@@ -164,7 +199,7 @@ def eval_human_dataset_2d_PCKh_rect(humans_pred_set, humans_gt_set, head_sz_set,
     hsz = 0.6 * diagonal."""
     assert len(humans_gt_set) == len(humans_pred_set)
     if human_gt_set_visibility is None:
-        human_gt_set_visibility = [np.ones((len(g), num_joints)).tolist() for g in humans_gt_set]
+        human_gt_set_visibility = _ones_rows(humans_gt_set, num_joints)
     hsz = _head_sizes_from_rect(head_sz_set, humans_gt_set)
     gt_thresh = [h * h_th for h in hsz]
     out, vis_all, n = _run_pck(humans_pred_set, humans_gt_set, None, None, num_joints, 0.0, iou_th,
@@ -221,27 +256,34 @@ def _voc_ap(recall, precision):
 def _assign(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, ref_dist_set, K, D, thresh):
     pred, pred_off = pack_humans(humans_pred_set, K, D)
     gt, gt_off = pack_humans(humans_gt_set, K, D)
-    for f in range(len(humans_gt_set)):
-        if pred_off[f + 1] > pred_off[f] and gt_off[f + 1] == gt_off[f]:
-            # eval_mAP.py:124 np.argmax over an empty GT axis
-            raise ValueError("attempt to get argmax of an empty sequence")
-    conf = _pack_rows(conf_pred_set, K, np.float64)
-    vis = _pack_rows(gt_visibility_set, K, np.float64)
-    ref = np.ascontiguousarray(np.asarray([r for fr in ref_dist_set for r in fr], np.float64))
-    arrs = {"pred": pred, "pred_off": pred_off, "gt": gt, "gt_off": gt_off, "ref_dist": ref,
-            "gt_vis": np.ascontiguousarray((vis > 0).astype(np.uint8))}
+    if np.any((np.diff(pred_off) > 0) & (np.diff(gt_off) == 0)):
+        # eval_mAP.py:124 np.argmax over an empty GT axis
+        raise ValueError("attempt to get argmax of an empty sequence")
+    conf = np.ones((pred.shape[0], K)) if conf_pred_set is _ALL_ONES else _pack_rows(conf_pred_set, K, np.float64)
+    if gt_visibility_set is _ALL_ONES:
+        vis8 = np.ones((gt.shape[0], K), np.uint8)
+    else:
+        vis8 = np.ascontiguousarray((_pack_rows(gt_visibility_set, K, np.float64) > 0).astype(np.uint8))
+    if ref_dist_set is _ALL_ONES:
+        ref = np.ones(gt.shape[0], np.float64)
+    else:
+        ref = np.ascontiguousarray(np.asarray([r for fr in ref_dist_set for r in fr], np.float64))
+    arrs = {"pred": pred, "pred_off": pred_off, "gt": gt, "gt_off": gt_off, "ref_dist": ref, "gt_vis": vis8}
     out = _get_backend().map_assign(arrs, thresh=float(thresh), K=K, D=D)
     return out, conf
 
 
-#: "numpy" = the reference's own NumPy calls for the sort / scan / envelope (bit-identical to util/eval_mAP.py:160-207);
-#: "device" = popnet_eval_ap (stable tie order, float64 sums in a different order: agrees to ~1e-12)
-AP_TAIL = "numpy"
+#: "device" (default) = popnet_eval_ap: per-joint sort by (score descending, prediction index ascending) -- one of the
+#: orders the reference's unstable np.argsort can produce --, true-positive scan, VOC envelope; float64 sums in a
+#: different order than NumPy's pairwise sum: AP agrees with the reference to ~1e-12 (tests assert 1e-9).
+#: "numpy" = the reference's own NumPy calls for the sort / scan / envelope (util/eval_mAP.py:160-207) on the device's labels.
+AP_TAIL = "device"
+_ALL_ONES = object()          # sentinel: "this input is the reference's all-ones default" -- nothing to pack
 
 
 def _ap_from_labels(out, conf, joint_names):
     K = len(joint_names)
-    if AP_TAIL == "device":
+    if AP_TAIL == "device" and hasattr(_get_backend(), "ap_tail"):       # (the CPU test seam has no device tail)
         ap = np.asarray(_get_backend().ap_tail(conf, out["labels"], out["n_gt"]), np.float64)
     else:
         ap = np.zeros(K + 1)
@@ -258,13 +300,16 @@ def _ap_from_labels(out, conf, joint_names):
 
 
 def _fill_defaults(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, K):
-    # eval_mAP.py:297-307: empty lists are filled in place (the caller's lists are mutated)
+    """eval_mAP.py:297-307: empty lists are filled in place with all-ones rows (the caller's lists are mutated, as in the
+    reference).  Returns the (conf, visibility) inputs for the packer: the sentinel when we just wrote the ones ourselves."""
+    vis, conf = gt_visibility_set, conf_pred_set
     if len(gt_visibility_set) == 0:
-        for g in humans_gt_set:
-            gt_visibility_set.append(np.ones((len(g), K)).tolist())
+        gt_visibility_set.extend(_ones_rows(humans_gt_set, K))
+        vis = _ALL_ONES
     if len(conf_pred_set) == 0:
-        for p in humans_pred_set:
-            conf_pred_set.append(np.ones((len(p), K)).tolist())
+        conf_pred_set.extend(_ones_rows(humans_pred_set, K))
+        conf = _ALL_ONES
+    return conf, vis
 
 
 def eval_ap_mpii_v2(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, head_id, neck_id,
@@ -274,8 +319,8 @@ def eval_ap_mpii_v2(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility
     assert len(humans_gt_set) == len(humans_pred_set)
     K = len(joint_names)
     ref_dist_set = [_head_sizes([g], head_id, neck_id) for g in humans_gt_set]
-    _fill_defaults(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, K)
-    out, conf = _assign(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, ref_dist_set, K, 2, thresh)
+    conf_in, vis_in = _fill_defaults(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, K)
+    out, conf = _assign(humans_pred_set, conf_in, humans_gt_set, vis_in, ref_dist_set, K, 2, thresh)
     ap = _ap_from_labels(out, conf, joint_names)
     return (ap, out) if _return_counts else ap
 
@@ -287,8 +332,8 @@ def eval_ap_mpii(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_se
     assert len(humans_gt_set) == len(humans_pred_set)
     K = len(joint_names)
     ref_dist_set = [_head_sizes_from_rect([head_sz_set[i]]) for i in range(len(humans_gt_set))]
-    _fill_defaults(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, K)
-    out, conf = _assign(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, ref_dist_set, K, 2, thresh)
+    conf_in, vis_in = _fill_defaults(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, K)
+    out, conf = _assign(humans_pred_set, conf_in, humans_gt_set, vis_in, ref_dist_set, K, 2, thresh)
     ap = _ap_from_labels(out, conf, joint_names)
     return (ap, out) if _return_counts else ap
 
@@ -299,8 +344,7 @@ def eval_ap_3D(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set,
     print('3D evaluation in AP under {:01f} meter rule ...'.format(thresh))
     assert len(humans_gt_set) == len(humans_pred_set)
     K = len(joint_names)
-    ref_dist_set = [np.ones(len(g)).tolist() for g in humans_gt_set]
-    _fill_defaults(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, K)
-    out, conf = _assign(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, ref_dist_set, K, 3, thresh)
+    conf_in, vis_in = _fill_defaults(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set, K)
+    out, conf = _assign(humans_pred_set, conf_in, humans_gt_set, vis_in, _ALL_ONES, K, 3, thresh)
     ap = _ap_from_labels(out, conf, joint_names)
     return (ap, out) if _return_counts else ap

@@ -24,92 +24,161 @@ RECORD_KEYS = ("n_person", "flags", "person_peak", "person_score", "person_njoin
 
 
 class PoseEstimator:
-    def __init__(self, model, camera: Camera = MP3DHP, config: DecodeConfig | None = None, *, input_size: int = 224,
-                 max_persons: int = 32, max_peaks: int = _abi.MAX_PEAKS, strict: bool = True):
+    """frames -> poses.  Each batch in flight owns a *slot*: the device input buffer, the six network output maps, the
+    decode record buffer and its pinned host mirror.  The launch sequence of a slot -- forward (39 convolutions on three
+    streams), then decode + lift (+ the record push to the peer GPUs) -- is captured ONCE into two CUDA graphs and
+    replayed every step: one graph launch on the main stream for the forward, one on the decode stream for the decode,
+    so the (latency-bound) decode of batch i runs under the forward of batch i+1 and the host issues two launches per
+    step instead of ~45.  ``use_graphs=False`` issues the same launches eagerly (tests compare both)."""
+
+    NSLOT = 3      # batches in flight: H2D of batch i+2, forward of batch i+1 and decode + D2H of batch i overlap
+
+    def __init__(self, model, camera: Camera = MP3DHP, config: DecodeConfig | None = None, *, input_size=224,
+                 max_persons: int = 32, max_peaks: int = _abi.MAX_PEAKS, strict: bool = True, use_graphs: bool = True,
+                 peers=None):
         from ._cuda_backend import CudaBackend          # raises without CUDA / the library
         self.backend = CudaBackend()
         self.model = model
         self.camera = camera
         self.config = config or DecodeConfig()
-        self.input_size = input_size
+        self.input_hw = (input_size, input_size) if isinstance(input_size, int) else tuple(input_size)
+        self.input_size = self.input_hw[0]
+        ds = self.config.downsample
         # the network's third head has num_limbs + 1 planes; joint j reads plane j (...mpreal_ablation.py:212-215)
-        self.params = _abi.make_decode_params(self.config, camera, input_size=input_size, max_peaks=max_peaks,
-                                              max_persons=max_persons, depth_channels=model.num_limbs + 1)
+        self.params = _abi.make_decode_params(self.config, camera, input_size=self.input_hw[1], max_peaks=max_peaks,
+                                              max_persons=max_persons, depth_channels=model.num_limbs + 1,
+                                              grid_hw=(self.input_hw[0] // ds, self.input_hw[1] // ds))
         #: the reference's lists are unbounded; max_peaks / max_persons are device capacities.  strict: collect() raises
         #: OverflowError when a frame hit one of them (its poses would differ from the reference's); strict=False
         #: leaves the check of out["flags"] to the caller.
         self.strict = strict
-        self._out = None
-        self._x_dev = None
+        self.use_graphs = use_graphs
+        self.peers = peers          # optional p2p.PeerGather: the multi-GPU record exchange, fused into the decode
         self._slots = None
+        self._B = None
         self.inject = None          # optional (heat, paf, depth) device tensors decoded INSTEAD of the network's maps
+                                    # (decode-only tests; eager mode only)
 
     # ---------------------------------------------------------------------------------------
-    NSLOT = 3      # batches in flight: H2D of batch i+2, forward of batch i+1 and decode + D2H of batch i overlap
-
     def _buffers(self, B):
-        if self._out is None or self._out["n_person"].shape[0] != B:
-            from ._cuda_backend import alloc_decode_out
-            self._slots = []
-            for _ in range(self.NSLOT):
-                out = alloc_decode_out(B, self.params)
-                self._slots.append({
-                    "out": out,
-                    "x": torch.empty((B, 1, self.input_size, self.input_size), dtype=torch.float32, device="cuda"),
-                    "host": torch.empty(out["_records"].shape, dtype=torch.uint8).pin_memory(),
-                    "h2d": torch.cuda.Event(), "done": torch.cuda.Event(), "busy": False,
-                })
-            self._out = self._slots[0]["out"]
-            self._x_dev = self._slots[0]["x"]
-            self._copy_stream = torch.cuda.Stream()
-            self.decode_stream = torch.cuda.Stream()
-            self._next = 0
-        return self._out
+        if self._slots is not None and self._B == B:
+            return self._slots
+        from ._cuda_backend import alloc_decode_out
+        H, W = self.input_hw
+        self._prepared = self.model.prepare(B, H, W)
+        self._slots = []
+        for i in range(self.NSLOT):
+            out = alloc_decode_out(B, self.params, records=None if self.peers is None else self.peers.local_records(i, B, self.params))
+            self._slots.append({
+                "index": i, "out": out, "x": torch.zeros((B, 1, H, W), dtype=torch.float32, device="cuda"),
+                "maps": self.model.alloc_maps(B, H, W),
+                "host": torch.empty(out["_records"].shape, dtype=torch.uint8).pin_memory(),
+                "h2d": torch.cuda.Event(), "fwd_done": torch.cuda.Event(), "done": torch.cuda.Event(), "busy": False,
+                "graphs": None,
+            })
+        self._B = B
+        self._copy_stream = torch.cuda.Stream()
+        self.decode_stream = torch.cuda.Stream()
+        self._capture_stream = torch.cuda.Stream()
+        self._next = 0
+        return self._slots
 
-    def infer_device(self, x_dev, out=None, after=None, _evs=None):
-        """x_dev [B,1,H,W] fp32 CUDA -> dict of device record tensors (no synchronisation).
+    def refresh(self):
+        """Drop the captured graphs and buffers (after editing the model's weights or changing operand_dtype)."""
+        self._slots, self._B = None, None
 
-        The forward runs on the current stream; decode + lift run on a second stream that waits on the forward's
-        completion event, so the (latency-bound, low-occupancy) decode of batch i overlaps the forward of batch i+1.
-        Work later enqueued on ``self.decode_stream`` (D2H, all-gather) is ordered after the decode; callers that read
-        the records from another stream must wait on ``out["_ready"]``.  ``after``: optional callable run on the decode
-        stream right after the decode (used for the D2H copy / the collective)."""
-        B = x_dev.shape[0]
-        self._buffers(B)
-        out = self._out if out is None else out
-        main = torch.cuda.current_stream()
-        if _evs is not None:
-            _evs[0].record(main)            # bench hook: start of the forward on its stream
-        (paf, heat, depth), _ = self.model(x_dev)
-        if _evs is not None:
-            _evs[1].record(main)            # bench hook: end of the forward
-        fwd_done = torch.cuda.Event()
-        fwd_done.record(main)
+    # the two halves of a step, as plain launch sequences on the current stream
+    def _launch_forward(self, slot):
+        self.model.forward_into(slot["x"], slot["maps"], self._prepared)
+
+    def _launch_decode(self, slot, d2h=True):
+        paf, heat, depth = slot["maps"][3:6]
         if self.inject is not None:
             heat, paf, depth = self.inject
-        ds = self.decode_stream
-        ds.wait_event(fwd_done)
-        with torch.cuda.stream(ds):
-            if _evs is not None:
-                _evs[2].record(ds)          # bench hook: start of the decode on the decode stream
-            self.backend.decode_device(heat, paf, depth, self.params, out)
-            for t in (heat, paf, depth):
-                t.record_stream(ds)
-            res = after(out) if after is not None else None
-            ready = torch.cuda.Event()
-            ready.record(ds)
-        out["_ready"] = ready
-        out["_after"] = res
-        return out
+        push = None if self.peers is None else self.peers.push_args(slot["index"])
+        self.backend.decode_device(heat, paf, depth, self.params, slot["out"], push=push)
+        if self.peers is not None:
+            self.peers.wait_arrivals(slot["index"])          # one-warp kernel: all ranks' records of this step have landed
+        if d2h:
+            slot["host"].copy_(slot["out"]["_records"], non_blocking=True)
 
-    def submit(self, frames, after=None):
+    def _capture(self, slot):
+        """Capture the slot's forward and decode sequences.  Warm-up launches first (lazy module loading, attribute
+        calls), then capture on side streams as torch requires."""
+        if self.inject is not None:
+            raise RuntimeError("inject is a decode-only test hook: construct the estimator with use_graphs=False")
+        s = self._capture_stream          # one side stream for all captures (the forward keeps branch streams per caller stream)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._launch_forward(slot)
+            self._launch_decode(slot)
+        s.synchronize()
+        if self.peers is not None:
+            self.peers.barrier()          # the warm-up pushed one record set: every rank is past it before the real ones
+        gf, gd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gf, stream=s, capture_error_mode="thread_local"):
+            self._launch_forward(slot)
+        with torch.cuda.graph(gd, stream=s, capture_error_mode="thread_local"):
+            self._launch_decode(slot)
+        slot["graphs"] = (gf, gd)
+
+    def _run_slot(self, slot, evs=None):
+        """Enqueue forward (current stream) and decode (decode stream) of a slot whose input buffer is (or will be, by
+        stream order) filled.  evs: optional 4 timing events [fwd start, fwd end, decode start, decode end]."""
+        main, ds = torch.cuda.current_stream(), self.decode_stream
+        graphs = self.use_graphs and self.inject is None
+        if graphs and slot["graphs"] is None:
+            self._capture(slot)
+        # the decode of this slot's previous use must have finished reading the maps before the forward rewrites them
+        main.wait_event(slot["done"])
+        if evs is not None:
+            evs[0].record(main)
+        if graphs:
+            slot["graphs"][0].replay()
+        else:
+            self._launch_forward(slot)
+        if evs is not None:
+            evs[1].record(main)
+        slot["fwd_done"].record(main)
+        ds.wait_event(slot["fwd_done"])
+        with torch.cuda.stream(ds):
+            if evs is not None:
+                evs[2].record(ds)
+            if graphs:
+                slot["graphs"][1].replay()
+            else:
+                self._launch_decode(slot)
+            if evs is not None:
+                evs[3].record(ds)
+            slot["done"].record(ds)
+
+    # ---------------------------------------------------------------------------------------
+    def infer_device(self, x_dev, evs=None):
+        """x_dev [B,1,H,W] fp32 CUDA -> the slot's dict of DEVICE record tensors (no synchronisation; wait on
+        ``out["_ready"]`` before reading them from another stream).  The frames are copied into the slot's input buffer
+        (device to device) unless ``x_dev`` is a slot buffer returned by ``slot_input``."""
+        B = x_dev.shape[0]
+        slots = self._buffers(B)
+        slot = next((s for s in slots if s["x"].data_ptr() == x_dev.data_ptr()), None)
+        if slot is None:
+            slot = slots[self._next % self.NSLOT]
+            self._next += 1
+            torch.cuda.current_stream().wait_event(slot["done"])
+            slot["x"].copy_(x_dev, non_blocking=True)
+        self._run_slot(slot, evs)
+        slot["out"]["_ready"] = slot["done"]
+        return slot["out"]
+
+    def slot_input(self, i, B):
+        """The device input buffer of slot i (fill it, then pass it to ``infer_device``: no staging copy)."""
+        return self._buffers(B)[i % self.NSLOT]["x"]
+
+    def submit(self, frames):
         """Asynchronous half of ``infer``: enqueue H2D (copy stream) -> forward -> decode -> D2H for one batch of HOST
-        frames and return a ticket.  Up to NSLOT batches may be in flight; ``collect`` them in submission order.
-        ``after(out)``: optional callable enqueued on the decode stream behind the D2H copy (e.g. ``gather_records``)."""
+        frames and return a ticket.  Up to NSLOT batches may be in flight; ``collect`` them in submission order."""
         x = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames, np.float32))
         B = x.shape[0]
-        self._buffers(B)
-        slot = self._slots[self._next % self.NSLOT]
+        slot = self._buffers(B)[self._next % self.NSLOT]
         if slot["busy"]:
             raise RuntimeError("collect() the oldest batch before submitting a %dth one" % (self.NSLOT + 1))
         self._copy_stream.wait_event(slot["done"])          # the previous user of this slot has finished with x / host
@@ -117,12 +186,7 @@ class PoseEstimator:
             slot["x"].copy_(x, non_blocking=True)
             slot["h2d"].record(self._copy_stream)
         torch.cuda.current_stream().wait_event(slot["h2d"])
-        # one D2H transfer for all record fields, on the decode stream right behind the decode
-        def tail(o):
-            slot["host"].copy_(o["_records"], non_blocking=True)
-            return after(o) if after is not None else None
-        out = self.infer_device(slot["x"], slot["out"], after=tail)
-        slot["done"] = out["_ready"]
+        self._run_slot(slot)
         slot["busy"] = True
         self._next += 1
         return (slot, B)
@@ -138,17 +202,21 @@ class PoseEstimator:
             _raise_on_overflow(rec["flags"])
         return rec
 
+    def gathered(self, ticket):
+        """Multi-GPU: DEVICE views of ALL ranks' records of a collected batch (rank r's frames at [r*B, (r+1)*B))."""
+        slot, B = ticket
+        return unpack_records(self.peers.gathered(slot["index"]), slot["out"]["_layout"], B, self.peers.world)
+
     def infer(self, frames):
         """The user-facing call: ``frames`` [B,1,H,W] fp32 on the HOST (NumPy array or, to avoid a staging copy,
         a pinned torch tensor) -> dict of NumPy pose records.  Includes H2D of the frames and D2H of the records."""
         return self.collect(self.submit(frames))
 
     def h2d_bytes(self, B):
-        return B * self.input_size * self.input_size * 4
+        return B * self.input_hw[0] * self.input_hw[1] * 4
 
     def d2h_bytes(self, B):
-        self._buffers(B)
-        return int(self._out["_records"].numel())
+        return int(self._buffers(B)[0]["out"]["_records"].numel())
 
 
 # ---------------------------------------------------------------------------------------------

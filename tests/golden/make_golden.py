@@ -165,8 +165,62 @@ def make_forward():
     np.savez_compressed(os.path.join(HERE, "forward_golden.npz"), **out)
 
 
+E2E_FRAMES, E2E_SEED, E2E_MAP_FRAMES = 1024, 777_000, 8
+
+
+def make_e2e():
+    """End-to-end golden of the fixture checkpoint (tests/golden/fixture_ckpt.npz, tools/make_fixture_ckpt.py): the
+    reference's eval loop (evaluation_rtpose_light3d_kdh3d_mpreal_ablation.py:161-263) on 1024 seeded synthetic depth
+    frames -- reference module forward (fp32, CPU) -> paf_to_pose -> paf_to_human_list -> retrieve_depth_heat_weighted ->
+    rescale / back-projection.  Stored: per frame the assembled persons (2D joints, 3D joints, confidences) and the
+    peak / person counts; the six fp32 output maps of the first 8 frames (tolerance anchor)."""
+    import cv2
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    ref = refshim.load()
+    sd = helpers.fixture_state_dict()
+    model = ref.rtpose_light3d(15, 14, 2, input_dim=1).float().eval()
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = synth.depth_frames(E2E_FRAMES, seed=E2E_SEED)
+    out = {"x_sha": np.array(sha(x)), "state_sha": np.array(sha(*[sd[k] for k in sorted(sd)]))}
+    n_person, off, p2, p3, pc, npk = [], [0], [], [], [], []
+    cv2.ipp.setUseIPP(False)                 # OpenCV's own C++ resize: the path the oracle is bit-exact against
+    for b0 in range(0, E2E_FRAMES, 32):
+        with torch.no_grad():
+            (paf, heat, depth), saved = model(torch.from_numpy(x[b0:b0 + 32]))
+        paf, heat, depth = paf.numpy(), heat.numpy(), depth.numpy()
+        if b0 == 0:
+            for name, t in (("paf", paf), ("heat", heat), ("depth", depth)):
+                out["maps/" + name] = t[:E2E_MAP_FRAMES].copy()
+            for name, t in zip(("paf1", "heat1", "depth1"), saved[:3]):
+                out["maps/" + name] = t.numpy()[:E2E_MAP_FRAMES].copy()
+        for f in range(paf.shape[0]):
+            r = refshim.reference_decode_frame(ref, heat[f], paf[f], depth[f], MP3DHP)
+            P = len(r["humans_2d"])
+            n_person.append(P)
+            npk.append(len(r["joint_list"]))
+            off.append(off[-1] + P)
+            p2.append(np.asarray(r["humans_2d"], np.float64).reshape(P, 15, 2))
+            p3.append(np.asarray(r["humans_3d"], np.float64).reshape(P, 15, 3))
+            pc.append(np.asarray(r["conf"], np.float64).reshape(P, 15))
+        print("e2e frames", b0 + 32, "persons so far", off[-1], flush=True)
+    cv2.ipp.setUseIPP(True)
+    out["n_person"] = np.asarray(n_person, np.int32)
+    out["n_peaks"] = np.asarray(npk, np.int32)
+    out["off"] = np.asarray(off, np.int32)
+    out["pose2d"] = np.concatenate(p2, 0)
+    out["pose3d"] = np.concatenate(p3, 0).astype(np.float32)     # compared with a tolerance (bf16 forward): fp32 storage
+    out["conf"] = np.concatenate(pc, 0).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "e2e_golden.npz"), **out)
+    print("e2e golden:", E2E_FRAMES, "frames,", off[-1], "persons")
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["decode", "eval", "forward"]
+    if "e2e" in what:
+        make_e2e()
     if "decode" in what:
         make_decode()
     if "eval" in what:

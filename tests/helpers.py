@@ -8,6 +8,7 @@ from popnet_b200 import _abi, synth
 from popnet_b200.topology import ITOP, MP3DHP, DecodeConfig
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CAMS = {"MP3DHP": MP3DHP, "ITOP": ITOP}
 # must mirror tests/golden/make_golden.py::DECODE_CASES
 DECODE_CASES = [("mp", 40, 100, (1, 6), 0.01, "MP3DHP"), ("crowd", 8, 900, (12, 16), 0.01, "MP3DHP"),
@@ -92,3 +93,11 @@ def records_equal(a, b, keys=None):
             if not np.array_equal(a[k][f, :n], b[k][f, :n]):
                 bad.append("%s[%d]" % (k, f))
     return bad
+
+
+def fixture_state_dict():
+    """The fixture checkpoint (tests/golden/fixture_ckpt.npz): the reference module trained for a few thousand steps
+    with the reference's own loss on synthetic frames (tools/make_fixture_ckpt.py).  Stored fp16, widened to fp32 here:
+    the fixture IS the fp16-rounded weights, used identically by the reference, the oracle and the CUDA path."""
+    z = np.load(os.path.join(GOLDEN, "fixture_ckpt.npz"))
+    return {k: (z[k].astype(np.float32) if z[k].dtype != np.int64 else z[k]) for k in z.files}

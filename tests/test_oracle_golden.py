@@ -165,3 +165,39 @@ def test_evaluator_edge_cases(eval_on_oracle):
     # mAP: predictions in a frame without GT make the reference raise ValueError
     with pytest.raises(ValueError):
         _quiet(eval_on_oracle.eval_ap_3D, [[np.zeros((K, 3)).tolist()]], [], [[]], [], list(JOINT_NAMES), 0.1)
+
+
+def test_packed_inputs_equal_list_inputs(oracle_lib, monkeypatch):
+    """The evaluator accepts CSR-packed humans (evaluate.Packed) in place of the reference's ragged lists: same counters,
+    same distances, same AP; the C list packer (csrc/packlists.c) reproduces np.asarray on the nested lists."""
+    import contextlib
+    import copy
+    import io
+    from oracle.backend import OracleBackend
+    from popnet_b200 import evaluate as E
+    from popnet_b200 import synth
+    from popnet_b200.topology import JOINT_NAMES
+    monkeypatch.setattr(E, "_backend", OracleBackend())
+    ds = synth.eval_set(300, seed=12)
+    ds["pred2d"][5] = []
+    ds["pred3d"][5] = []
+    ds["conf"][5] = []
+    pk = {k: E.Packed(*E.pack_humans(ds[k], 15, 3 if "3d" in k else 2)) for k in ("pred2d", "pred3d", "gt2d", "gt3d")}
+    flat = np.asarray([h for fr in ds["pred3d"] for h in fr], np.float64)
+    assert np.array_equal(pk["pred3d"].flat, flat) and pk["pred3d"].off[-1] == len(flat)
+    conf = E.Packed(E._pack_rows(ds["conf"], 15, np.float64), pk["pred2d"].off)
+    names = list(JOINT_NAMES)
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = E.eval_human_dataset_3d(ds["pred2d"], ds["gt2d"], ds["pred3d"], ds["gt3d"], 15, 0.1, 0.5)
+        b = E.eval_human_dataset_3d(pk["pred2d"], pk["gt2d"], pk["pred3d"], pk["gt3d"], 15, 0.1, 0.5)
+        c = E.eval_human_dataset_2d_PCKh(ds["pred2d"], ds["gt2d"], 0, 1, 15, 0.5, 0.5)
+        d = E.eval_human_dataset_2d_PCKh(pk["pred2d"], pk["gt2d"], 0, 1, 15, 0.5, 0.5)
+        e = E.eval_ap_3D(ds["pred3d"], copy.deepcopy(ds["conf"]), ds["gt3d"], [], names, 0.1)
+        f = E.eval_ap_3D(pk["pred3d"], conf, pk["gt3d"], [], names, 0.1)
+        g2 = E.eval_ap_mpii_v2(ds["pred2d"], copy.deepcopy(ds["conf"]), ds["gt2d"], [], 0, 1, names, 0.5)
+        h2 = E.eval_ap_mpii_v2(pk["pred2d"], conf, pk["gt2d"], [], 0, 1, names, 0.5)
+    for x, y in ((a, b), (c, d)):
+        assert np.array_equal(np.asarray(x[0]), np.asarray(y[0])) and np.array_equal(np.asarray(x[1]), np.asarray(y[1]))
+    assert np.array_equal(e, f) and np.array_equal(g2, h2)
+    with pytest.raises(ValueError):
+        E.pack_humans([[[[0.0, 1.0]] * 14]], 15, 2)

@@ -168,8 +168,11 @@ def test_head_rectangle_variants_cuda_vs_oracle(cuda_backend, monkeypatch):
         a = _quiet(E.eval_human_dataset_2d_PCKh_rect, ds["pred2d"], ds["gt2d"], rects, 15, 0.5, 0.5)
         b = _quiet(E.eval_ap_mpii, ds["pred2d"], copy.deepcopy(ds["conf"]), ds["gt2d"], [], rects, names, 0.5)
         res.append((np.asarray(a[0]), np.asarray(a[1]), np.asarray(b)))
-    for x, y in zip(*res):
+    for x, y in zip(res[0][:2], res[1][:2]):           # PCKh values: identical counters -> identical numbers
         assert np.array_equal(x, y, equal_nan=True)
+    # AP: the CUDA backend runs the tail on the device (the default), the oracle backend runs the NumPy tail: float64
+    # sums in a different order -> 1e-9 on the 0..100 scale (as in test_ap_tail_on_device)
+    assert np.allclose(res[0][2], res[1][2], rtol=0, atol=1e-9, equal_nan=True), np.abs(res[0][2] - res[1][2]).max()
     assert res[0][2][-1] > 10.0          # a meaningful AP, not an all-zero agreement
 
 

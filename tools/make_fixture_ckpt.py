@@ -56,11 +56,12 @@ def main():
     ap.add_argument("--resume", default=None)
     ap.add_argument("--out", default=OUT)
     ap.add_argument("--save-every", type=int, default=250)
+    ap.add_argument("--threads", type=int, default=0, help="torch CPU threads (0 = all cores)")
     args = ap.parse_args()
 
     import torch
     torch.manual_seed(0)
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(args.threads or os.cpu_count() or 1)
     ref = refshim.load()
     from lib.network.losses import rtpose_light3d_loss_fgweight          # the reference's loss, unmodified
     names = ["loss_stage%d_L%d" % (j, k) for j in (1, 2) for k in (1, 2, 3)]

@@ -297,6 +297,7 @@ def run_ours(args, rank, local_rank, world):
     model = network.rtpose_light3d(15, 14, 2, input_dim=1)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in fixture_state_dict().items()})
     model.operand_dtype = _abi.OPERAND_BF16 if args.dtype == "bf16" else _abi.OPERAND_FP16
+    model.tuning = args.tuning
     peers = None
     if world > 1:
         from popnet_b200 import p2p
@@ -435,6 +436,8 @@ def run_ours(args, rank, local_rank, world):
     cfg["l2"] = ("%d rotating input sets; one step moves > 1.5 GB through the 126 MB L2 (activation workspace %.0f MB), "
                  "nothing survives from one step to the next" % (NS, lib.popnet_workspace_bytes(model._net_config(224, 224), B) / 1e6))
     cfg["cuda_graphs"] = bool(est.use_graphs)
+    if args.tuning:
+        cfg["tuning"] = "0x%x" % args.tuning
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "repeats": repeats, "timed_region_s": elapsed_ms * 1e-3,
@@ -488,6 +491,7 @@ def main():
                     help="16-bit operand format (fp32 accumulate); fp16 is the product default, see DESIGN.md section 2")
     ap.add_argument("--rotate", type=int, default=3)
     ap.add_argument("--eager", action="store_true", help="issue every launch from the host instead of replaying CUDA graphs")
+    ap.add_argument("--tuning", type=lambda v: int(v, 0), default=0, help="PopnetNetConfig.tuning bits (A/B of launch schedules; 0 = product defaults)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-evaluator", action="store_true", help="skip the secondary evaluator metric")
     args = ap.parse_args()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define POPNET_ABI_VERSION 2
+#define POPNET_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define POPNET_API __attribute__((visibility("default")))
@@ -282,7 +282,20 @@ typedef struct PopnetNetConfig {
                                   on trained weights) or POPNET_OPERAND_BF16: storage format of weights and
                                   inter-layer activations; accumulation is always fp32 and the six output maps
                                   are always fp32                                                          */
+  uint32_t tuning;             /* POPNET_TUNE_* bits; 0 = the product defaults.  Results are bit-identical for every value:
+                                  the bits only choose between validated launch schedules (tests/test_forward.py) */
 } PopnetNetConfig;
+
+/* Launch-schedule switches (A/B measurements).  They replace the environment variables of ABI 2:
+ * the library reads no environment. */
+#define POPNET_TUNE_NO_ZIGZAG 0x1u          /* walk the tiles of every 112 x 112 layer front to back                        */
+#define POPNET_TUNE_MC 0x2u                 /* N = 256 stage layers as cluster-of-two kernels with multicast weight stages */
+#define POPNET_TUNE_STAGE_NACC(v) (((uint32_t)(v) & 3u) << 2)   /* 2 / 3: 256- / 384-position tiles in the 28 x 28 stages (0 = 512) */
+#define POPNET_TUNE_PAIR(v) (((uint32_t)(v) & 7u) << 4)         /* 3 / 4: cta_group::2 pair kernel for the 64 -> 64 layers (0 = off) */
+#define POPNET_TUNE_PAIR_RES 0x80u          /* ... including the residual layers                                           */
+#define POPNET_TUNE_CHAIN 0x100u            /* the four 64 -> 64 layers of the 112 x 112 block as ONE spatially pipelined launch
+                                               (CTA slices linked by per-tile progress counters; tensors travel through the L2)
+                                               instead of four launches: bit-identical, measured 3 % slower per forward      */
 
 #define POPNET_OPERAND_BF16 0
 #define POPNET_OPERAND_FP16 1

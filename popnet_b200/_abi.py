@@ -9,7 +9,7 @@ MAX_LIMBS = 24
 LIFT_HEAT_WEIGHTED, LIFT_MEAN, LIFT_HEAT_MAX = 0, 1, 2
 MAX_PEAKS = 64
 MAX_PERSONS = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_PEERS = 8
 
 OK = 0
@@ -21,6 +21,20 @@ FWD_IMPL_TCGEN05 = 0
 FWD_IMPL_SIMT = 1
 OPERAND_BF16 = 0
 OPERAND_FP16 = 1
+# PopnetNetConfig.tuning bits (include/popnet_b200.h, POPNET_TUNE_*); 0 = product defaults
+TUNE_NO_ZIGZAG = 0x1
+TUNE_MC = 0x2
+TUNE_PAIR_RES = 0x80
+TUNE_CHAIN = 0x100
+
+
+def tune_stage_nacc(v):
+    return (v & 3) << 2
+
+
+def tune_pair(v):
+    return (v & 7) << 4
+
 
 vp = C.c_void_p
 
@@ -81,7 +95,7 @@ class ApArgs(C.Structure):
 
 class NetConfig(C.Structure):
     _fields_ = [("num_parts", C.c_int32), ("num_limbs", C.c_int32), ("input_dim", C.c_int32),
-                ("height", C.c_int32), ("width", C.c_int32), ("operand_dtype", C.c_int32)]
+                ("height", C.c_int32), ("width", C.c_int32), ("operand_dtype", C.c_int32), ("tuning", C.c_uint32)]
 
 
 class ConvHost(C.Structure):

@@ -71,6 +71,7 @@ struct ConvArgs {
   int reverse;                  // 1 = walk the tiles from the last to the first (zig-zag between consecutive layers: a layer then
                                 //   starts on the positions its producer wrote last, which are the ones still in the L2)
   int mc;                       // 1 = cluster-of-two kernel with multicast weight stages (conv_kernels.cu, "MC")
+  int pair, pair_res;           // tuning (PopnetNetConfig.tuning): CTA-pair kernel for the 64 -> 64 layers, 0 = off, 3 / 4 = tile size / 128
   unsigned long long* trace;    // optional [3] globaltimer stamps {first CTA in, first CTA past griddepcontrol.wait, last CTA out}
 };
 
@@ -105,6 +106,9 @@ extern std::atomic<int> g_trace_next;
 extern int g_trace_tags[1024];
 int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st);
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
+// n consecutive 64 -> 64 3x3 layers of one geometry as ONE launch (spatial pipeline through the L2, conv_kernels.cu "CHAIN")
+int launch_conv_chain(const ConvArgs* layers, int n, int nacc, unsigned int* flags, cudaStream_t st);
+size_t conv_chain_flag_words(int P, int nacc, int nlayers);
 int launch_stem(const StemArgs& a, cudaStream_t st);
 int launch_pool(const PoolArgs& a, cudaStream_t st);
 size_t conv_tc_smem_bytes(int nt, int nacc, int taps, int a_stages, int Wp, int* b_stages_out, bool b_resident = false);

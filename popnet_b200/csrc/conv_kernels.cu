@@ -348,10 +348,42 @@ constexpr int acc_stages() { return (2 * NACC * NT <= 512) ? 2 : 1; }
 //         run 128-position tiles with double-buffered accumulators (epilogue hidden) instead of 256-position tiles
 //         whose two accumulators fill the TMEM.  Both CTAs walk the same number of tiles (the last may be a dummy
 //         that only keeps the B ring in step).
-template <int NT, int NACC, int TAPS, int BST, bool BRES, bool DBG, bool MC = false>
-__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a) {
+// Layer chain (CHAIN): several layers of the same geometry run side by side inside ONE launch, each on its own slice of
+// the CTAs, as a spatial pipeline: the CTAs of layer r+1 consume the tiles of layer r a few tiles behind their
+// production, so a tensor travels from producer to consumer through the L2 instead of making a round trip through HBM
+// (the 105 MB tensors of the 112 x 112 block do not survive in the 126 MB L2 from one launch to the next).
+//   done[t]  (this layer, global memory)  raised to kEpiWarps when physical tile t is stored: every epilogue warp arrives on a
+//            shared-memory mbarrier after its stores; the publisher warp (warp 3) waits for it, then proxy fence +
+//            __threadfence + red.release.gpu -- the fence's round trip to the L2 stays out of the epilogue warps' path
+//   wait[t]  (= done[] of the producing layer)  the copy thread takes tile t only when tiles t-1, t, t+1 (its halo reaches
+//            at most one tile into either neighbour: halo <= MT) are complete: ld.acquire.gpu spin, then a proxy fence in
+//            front of the bulk copies (generic-proxy stores of another SM -> async-proxy reads).
+// Write-after-read on the ping-pong buffers is covered by the same condition: layer r+1 overwrites tile t of a buffer
+// only after the tiles t-1 .. t+1 of layer r, the only readers of those positions, have completed.
+// Spins are bounded (kChainTimeoutNs): a consumer gives up, sets *err and runs on with whatever is there -- a scheduling
+// surprise must not hang the GPU.  All CTAs of the launch are co-resident (one per SM) and start in blockIdx order, so
+// producers never wait for an SM held by their own consumers.
+struct ChainLink {
+  const unsigned int* wait;     // done[] of the producing layer, nullptr for the first layer of the chain
+  unsigned int* done;           // this layer's counters [num_tiles]
+  unsigned int* err;            // set to 1 when a wait timed out
+};
+constexpr unsigned long long kChainTimeoutNs = 200ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int NT, int NACC, int TAPS, int BST, bool BRES, bool DBG, bool MC, bool CHAIN>
+__device__ __forceinline__ void conv_tc_body(const ConvArgs& a, uint8_t* smem, const int cta, const int ncta, const ChainLink link) {
   static_assert(!(MC && BRES), "multicast applies to the B ring");
-  extern __shared__ __align__(128) uint8_t smem[];
+  static_assert(!(MC && CHAIN), "chains run the single-CTA kernel");
   constexpr int MT = NACC * 128;
   constexpr int AS = acc_stages<NT, NACC>();
   constexpr int kBSlots = BRES ? TAPS : BST;                 // B slabs held in shared memory
@@ -360,7 +392,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   constexpr uint32_t kCols = (AS * kAccCols <= 32) ? 32 : (AS * kAccCols <= 64) ? 64 : (AS * kAccCols <= 128) ? 128
                              : (AS * kAccCols <= 256) ? 256 : 512;
   static_assert(AS * kAccCols <= 512, "accumulators exceed TMEM");
-  constexpr int kNumBars = 4 + 2 * BST + 2 * AS;
+  constexpr int kNumBars = 4 + 2 * BST + 2 * AS + (CHAIN ? 2 : 0);
   const int halo = (TAPS == 9) ? a.Wp + 1 : 0;
   const int apos = MT + 2 * halo;                            // positions per staged plane
   const uint32_t a_plane_bytes = (uint32_t)apos * 16u;
@@ -378,14 +410,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   auto b_empty = [&](int s) { return bar0 + 8u * (4 + BST + s); };
   auto acc_full = [&](int s) { return bar0 + 8u * (4 + 2 * BST + s); };
   auto acc_empty = [&](int s) { return bar0 + 8u * (4 + 2 * BST + AS + s); };
+  auto st_done = [&](int s) { return bar0 + 8u * (4 + 2 * BST + 2 * AS + s); };      // CHAIN: a tile's outputs are stored (2, alternating)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (a.P + MT - 1) / MT;
   // MC: every CTA walks the same number of tile slots (the B ring of a cluster must stay in step); slots past the last
   // tile are dummies: their B stages are loaded and released, nothing else happens
-  const int tile_end = MC ? (int)((num_tiles + gridDim.x - 1) / gridDim.x * gridDim.x) : num_tiles;
+  const int tile_end = MC ? (int)((num_tiles + ncta - 1) / ncta * ncta) : num_tiles;
   const uint32_t cta_rank = MC ? cluster_ctarank() : 0u;
-  long long* probe = (DBG && a.probe) ? a.probe + (long long)blockIdx.x * 16 : nullptr;
+  long long* probe = (DBG && a.probe) ? a.probe + (long long)cta * 16 : nullptr;
   const int dbg = DBG ? a.dbg : 0;
   if (probe && threadIdx.x == 0) probe[0] = clock64();
   trace_min(a.trace, 0);
@@ -397,7 +430,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumBars; ++i) {
       uint32_t cnt = 1u;
-      if (i >= 4 + 2 * BST + AS) cnt = (uint32_t)kEpiWarps;                    // acc_empty: one arrive per epilogue warp
+      if (i >= 4 + 2 * BST + AS) cnt = (uint32_t)kEpiWarps;                    // acc_empty (and st_done): one arrive per epilogue warp
       else if (MC && i >= 4 + BST && i < 4 + 2 * BST) cnt = 2u;                // b_empty: the MMA threads of both CTAs
       mbar_init(bar0 + 8u * i, cnt);
     }
@@ -421,14 +454,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
     if (elect_one()) {
       // ---------------- producer ----------------
       int ia = 0, ib = 0;
+      bool chain_gave_up = false;
       if (BRES) {                                   // all taps of the (single) chunk, once
         mbar_expect_tx(b_full(0), (uint32_t)TAPS * kBStageBytes);
         for (int t = 0; t < TAPS; ++t)
           bulk_g2s(smem_u32(sB + (size_t)t * kBStageBytes), a.w + (long long)t * k8_total * NT * 8, kBStageBytes, b_full(0));
       }
-      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      for (int tile = cta; tile < tile_end; tile += ncta) {
         const int t0 = ((a.reverse && tile < num_tiles) ? num_tiles - 1 - tile : tile) * MT;
         const bool live = tile < num_tiles;                 // (always true without MC)
+        if (CHAIN && link.wait != nullptr) {
+          // the producing layer's tiles under this tile and its halo are complete (see ChainLink)
+          const int pt = t0 / MT;
+          unsigned long long ts = 0;
+          for (int q = (pt > 0 ? pt - 1 : 0); q <= pt + 1 && q < num_tiles && !chain_gave_up; ++q) {
+            while (ld_acquire_gpu_u32(link.wait + q) < (unsigned)kEpiWarps) {
+              const unsigned long long now = gtime();
+              if (ts == 0) ts = now;
+              if (now - ts > kChainTimeoutNs) { atomicExch(link.err, 1u); chain_gave_up = true; break; }
+              __nanosleep(64);
+            }
+          }
+          fence_proxy_async_all();
+        }
         for (int c = 0; c < chunks_all; ++c) {
           const bool ex = c >= chunks;                      // extra 1x1 chunk of the fused shortcut
           if (live) {
@@ -492,7 +540,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
         if (MC) umma_commit_mc(b_empty(stage), (uint16_t)3);
         else umma_commit(b_empty(stage));
       };
-      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      for (int tile = cta; tile < tile_end; tile += ncta) {
         if (MC && tile >= num_tiles) {
           // dummy slot: keep the shared B ring in step with the peer -- take every stage and release it again
           for (int c = 0; c < chunks_all; ++c) {
@@ -587,6 +635,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
       }
       if (probe) { probe[3] = wait_a; probe[4] = wait_b; probe[5] = clock64(); probe[10] = wait_acc; probe[9] = ti; }
     }
+  } else if (CHAIN && warp == 3) {
+    // ---------------- publisher (CHAIN): when all epilogue warps have stored a tile, make it visible GPU-wide and count it.
+    // A warp of its own: the fence waits for the stores to reach the L2, which must not sit in the epilogue's path.
+    if (elect_one()) {
+      int ti = 0;
+      for (int tile = cta; tile < num_tiles; tile += ncta, ++ti) {
+        const int t0 = (a.reverse ? num_tiles - 1 - tile : tile) * MT;
+        mbar_wait_relaxed(st_done(ti & 1), (ti >> 1) & 1);
+        fence_proxy_async_all();
+        __threadfence();
+        red_release_gpu_add(link.done + t0 / MT, (unsigned)kEpiWarps);
+      }
+    }
   } else if (warp >= kEpiWarp0) {
     // ---------------- epilogue: TMEM lane quarter q, thread = one output position; the two warps of a
     // quarter split the column chunks between them (a lone warp per scheduler is issue-latency bound) ----
@@ -598,15 +659,92 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
     const int epi_variant = (a.fmt != 0 ? 2 : 0) + (slope == 0.f ? 0 : 1);
     long long wait_full = 0, busy = 0;
     int ti = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+    for (int tile = cta; tile < num_tiles; tile += ncta, ++ti) {
       const int s = ti % AS;
       const int t0 = ((a.reverse && tile < num_tiles) ? num_tiles - 1 - tile : tile) * MT;
       long long tw = probe ? clock64() : 0;
+      // Balanced split for the 64-channel, three-accumulator tiles of the 112 x 112 layers (6 work items of 32 channels do not
+      // divide over the 4 warps of a lane quarter: two warps would do twice the work of the others and the epilogue, not
+      // the MMAs, would set the tile time): warp (q, sub) owns channels [16 sub, 16 sub + 16) of all three accumulators.
+      // The residual vectors of the tile are requested BEFORE the wait for its accumulators, so their latency runs under
+      // the MMAs.  (CHAIN: the residual was written during this launch -- it is complete once this tile's A slab has
+      // landed, which a single non-blocking probe of its a_full barrier tells; if the probe fails the loads happen after
+      // the wait as before.  The probe cannot report a slab that has not landed: see the phase argument in DESIGN.md.)
+      constexpr bool kSplit16 = (NT == 64 && NACC == 3 && BRES);
+      uint4 rs16[kSplit16 ? 6 : 1];
+      bool res_early = false;
+      if constexpr (kSplit16) {
+        if (a.res != nullptr && !head) {
+          res_early = !CHAIN || mbar_try_wait(a_full(ti % ast), (uint32_t)((ti / ast) & 1));
+          if (res_early) {
+#pragma unroll
+            for (int acc = 0; acc < 3; ++acc) {
+              const int pos = t0 + acc * 128 + q * 32 + lane;
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                const uint4* rp = reinterpret_cast<const uint4*>(a.res + (long long)(sub * 2 + g) * a.res_plane_stride + (long long)pos * 8);
+                rs16[acc * 2 + g] = pos < a.P ? (CHAIN ? __ldcg(rp) : *rp) : make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+          }
+        }
+      }
       mbar_wait_relaxed(acc_full(s), (ti / AS) & 1);
       tc_fence_after();
       long long tb = probe ? clock64() : 0;
       if (probe) wait_full += tb - tw;
-      if (head) {
+      if constexpr (kSplit16) {
+        if (!head) {
+          if (a.res != nullptr && tile + ncta < num_tiles && (lane & 7) == 0) {      // next tile's residual -> L2
+            const int tn0 = (a.reverse ? num_tiles - 1 - (tile + ncta) : tile + ncta) * MT;
+#pragma unroll
+            for (int acc = 0; acc < 3; ++acc) {
+              const int pos = tn0 + acc * 128 + q * 32 + lane;
+              if (pos < a.P) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + (long long)(sub * 2 + g) * a.res_plane_stride + (long long)pos * 8));
+              }
+            }
+          }
+#pragma unroll
+          for (int acc = 0; acc < 3; ++acc) {
+            const int pos = t0 + acc * 128 + q * 32 + lane;
+            const PosInfo pi = c8p_locate_fast(pos, a.P, a.Hs, a.Wp, mHs, mWp);
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + acc * NT + sub * 16), r);
+            const bool has_res = a.res != nullptr && pi.interior;
+            if (a.res != nullptr && !res_early && pi.in_range) {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                const uint4* rp = reinterpret_cast<const uint4*>(a.res + (long long)(sub * 2 + g) * a.res_plane_stride + (long long)pos * 8);
+                rs16[acc * 2 + g] = CHAIN ? __ldcg(rp) : *rp;
+              }
+            }
+            tmem_ld_wait();
+            if (pi.in_range && !(dbg & 2)) {
+              auto store2 = [&](auto fmt_c, auto mode_c) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                  const uint4 o = finish8_fast<decltype(fmt_c)::value, decltype(mode_c)::value>(
+                      r + g * 8, s_shift + sub * 16 + g * 8, has_res, rs16[acc * 2 + g], slope, pi.interior);
+                  *reinterpret_cast<uint4*>(a.out + (long long)(sub * 2 + g) * a.out_plane_stride + (long long)pos * 8) = o;
+                }
+              };
+              using std::integral_constant;
+              switch (epi_variant) {
+                case 0: store2(integral_constant<int, 0>{}, integral_constant<int, 0>{}); break;
+                case 1: store2(integral_constant<int, 0>{}, integral_constant<int, 1>{}); break;
+                case 2: store2(integral_constant<int, 1>{}, integral_constant<int, 0>{}); break;
+                default: store2(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
+              }
+            }
+          }
+        }
+      }
+      if (kSplit16 && !head) {
+        // (done above)
+      } else if (head) {
         // output heads (NT = 16 / 32): fp32 NCHW maps with the sigmoid scaling, optional 16-bit copy
         constexpr int kItems = NACC * (NT / 16);
 #pragma unroll 1
@@ -630,8 +768,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
         // Residual layers: this warp's residual vectors of its NEXT tile are pulled into L2 now (one 128-byte line per
         // 8 lanes), one epilogue ahead of their use -- the residual tensor was written two layers ago and has left the
         // L2; without this the epilogue of the 64-channel residual layers waits on DRAM and outlasts the MMA phase.
-        if (a.res != nullptr && tile + (int)gridDim.x < num_tiles && (lane & 7) == 0) {
-          const int tn0 = (a.reverse ? num_tiles - 1 - (tile + (int)gridDim.x) : tile + (int)gridDim.x) * MT;
+        if (a.res != nullptr && tile + ncta < num_tiles && (lane & 7) == 0) {
+          const int tn0 = (a.reverse ? num_tiles - 1 - (tile + ncta) : tile + ncta) * MT;
 #pragma unroll 1
           for (int it = sub; it < kItems; it += 4) {
             const int acc = it / (NT / 32), j = it - acc * (NT / 32);
@@ -655,8 +793,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
           const bool has_res = a.res != nullptr && pi.interior;
           if (has_res) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              rs[g] = *reinterpret_cast<const uint4*>(a.res + (long long)(plane + g) * a.res_plane_stride + (long long)pos * 8);
+            for (int g = 0; g < 4; ++g) {
+              const uint4* rp = reinterpret_cast<const uint4*>(a.res + (long long)(plane + g) * a.res_plane_stride + (long long)pos * 8);
+              rs[g] = CHAIN ? __ldcg(rp) : *rp;       // chains: written by another SM during this launch -> read at the L2
+            }
           }
           tmem_ld_wait();
           if (pi.in_range && !(dbg & 2)) {
@@ -681,6 +821,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
+      // CHAIN: this warp's part of the tile is stored (all lanes: __syncwarp above).  Tell the publisher warp -- BEFORE the
+      // accumulator is handed back, so that no warp can run two tiles (the two st_done barriers) ahead of the slowest one.
+      if (CHAIN && lane == 0) mbar_arrive(st_done(ti & 1));
       if (lane == 0) mbar_arrive(acc_empty(s));
       if (probe) busy += clock64() - tb;
     }
@@ -695,6 +838,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a
     tc_fence_after();
     tmem_dealloc(tmem_base, kCols);
   }
+}
+
+template <int NT, int NACC, int TAPS, int BST, bool BRES, bool DBG, bool MC = false>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const ConvArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  conv_tc_body<NT, NACC, TAPS, BST, BRES, DBG, MC, false>(a, smem, (int)blockIdx.x, (int)gridDim.x, ChainLink{nullptr, nullptr, nullptr});
+}
+
+// A chain of up to kMaxChain single-chunk 3x3 layers with resident weights and identical geometry (the four 64 -> 64
+// convolutions of the 112 x 112 block): CTA slice r of the grid runs layer r (see ChainLink).
+constexpr int kMaxChain = 4;
+struct ChainArgs {
+  ConvArgs base;                        // geometry, activation, operand format: common to all layers
+  const h16* in[kMaxChain];
+  const h16* w[kMaxChain];
+  const float* shift[kMaxChain];
+  h16* out[kMaxChain];
+  const h16* res[kMaxChain];            // nullptr = no residual
+  unsigned long long* trace[kMaxChain];
+  unsigned int* flags;                  // [1 + nlayers * num_tiles]: word 0 = error, then done[] per layer; zeroed before the launch
+  int nlayers;
+};
+
+template <int NT, int NACC>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_chain_kernel(const ChainArgs c) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int per = (int)gridDim.x / c.nlayers;
+  const int role = (int)blockIdx.x / per;               // host: gridDim.x is a multiple of nlayers
+  ConvArgs a = c.base;
+#pragma unroll
+  for (int i = 0; i < kMaxChain; ++i)
+    if (role == i) { a.in = c.in[i]; a.w = c.w[i]; a.shift = c.shift[i]; a.out = c.out[i]; a.res = c.res[i]; a.trace = c.trace[i]; }
+  const int num_tiles = (a.P + NACC * 128 - 1) / (NACC * 128);
+  ChainLink link;
+  link.err = c.flags;
+  link.done = c.flags + 1 + (size_t)role * num_tiles;
+  link.wait = role > 0 ? c.flags + 1 + (size_t)(role - 1) * num_tiles : nullptr;
+  conv_tc_body<NT, NACC, 9, 2, true, false, false, true>(a, smem, (int)blockIdx.x - role * per, per, link);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1306,17 +1487,15 @@ int launch_pair64(const ConvArgs& a, cudaStream_t st) {
 }  // namespace
 
 int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st) {
-  // CTA-pair kernel (cta_group::2) for the large single-chunk 64 -> 64 3x3 layers: opt-in with POPNET_PAIR=4 (512-position
-  // tiles) or 3 (384).  Measured, same box, A/B/A/B: the two non-residual layers go from 57 to 51 us and the forward ALONE
-  // from 0.994 to 0.984 ms -- but inside the pipelined step, where the decode of the previous batch shares the SMs, the
-  // step gets 1.6 % SLOWER (1.035 vs 1.019 ms: a cluster needs both SMs of a pair free at once), so it is off by default.
-  // The residual layers are HBM-bound (210 MB read + 105 MB written in 66 us -- the 105 MB tensors do not survive in the
-  // L2 from one layer to the next) and the pair's coupled accumulator release makes them 4 us slower
-  // (POPNET_PAIR_RES=1 includes them).
-  const char* pe = getenv("POPNET_PAIR");
-  const int pair = pe ? atoi(pe) : 0;
-  const char* pr = getenv("POPNET_PAIR_RES");
-  const bool pair_res = pr && atoi(pr) != 0;
+  // CTA-pair kernel (cta_group::2) for the large single-chunk 64 -> 64 3x3 layers: opt-in with PopnetNetConfig.tuning
+  // POPNET_TUNE_PAIR(4) (512-position tiles) or (3) (384).  Measured, same box, A/B/A/B: the two non-residual layers go from
+  // 57 to 51 us and the forward ALONE from 0.994 to 0.984 ms -- but inside the pipelined step, where the decode of the
+  // previous batch shares the SMs, the step gets 1.6 % SLOWER (1.035 vs 1.019 ms: a cluster needs both SMs of a pair free at
+  // once), so it is off by default.  The residual layers are HBM-bound (210 MB read + 105 MB written in 66 us -- the 105 MB
+  // tensors do not survive in the L2 from one layer to the next) and the pair's coupled accumulator release makes them
+  // 4 us slower (POPNET_TUNE_PAIR_RES includes them).
+  const int pair = a.pair;
+  const bool pair_res = a.pair_res != 0;
   if (pair && !a.mc && a.nt == 64 && a.taps == 9 && a.chunks == 1 && a.chunks2 == 0 && a.head_out == nullptr &&
       a.cout_pad == 64 && a.out != nullptr && a.probe == nullptr && a.dbg == 0 && (pair_res || a.res == nullptr) &&
       a.P >= 148 * 512) {
@@ -1357,6 +1536,51 @@ int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st) {
   POPNET_TC_CASE(32, 4, 1, false)
   POPNET_TC_CASE(16, 4, 9, false)
 #undef POPNET_TC_CASE
+  return POPNET_ERR_UNSUPPORTED;
+}
+
+size_t conv_chain_flag_words(int P, int nacc, int nlayers) {
+  const int tiles = (P + nacc * 128 - 1) / (nacc * 128);
+  return 1 + (size_t)nlayers * tiles;
+}
+
+// One launch for `n` consecutive single-chunk 64 -> 64 3x3 layers of the same geometry (ChainArgs / ChainLink above).
+// `flags`: conv_chain_flag_words() words of device memory, zeroed in stream order before this launch.
+int launch_conv_chain(const ConvArgs* layers, int n, int nacc, unsigned int* flags, cudaStream_t st) {
+  if (n < 2 || n > kMaxChain || !flags) return POPNET_ERR_INVALID_ARG;
+  const ConvArgs& a0 = layers[0];
+  for (int i = 0; i < n; ++i) {
+    const ConvArgs& a = layers[i];
+    if (a.nt != 64 || a.cout_pad != 64 || a.taps != 9 || a.chunks != 1 || a.chunks2 != 0 || a.head_out || !a.out || a.mc ||
+        a.probe || a.dbg || a.P != a0.P || a.Hs != a0.Hs || a.Wp != a0.Wp || a.act != a0.act || a.fmt != a0.fmt ||
+        a.in_plane_stride != a0.in_plane_stride || a.out_plane_stride != a0.out_plane_stride ||
+        (a.res && a.res_plane_stride != a0.out_plane_stride) || a.reverse != a0.reverse)
+      return POPNET_ERR_UNSUPPORTED;
+  }
+  if (a0.Wp + 1 > nacc * 128) return POPNET_ERR_UNSUPPORTED;          // the halo must stay inside the neighbouring tile
+  const size_t smem = conv_tc_smem_bytes(64, nacc, 9, 2, a0.Wp, nullptr, true);
+  if (smem > kSmemLimit) return POPNET_ERR_UNSUPPORTED;
+  ChainArgs c{};
+  c.base = a0;
+  c.base.a_stages = 2;
+  c.base.res_plane_stride = a0.out_plane_stride;
+  for (int i = 0; i < n; ++i) {
+    c.in[i] = layers[i].in; c.w[i] = layers[i].w; c.shift[i] = layers[i].shift; c.out[i] = layers[i].out; c.res[i] = layers[i].res;
+    c.trace[i] = next_trace_slot(64 * 1000 + nacc * 100 + 90 + 1 + i);
+  }
+  c.flags = flags;
+  c.nlayers = n;
+  const int grid = kNumSMs / n * n;                                 // equal CTA slices (4 x 37 on 148 SMs)
+  auto launch = [&](auto kern) -> int {
+    POPNET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    POPNET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    PdlConfig pc(dim3(grid), dim3(kTcThreads), smem, st);
+    POPNET_CUDA_TRY(cudaLaunchKernelEx(&pc.cfg, kern, c));
+    POPNET_AFTER_LAUNCH();
+    return POPNET_OK;
+  };
+  if (nacc == 3) return launch(conv_chain_kernel<64, 3>);
+  if (nacc == 2) return launch(conv_chain_kernel<64, 2>);
   return POPNET_ERR_UNSUPPORTED;
 }
 

@@ -56,6 +56,7 @@ struct Plan {
   Buf bufs[kNumBufs];
   std::vector<Layer> layers;
   size_t blob_bytes = 0, ws_bytes = 0;
+  size_t flags_off = 0, flags_bytes = 0;   // progress counters of the layer chain (bytes from the workspace start)
   int K, L, pl, ph, pd;
 };
 
@@ -86,6 +87,9 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
     off = align_up(off, 128);
   }
   p.ws_bytes = off * sizeof(h16);
+  p.flags_off = align_up(p.ws_bytes, 256);
+  p.flags_bytes = align_up(conv_chain_flag_words(p.bufs[A112].P, 3, 4) * sizeof(unsigned int), 256);
+  p.ws_bytes = p.flags_off + p.flags_bytes;
 
   auto add = [&](int cin, int cout, int k, int nt, int nacc, int act, int in_buf, int in_plane0, int out_buf,
                  int out_plane0, int res_buf, int head, int stage, int remap) {
@@ -116,15 +120,14 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   // branches already fill each other's idle SMs.
   const bool kFuseFirst = p.bufs[DA].off == p.bufs[SA].off + (size_t)(p.bufs[SA].C / 8) * p.bufs[SA].plane_stride &&
                           p.bufs[DA].plane_stride == p.bufs[SA].plane_stride;
-  // POPNET_MC=1: the N = 256 stage layers as cluster-of-two multicast kernels with 128-position tiles and double-buffered
+  // POPNET_TUNE_MC: the N = 256 stage layers as cluster-of-two multicast kernels with 128-position tiles and double-buffered
   // accumulators.  Validated (tests/test_forward.py) and 20-25 % faster per layer (#11: 56.6 -> 43.5 us in the timeline), but
   // the forward as a whole does not gain (0.980 vs 0.971 ms, same box): the stage is then bounded by the serial heat-map chain
   // and the power cap (the heat-map chain's 128 -> 128 convs as multicast kernels with 256-position tiles: 1.01 ms).
   // Off by default; kept as the basis for cta_group::2 pairs.
-  int kMc = 0;
-  if (const char* e = getenv("POPNET_MC")) kMc = atoi(e);
+  const int kMc = (cfg.tuning & POPNET_TUNE_MC) ? 1 : 0;
   int kStageNacc = 4;
-  if (const char* e = getenv("POPNET_STAGE_NACC")) { const int v = atoi(e); if (v >= 2 && v <= 4) kStageNacc = v; }
+  { const int v = (int)((cfg.tuning >> 2) & 3u); if (v >= 2) kStageNacc = v; }
   for (int s = 1; s <= 2; ++s) {
     const int in0 = (s == 1) ? (p.pl + p.ph + p.pd) / 8 : 0;     // stage 1 reads only the feature planes
     const int cin = (s == 1) ? 128 : 128 + L2 + K1 + L1;
@@ -329,13 +332,13 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
 
   // Zig-zag tile order through the 112 x 112 block (stem forward, layer 1 backward, layer 2 forward, ...): a layer starts on
   // the positions its producer wrote last, the only part of the 105 MB tensor that is still in the 126 MB L2.  Measured in the
-  // bench, same box, A/B/A/B: 62.39 k vs 61.77 k frames/s; each 64 -> 64 layer 3 us shorter.  POPNET_ZIGZAG=0 disables.
-  const char* zz = getenv("POPNET_ZIGZAG");
-  const int zigzag = zz ? atoi(zz) : 1;
-  auto run_conv = [&](int li) -> int {
+  // bench, same box, A/B/A/B: 62.39 k vs 61.77 k frames/s; each 64 -> 64 layer 3 us shorter.  POPNET_TUNE_NO_ZIGZAG disables.
+  const int zigzag = (cfg->tuning & POPNET_TUNE_NO_ZIGZAG) ? 0 : 1;
+  const bool chain = (cfg->tuning & POPNET_TUNE_CHAIN) != 0 && impl == POPNET_FWD_IMPL_TCGEN05;
+  auto make_conv_args = [&](int li, ConvArgs& a) {
     const Layer& l = p.layers[li];
     const Buf& bi = p.bufs[l.in_buf];
-    ConvArgs a{};
+    a = ConvArgs{};
     a.in = buf_ptr(workspace, bi, l.in_plane0);
     a.in_plane_stride = bi.plane_stride;
     a.w = reinterpret_cast<const h16*>(blob + l.w_off);
@@ -364,7 +367,14 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     a.act = l.act; a.cout = l.nfuse_layer >= 0 ? l.cout_pad : l.cout; a.cout_pad = l.cout_pad; a.nt = l.nt; a.taps = l.k * l.k;
     a.fmt = cfg->operand_dtype;
     a.mc = l.mc;
-    a.reverse = (zigzag && li >= 1 && li <= 4) ? (li & 1) : 0;
+    a.reverse = (zigzag && li >= 1 && li <= 4) ? (chain ? 1 : (li & 1)) : 0;
+    a.pair = (int)((cfg->tuning >> 4) & 7u);
+    a.pair_res = (cfg->tuning & POPNET_TUNE_PAIR_RES) ? 1 : 0;
+  };
+  auto run_conv = [&](int li) -> int {
+    const Layer& l = p.layers[li];
+    ConvArgs a;
+    make_conv_args(li, a);
     if (impl == POPNET_FWD_IMPL_SIMT) return launch_conv_simt(a, st);
     // shrink the A staging if the tile does not fit next to two B stages
     int bst = 0;
@@ -379,10 +389,12 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     a.in = buf_ptr(workspace, bi, 0); a.in_plane_stride = bi.plane_stride;
     a.out = buf_ptr(workspace, p.bufs[out_buf], out_plane0); a.out_plane_stride = p.bufs[out_buf].plane_stride;
     a.planes = bi.C / 8; a.N = batch; a.H = bi.H; a.W = bi.W; a.fmt = cfg->operand_dtype;
-    a.reverse = (zigzag && in_buf == A112) ? 1 : 0;
+    a.reverse = (zigzag && in_buf == A112 && !chain) ? 1 : 0;      // (after the chain, which ends on the FIRST tiles: forward)
     return launch_pool(a, st);
   };
 #define POPNET_TRY(expr) do { int _rc = (expr); if (_rc != POPNET_OK) return _rc; } while (0)
+  if (chain)          // (in front of the stem: nothing sits between two kernels, so programmatic dependent launch stays intact)
+    POPNET_CUDA_TRY(cudaMemsetAsync(static_cast<unsigned char*>(workspace) + p.flags_off, 0, p.flags_bytes, st));
   {
     const Layer& l = p.layers[0];
     StemArgs a{};
@@ -391,7 +403,21 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     a.N = batch; a.H = cfg->height; a.W = cfg->width; a.fmt = cfg->operand_dtype;
     POPNET_TRY(launch_stem(a, st));
   }
-  for (int li = 1; li <= 4; ++li) POPNET_TRY(run_conv(li));
+  bool chained = false;
+  if (chain) {
+    // layers 1-4 (the four 64 -> 64 convolutions at 112 x 112) as ONE launch: a spatial pipeline of four CTA slices whose
+    // tensors travel through the L2 (conv_kernels.cu, "CHAIN").  All four walk the tiles from the last to the first: the
+    // stem wrote the last tiles last.  Falls back to one launch per layer for geometries the chain does not take
+    // (a row pitch above the tile size).
+    ConvArgs ca[4];
+    for (int li = 1; li <= 4; ++li) make_conv_args(li, ca[li - 1]);
+    unsigned int* flags = reinterpret_cast<unsigned int*>(static_cast<unsigned char*>(workspace) + p.flags_off);
+    const int rc = launch_conv_chain(ca, 4, p.layers[1].nacc, flags, st);
+    if (rc == POPNET_OK) chained = true;
+    else if (rc != POPNET_ERR_UNSUPPORTED) return rc;
+  }
+  if (!chained)
+    for (int li = 1; li <= 4; ++li) POPNET_TRY(run_conv(li));
   POPNET_TRY(run_pool(A112, D56, 0));
   POPNET_TRY(run_conv(5));
   POPNET_TRY(run_conv(6));                 // includes the projection shortcut (layer 7) as an extra K chunk

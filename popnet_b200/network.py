@@ -99,6 +99,9 @@ class rtpose_light3d(nn.Module):
         # and bytes).  fp16 is the default: on a trained checkpoint it holds the 1e-2 bound of the north star with margin
         # (4.5e-3 measured on the fixture checkpoint) where bf16's 8-bit mantissa does not (3.6e-2) -- DESIGN.md section 2.
         self.operand_dtype = _abi.OPERAND_FP16     # or _abi.OPERAND_BF16; repacked automatically on the next forward
+        #: launch-schedule switches (_abi.TUNE_*; include/popnet_b200.h POPNET_TUNE_*): 0 = product defaults.  Every value
+        #: gives bit-identical maps; PoseEstimator.refresh() after a change (captured graphs hold the old schedule).
+        self.tuning = 0
         self._packed = None        # (device blob, config key)
         self._workspace = None
         for p in self.parameters():
@@ -149,7 +152,7 @@ class rtpose_light3d(nn.Module):
 
     def _net_config(self, h, w):
         return _abi.NetConfig(num_parts=self.num_parts, num_limbs=self.num_limbs, input_dim=self.input_dim,
-                              height=h, width=w, operand_dtype=int(self.operand_dtype))
+                              height=h, width=w, operand_dtype=int(self.operand_dtype), tuning=int(self.tuning))
 
     def pack(self, h=224, w=224):
         """Fold + pack the current parameters into the device blob (idempotent until load_state_dict)."""

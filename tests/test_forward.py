@@ -107,52 +107,60 @@ def test_cuda_forward_batch_invariance(cuda_backend):
     assert torch.equal(p9[3:6], p3) and torch.equal(h9[3:6], h3) and torch.equal(d9[3:6], d3)
 
 
-@pytest.mark.gpu
-def test_cuda_forward_multicast_variant_identical(cuda_backend, monkeypatch):
-    """POPNET_MC=1 runs the N = 256 stage layers as cluster-of-two kernels whose weight stages are multicast (128-position
-    tiles, dummy tile slots, cross-CTA stage release).  Same K order per output, so the maps must be bit-identical to the
-    default path -- at a batch with dummy slots (odd tile counts) and at the bench batch."""
+def _maps_for_tunings(tunings, batches=((3, 5), (64, 6))):
+    """The six output maps at every (batch, seed) for every schedule in `tunings` (name -> PopnetNetConfig.tuning bits)."""
     from popnet_b200 import synth
     sd = network.synth_state_dict(seed=11, style="trained_like")
     outs = {}
-    for mc in ("0", "1"):
-        monkeypatch.setenv("POPNET_MC", mc)
+    for tag, bits in tunings.items():
         m = network.rtpose_light3d(15, 14, 2, input_dim=1)
         m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        m.tuning = bits
         res = []
-        for B, seed in ((3, 5), (64, 6)):
+        for B, seed in batches:
             x = torch.from_numpy(synth.depth_frames(B, seed=seed)).cuda()
             (p, h, d), saved = m(x)
             torch.cuda.synchronize()
             res += [p.clone(), h.clone(), d.clone()] + [t.clone() for t in saved[:3]]
-        outs[mc] = res
+        outs[tag] = res
+    return outs
+
+
+@pytest.mark.gpu
+def test_cuda_forward_layer_chain_identical(cuda_backend):
+    """POPNET_TUNE_CHAIN runs the four 64 -> 64 layers of the 112 x 112 block as ONE spatially pipelined launch (CTA
+    slices linked by per-tile progress counters, conv_kernels.cu "CHAIN").  Same kernel body and K order per output as the
+    default one-launch-per-layer schedule (with and without the zig-zag order): bit-identical maps, at a batch with few
+    tiles per CTA slice (3), at the bench batch (64), and repeated (the counters are re-zeroed per forward)."""
+    from popnet_b200 import _abi
+    outs = _maps_for_tunings({"chain": _abi.TUNE_CHAIN, "chain-again": _abi.TUNE_CHAIN, "layers": 0,
+                              "layers-nozz": _abi.TUNE_NO_ZIGZAG, "chain-nozz": _abi.TUNE_CHAIN | _abi.TUNE_NO_ZIGZAG},
+                             batches=((3, 5), (64, 6), (1, 7), (64, 8)))
+    for tag in ("chain-again", "layers", "layers-nozz", "chain-nozz"):
+        for a, b in zip(outs["chain"], outs[tag]):
+            assert torch.equal(a, b), tag
+
+
+@pytest.mark.gpu
+def test_cuda_forward_multicast_variant_identical(cuda_backend):
+    """POPNET_TUNE_MC runs the N = 256 stage layers as cluster-of-two kernels whose weight stages are multicast (128-position
+    tiles, dummy tile slots, cross-CTA stage release).  Same K order per output, so the maps must be bit-identical to the
+    default path -- at a batch with dummy slots (odd tile counts) and at the bench batch."""
+    from popnet_b200 import _abi
+    outs = _maps_for_tunings({"0": 0, "1": _abi.TUNE_MC})
     for a, b in zip(outs["0"], outs["1"]):
         assert torch.equal(a, b)
 
 
 @pytest.mark.gpu
-def test_cuda_forward_pair_kernel_identical(cuda_backend, monkeypatch):
-    """The cta_group::2 pair kernel (opt-in, POPNET_PAIR=4|3) for the 64 -> 64 layers at 112 x 112 against the single-CTA
+def test_cuda_forward_pair_kernel_identical(cuda_backend):
+    """The cta_group::2 pair kernel (opt-in, POPNET_TUNE_PAIR(4|3)) for the 64 -> 64 layers at 112 x 112 against the single-CTA
     kernel, without and with the residual layers, 512- and 384-position tiles: same K order per output -> bit-identical.
     Batch 3 gives odd tile counts (dummy tile slots), batch 64 is the bench shape."""
-    from popnet_b200 import synth
-    sd = network.synth_state_dict(seed=11, style="trained_like")
-    outs = {}
-    for tag, env in (("off", {"POPNET_PAIR": "0"}), ("default", {"POPNET_PAIR": "4"}), ("res3", {"POPNET_PAIR": "3", "POPNET_PAIR_RES": "1"}),
-                     ("res4", {"POPNET_PAIR": "4", "POPNET_PAIR_RES": "1"})):
-        monkeypatch.delenv("POPNET_PAIR", raising=False)
-        monkeypatch.delenv("POPNET_PAIR_RES", raising=False)
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        m = network.rtpose_light3d(15, 14, 2, input_dim=1)
-        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
-        res = []
-        for B, seed in ((3, 5), (64, 6)):
-            x = torch.from_numpy(synth.depth_frames(B, seed=seed)).cuda()
-            (p, h, d), saved = m(x)
-            torch.cuda.synchronize()
-            res += [p.clone(), h.clone(), d.clone()]
-        outs[tag] = res
+    from popnet_b200 import _abi
+    nc = 0
+    outs = _maps_for_tunings({"off": nc, "default": nc | _abi.tune_pair(4), "res3": nc | _abi.tune_pair(3) | _abi.TUNE_PAIR_RES,
+                              "res4": nc | _abi.tune_pair(4) | _abi.TUNE_PAIR_RES})
     for tag in ("default", "res3", "res4"):
         for a, b in zip(outs["off"], outs[tag]):
             assert torch.equal(a, b), tag

@@ -14,6 +14,7 @@ from popnet_b200 import network, synth, _abi, _lib  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--tuning", type=lambda v: int(v, 0), default=0, help="PopnetNetConfig.tuning bits (_abi.TUNE_*)")
 a = ap.parse_args()
 lib = _lib.get()
 lib.popnet_debug_trace.restype = C.c_int
@@ -22,6 +23,7 @@ lib.popnet_debug_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
 m = network.rtpose_light3d(15, 14, 2, input_dim=1)
 sd = network.synth_state_dict(seed=11, style="trained_like")
 m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+m.tuning = a.tuning
 x = torch.from_numpy(synth.depth_frames(8, seed=1)).cuda().repeat(a.batch // 8 + 1, 1, 1, 1)[:a.batch].contiguous()
 for _ in range(5):
     m(x)
@@ -44,6 +46,6 @@ print("%3s %-14s %9s %9s %9s %8s %8s" % ("#", "kernel", "start", "past-wait", "e
 order = np.argsort(r[:, 0])
 for i in order:
     t = tags[i]
-    name = "stem" if t == 1 else "pool" if t == 2 else "conv<%d,%d,%d>" % (t // 1000, t // 100 % 10, t // 10 % 10)
+    name = "stem" if t == 1 else "pool" if t == 2 else "conv<%d,%d,%d>%s" % (t // 1000, t // 100 % 10, t // 10 % 10, ("/chain%d" % (t % 10)) if t % 10 in (1, 2, 3, 4) and t // 10 % 10 == 9 and t // 1000 == 64 else "")
     print("%3d %-14s %9.1f %9.1f %9.1f %8.1f %8.1f" % (i, name, (r[i, 0] - t0) / 1e3, (r[i, 1] - t0) / 1e3, (r[i, 2] - t0) / 1e3,
                                                    (r[i, 2] - r[i, 1]) / 1e3, (r[i, 1] - r[i, 0]) / 1e3))

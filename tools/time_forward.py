@@ -16,6 +16,7 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--impl", default="tc")
 ap.add_argument("--streams", type=int, default=1)
+ap.add_argument("--tuning", type=lambda v: int(v, 0), default=0, help="PopnetNetConfig.tuning bits (_abi.TUNE_*)")
 a = ap.parse_args()
 
 m = network.rtpose_light3d(15, 14, 2, input_dim=1)
@@ -23,6 +24,7 @@ sd = network.synth_state_dict(seed=11, style="trained_like")
 m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
 m.operand_dtype = _abi.OPERAND_BF16 if a.dtype == "bf16" else _abi.OPERAND_FP16
 m.impl = _abi.FWD_IMPL_TCGEN05 if a.impl == "tc" else _abi.FWD_IMPL_SIMT
+m.tuning = a.tuning
 x = torch.from_numpy(synth.depth_frames(8, seed=1)).cuda().repeat(a.batch // 8 + 1, 1, 1, 1)[:a.batch].contiguous()
 for _ in range(3):
     m(x)
@@ -35,6 +37,7 @@ for i in range(a.iters):
 torch.cuda.synchronize()
 ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.iters)]
 t = float(np.median(ts))
+print("tuning 0x%x" % a.tuning, end=" ")
 print("forward batch %d: median %.3f ms  (%.0f frames/s, %.1f TFLOP/s)  all: %s" %
       (a.batch, t, a.batch / t * 1e3, a.batch * 13.343404032 / t, ["%.3f" % v for v in ts]))
 

@@ -324,6 +324,11 @@ __device__ __forceinline__ void trace_min(unsigned long long* tr, int slot) {
 __device__ __forceinline__ void trace_max(unsigned long long* tr, int slot) {
   if (tr && threadIdx.x == 0) atomicMax(tr + slot, gtime());
 }
+// slot 3: sum over the CTAs of (exit - entry) = the SM time the launch occupied, whatever queued in front of its CTAs
+__device__ __forceinline__ unsigned long long trace_enter(unsigned long long* tr) { return (tr && threadIdx.x == 0) ? gtime() : 0ull; }
+__device__ __forceinline__ void trace_exit(unsigned long long* tr, unsigned long long t_in) {
+  if (tr && threadIdx.x == 0) atomicAdd(tr + 3, gtime() - t_in);
+}
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -422,6 +427,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a, uint8_t* smem, c
   const int dbg = DBG ? a.dbg : 0;
   if (probe && threadIdx.x == 0) probe[0] = clock64();
   trace_min(a.trace, 0);
+  const unsigned long long t_enter = trace_enter(a.trace);
   const int chunks = a.chunks;
   const int chunks_all = chunks + (BRES ? 0 : a.chunks2);
   const int k8_total = chunks * 8;
@@ -834,6 +840,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a, uint8_t* smem, c
   if (MC) cluster_sync_all();        // the peer may still multicast into this CTA's shared memory / barriers until it is done too
   if (probe && threadIdx.x == 0) probe[8] = clock64();
   trace_max(a.trace, 2);
+  trace_exit(a.trace, t_enter);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kCols);
@@ -1007,6 +1014,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_pair64_kernel(const ConvAr
   const int num_tiles = (a.P + MT - 1) / MT;
   const int tile_end = (int)((num_tiles + gridDim.x - 1) / gridDim.x * gridDim.x);      // same slot count in every CTA
   trace_min(a.trace, 0);
+  const unsigned long long t_enter = trace_enter(a.trace);
   pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
@@ -1179,6 +1187,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_pair64_kernel(const ConvAr
   __syncthreads();
   cluster_sync_all();
   trace_max(a.trace, 2);
+  trace_exit(a.trace, t_enter);
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols) : "memory");
@@ -1188,19 +1197,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_pair64_kernel(const ConvAr
 // ------------------------------------------------------------------------------------------------
 // stem: model0.conv1 (7x7, stride 2, pad 3, one input channel) + folded BN + ReLU -> C8P (64 channels).
 // Also on the tensor cores: each CTA im2col's 128 output positions into the K-major core-matrix layout
-// (K = 8 input rows x 8 input columns = 64, of which the 7x7 kernel uses 49), issues four M128 x N64 x K16 MMAs against the resident weights and runs the
-// same TMEM epilogue; the input image is read through L1 (every pixel feeds ~12 taps).
+// (K = 8 input rows x 8 input columns = 64, of which the 7x7 kernel uses 49), issues M128 x N64 x K16 MMAs against the
+// resident weights and runs the same TMEM epilogue; the input image is read through L1 (every pixel feeds ~12 taps).
+// INPUT PRECISION: the depth frame is the one fp32 tensor of the forward, and rounding it to 16 bits was measured to be
+// 85 % of the forward's whole output error (tools/e2e_sensitivity.py --skip input: max-abs 3.6e-3 -> 5.4e-4 with fp16
+// operands; the frame is large flat areas whose features are small differences of O(1) values, which an 11-bit mantissa
+// erases).  The im2col therefore splits every pixel into hi = rn16(x) and lo = rn16(x - hi) and the tile is multiplied
+// twice against the same weights into the same accumulator (K = 64 hi + 64 lo): 22 (fp16) / 16 (bf16) mantissa bits of the
+// input reach the fp32 accumulator, for four more N = 64 MMAs per 128 positions (0.6 % of the forward's FLOPs).
 // ------------------------------------------------------------------------------------------------
 constexpr int kStemThreads = 128;
 #ifndef POPNET_STEM_BATCHES
 #define POPNET_STEM_BATCHES 2
 #endif
-constexpr int kStemBatches = POPNET_STEM_BATCHES;   // 2: 16 loads in flight per thread, 64 registers, 8 CTAs per SM (30.7 us);
-                                                    // 1: 32 loads, 72 registers, 6 CTAs per SM (32.5 us, same box)
-constexpr int kStemCtasPerSm = kStemBatches == 1 ? 6 : 8;
+constexpr int kStemBatches = POPNET_STEM_BATCHES;   // rows loaded per batch = 8 / kStemBatches: 2 -> 16 float2 loads in flight per thread
+constexpr int kStemCtasPerSm = 5;                   // 40.3 KB of shared memory per CTA (hi + lo tiles, weights)
 
 __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(const StemArgs a) {
-  __shared__ __align__(128) h16 sA[8 * 128 * 8];          // [k8][row][8]
+  __shared__ __align__(128) h16 sA[2 * 8 * 128 * 8];      // [hi | lo][k8][row][8]
   __shared__ __align__(128) h16 sB[8 * 64 * 8];           // [k8][cout][8]
   __shared__ __align__(16) float s_shift[64];
   __shared__ __align__(8) uint64_t s_bar;
@@ -1229,6 +1243,7 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
   uint32_t phase = 0;
   const uint32_t mHs = div_magic(Hs), mWp = div_magic(Wp);
   trace_min(a.trace, 0);
+  const unsigned long long t_enter = trace_enter(a.trace);
   pdl_launch_dependents();
   pdl_wait();
   trace_min(a.trace, 1);
@@ -1263,10 +1278,17 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
             v[r4][j] = (rok && cok[j]) ? __ldg(reinterpret_cast<const float2*>(row + 2 * j)) : make_float2(0.f, 0.f);
         }
 #pragma unroll
-        for (int r4 = 0; r4 < RB; ++r4)
-          reinterpret_cast<uint4*>(sA)[(half * RB + r4) * 128 + tid] =
-              make_uint4(pack2(v[r4][0].x, v[r4][0].y, a.fmt), pack2(v[r4][1].x, v[r4][1].y, a.fmt),
-                         pack2(v[r4][2].x, v[r4][2].y, a.fmt), pack2(v[r4][3].x, v[r4][3].y, a.fmt));
+        for (int r4 = 0; r4 < RB; ++r4) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            hi[j] = pack2(v[r4][j].x, v[r4][j].y, a.fmt);
+            const float2 h = unpack2(hi[j], a.fmt);                     // what the 16-bit value holds: the rest goes into lo
+            lo[j] = pack2(v[r4][j].x - h.x, v[r4][j].y - h.y, a.fmt);
+          }
+          reinterpret_cast<uint4*>(sA)[(half * RB + r4) * 128 + tid] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          reinterpret_cast<uint4*>(sA)[(8 + half * RB + r4) * 128 + tid] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
       }
     }
     // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -1277,8 +1299,8 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
       tc_fence_after();
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_bf16(tmem_base, umma_desc(a0 + (2 * kk) * 128 * 16, 128 * 16, 128), umma_desc(b0 + (2 * kk) * 64 * 16, 64 * 16, 128),
+      for (int kk = 0; kk < 8; ++kk)       // K steps 0-3: hi tile, 4-7: lo tile, both against the same weights
+        umma_bf16(tmem_base, umma_desc(a0 + (2 * kk) * 128 * 16, 128 * 16, 128), umma_desc(b0 + (2 * (kk & 3)) * 64 * 16, 64 * 16, 128),
                   idesc, kk != 0 ? 1u : 0u);
       umma_commit(bar);
     }
@@ -1307,6 +1329,7 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) stem_kernel(cons
   }
   __syncthreads();
   trace_max(a.trace, 2);
+  trace_exit(a.trace, t_enter);
   if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
 
@@ -1509,7 +1532,10 @@ int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st) {
   }
   int bst = 0;
   // weights resident in shared memory whenever the layer is a single chunk and everything fits
-  const bool bres = a.chunks == 1 && a.taps == 9 && a.nt == 64 &&
+  // (64 output channels: 72 KB of weights; 128 output channels: 144 KB, next to two 128-position A stages -- the 64 -> 128
+  //  layer at 56 x 56, which with streamed weights and 256-position tiles pulled 40 B per cycle and SM from the L2: the
+  //  chip-wide L2 limit, 28 us instead of the 13 us its MMAs take)
+  const bool bres = a.chunks == 1 && a.chunks2 == 0 && a.taps == 9 && (a.nt == 64 || (a.nt == 128 && nacc == 1)) &&
                     conv_tc_smem_bytes(a.nt, nacc, a.taps, a.a_stages, a.Wp, nullptr, true) <= kSmemLimit;
   const size_t smem = conv_tc_smem_bytes(a.nt, nacc, a.taps, a.a_stages, a.Wp, &bst, bres);
   if (smem > kSmemLimit) return POPNET_ERR_UNSUPPORTED;
@@ -1519,6 +1545,7 @@ int launch_conv_tc(const ConvArgs& a, int nacc, cudaStream_t st) {
   POPNET_TC_CASE(64, 2, 9, true)
   POPNET_TC_CASE(64, 3, 9, true)
   POPNET_TC_CASE(64, 4, 9, true)
+  POPNET_TC_CASE(128, 1, 9, true)
   POPNET_TC_CASE(64, 2, 9, false)
   POPNET_TC_CASE(64, 4, 9, false)
   POPNET_TC_CASE(128, 2, 9, false)
@@ -1594,7 +1621,7 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
 int launch_stem(const StemArgs& a, cudaStream_t st) {
   const int P = (int)c8p_positions(a.N, a.H / 2, a.W / 2);
   const int tiles = (P + 127) / 128;
-  const int cps = kStemCtasPerSm;       // CTAs per SM (TMEM: 8 x 64 columns; registers: 8 x 128 x 64)
+  const int cps = kStemCtasPerSm;       // CTAs per SM (shared memory: 5 x 40.3 KB)
   // (a function attribute is per device context: set on every call, it is a host-side table write)
   POPNET_CUDA_TRY(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int grid = tiles < 148 * cps ? tiles : 148 * cps;      // persistent: `cps` CTAs per SM walk the tiles

@@ -109,7 +109,7 @@ bool make_plan(const PopnetNetConfig& cfg, int batch, Plan& p) {
   add(64, 64, 3, 64, 3, kActRelu, B112, 0, C112, 0, A112, 0, 0, 0);         // 2 layer1.0.conv2 (+x)
   add(64, 64, 3, 64, 3, kActRelu, C112, 0, B112, 0, -1, 0, 0, 0);           // 3 layer1.1.conv1
   add(64, 64, 3, 64, 3, kActRelu, B112, 0, A112, 0, C112, 0, 0, 0);         // 4 layer1.1.conv2 (+x)
-  add(64, 128, 3, 128, 2, kActRelu, D56, 0, E56, 0, -1, 0, 0, 0);           // 5 layer2.0.conv1
+  add(64, 128, 3, 128, 1, kActRelu, D56, 0, E56, 0, -1, 0, 0, 0);           // 5 layer2.0.conv1 (128-position tiles, weights resident)
   add(128, 128, 3, 128, 4, kActRelu, E56, 0, G56, 0, -1, 0, 0, 0);         // 6 layer2.0.conv2, projection shortcut fused:
   p.layers.back().fuse_layer = 7; p.layers.back().in2_buf = D56;            //   relu(bn2(conv2(e)) + bn_d(conv1x1(d))) as ONE K = 9*128 + 64 GEMM
   add(64, 128, 1, 128, 4, kActNone, D56, 0, F56, 0, -1, 0, 0, 0);           // 7 layer2.0.downsample (weights only; never launched)

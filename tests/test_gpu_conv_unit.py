@@ -62,6 +62,7 @@ CASES = [  # nt, nacc, taps, cin, cout, H, W, N, act, residual, head
     (64, 3, 9, 64, 64, 20, 24, 7, 1, True, False),
     (64, 4, 9, 64, 64, 12, 12, 9, 2, False, False),
     (128, 2, 9, 64, 128, 14, 10, 4, 1, False, False),
+    (128, 1, 9, 64, 128, 14, 10, 9, 1, False, False),          # weights resident (layer2.0.conv1)
     (128, 4, 9, 192, 128, 12, 12, 5, 2, False, False),
     (128, 4, 1, 256, 128, 12, 12, 5, 2, False, False),
     (128, 4, 1, 64, 128, 14, 10, 4, 0, False, False),

@@ -15,6 +15,8 @@ from test_gpu_conv_unit import DebugConv, GUARD, ROUND  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--layers", default="128->128@28,256->256@28", help="comma-separated names from LAYERS_ALL")
+ap.add_argument("--ctas", default="0", help="comma-separated CTA indices whose probes are printed")
 a = ap.parse_args()
 lib = _lib.get()
 lib.popnet_debug_conv.restype = C.c_int
@@ -27,7 +29,7 @@ LAYERS_ALL = [("64->64@112", 64, 2, 9, 64, 64, 112), ("64->64@112 acc3", 64, 3, 
           ("128->128@56", 128, 4, 9, 128, 128, 56), ("1x1 128->128@56", 128, 4, 1, 128, 128, 56),
           ("256->256@28", 256, 2, 9, 256, 256, 28), ("128->128@28", 128, 4, 9, 128, 128, 28),
           ("64->64@28", 64, 4, 9, 64, 64, 28)]
-LAYERS = [l for l in LAYERS_ALL if l[0] in ("128->128@28", "256->256@28") or l[0] in ("none",) and l[0] in ("64->64@112 acc3", "128->128@56", "128->128@56 acc2", "128->128@28", "128->128@28 acc2", "64->128@56", "64->128@56 acc4", "256->256@28")]
+LAYERS = [l for l in LAYERS_ALL if l[0] in a.layers.split(",")]
 for name, nt, nacc, taps, cin, cout, H in LAYERS:
     N = a.batch
     P = (2 + N * (H + 1)) * (H + 1)
@@ -62,8 +64,9 @@ for name, nt, nacc, taps, cin, cout, H in LAYERS:
         d.probe = probe.data_ptr()
         lib.popnet_debug_conv(C.byref(d), None)
         torch.cuda.synchronize()
-        r = probe.cpu().numpy()[0]
-        nm = r[9] * nacc * 4 * taps * (cin // 64)
-        print("   dbg %2d cta 0: tiles %3d | mma thread: wait_a %7d wait_b %7d wait_acc %7d end +%7d (%.1f cyc/MMA net) | epilogue: "
-              "wait %7d busy %7d" % (dbg, r[9], r[3], r[4], r[10], r[5] - r[1], (r[5] - r[1] - r[3] - r[4] - r[10]) / max(nm, 1),
-                                     r[6], r[7]))
+        for ci in [int(v) for v in a.ctas.split(",")]:
+            r = probe.cpu().numpy()[ci]
+            nm = r[9] * nacc * 4 * taps * (cin // 64)
+            print("   dbg %2d cta %3d: tiles %3d | mma thread: wait_a %7d wait_b %7d wait_acc %7d end +%7d (%.1f cyc/MMA net) | epilogue: "
+              "wait %7d busy %7d | total %7d" % (dbg, ci, r[9], r[3], r[4], r[10], r[5] - r[1], (r[5] - r[1] - r[3] - r[4] - r[10]) / max(nm, 1),
+                                     r[6], r[7], r[8] - r[0]))

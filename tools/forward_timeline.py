@@ -42,10 +42,12 @@ n = lib.popnet_debug_trace(None, 0, tags, CAP)
 r = buf.cpu().numpy().view(np.uint64).reshape(CAP, 4)[:n].astype(np.float64)
 t0 = r[:, 0].min()
 print("forward (events, traced): %.1f us; %d launches; span of stamps %.1f us" % (e0.elapsed_time(e1) * 1e3, n, (r[:, 2].max() - t0) / 1e3))
-print("%3s %-14s %9s %9s %9s %8s %8s" % ("#", "kernel", "start", "past-wait", "end", "active", "prologue"))
+print("%3s %-14s %9s %9s %9s %8s %8s %9s" % ("#", "kernel", "start", "past-wait", "end", "active", "prologue", "SM-us/148"))
 order = np.argsort(r[:, 0])
 for i in order:
     t = tags[i]
     name = "stem" if t == 1 else "pool" if t == 2 else "conv<%d,%d,%d>%s" % (t // 1000, t // 100 % 10, t // 10 % 10, ("/chain%d" % (t % 10)) if t % 10 in (1, 2, 3, 4) and t // 10 % 10 == 9 and t // 1000 == 64 else "")
-    print("%3d %-14s %9.1f %9.1f %9.1f %8.1f %8.1f" % (i, name, (r[i, 0] - t0) / 1e3, (r[i, 1] - t0) / 1e3, (r[i, 2] - t0) / 1e3,
-                                                   (r[i, 2] - r[i, 1]) / 1e3, (r[i, 1] - r[i, 0]) / 1e3))
+    print("%3d %-14s %9.1f %9.1f %9.1f %8.1f %8.1f %9.1f" % (i, name, (r[i, 0] - t0) / 1e3, (r[i, 1] - t0) / 1e3, (r[i, 2] - t0) / 1e3,
+                                                         (r[i, 2] - r[i, 1]) / 1e3, (r[i, 1] - r[i, 0]) / 1e3, r[i, 3] / 1e3 / 148))
+# SM time (sum over the CTAs of exit - entry, in units of the whole chip): what each launch occupies whatever queued before it
+print("SM time / 148: total %.1f us of a %.1f us span (pools not counted)" % (r[:, 3].sum() / 1e3 / 148, (r[:, 2].max() - t0) / 1e3))

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define POPNET_ABI_VERSION 3
+#define POPNET_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define POPNET_API __attribute__((visibility("default")))
@@ -89,7 +89,13 @@ typedef struct PopnetDecodeParams {
   int32_t max_persons;                      /* <= POPNET_MAX_PERSONS                               */
   int32_t depth_channels;                   /* planes per frame in `depth`: the network's third head has L + 1
                                                (rtpose_light3d.py:299-309), joint j reads plane j; 0 means K        */
+  int32_t schedule;                         /* POPNET_DECODE_*: which launch schedule computes the (identical) result */
 } PopnetDecodeParams;
+
+#define POPNET_DECODE_AUTO 0           /* one fused kernel (a CTA walks whole frames through every phase with the frame's maps in
+                                          shared memory) when a frame fits, else the three-kernel schedule          */
+#define POPNET_DECODE_THREE_KERNELS 1  /* peaks (K x B CTAs) -> limbs (L x B CTAs) -> assembly + lift (B CTAs)         */
+#define POPNET_DECODE_FUSED 2          /* the fused kernel or POPNET_ERR_UNSUPPORTED                                 */
 
 /* Output buffers (see popnet_decode for which may be NULL).
  * Strides use the capacities in PopnetDecodeParams (P = max_peaks, M = max_persons, K, L). */
@@ -293,6 +299,8 @@ typedef struct PopnetNetConfig {
 #define POPNET_TUNE_STAGE_NACC(v) (((uint32_t)(v) & 3u) << 2)   /* 2 / 3: 256- / 384-position tiles in the 28 x 28 stages (0 = 512) */
 #define POPNET_TUNE_PAIR(v) (((uint32_t)(v) & 7u) << 4)         /* 3 / 4: cta_group::2 pair kernel for the 64 -> 64 layers (0 = off) */
 #define POPNET_TUNE_PAIR_RES 0x80u          /* ... including the residual layers                                           */
+#define POPNET_TUNE_RESERVE_SMS(v) (((uint32_t)(v) & 7u) << 9)  /* persistent conv grids use 148 - 4 v SMs: the rest stays free for the
+                                               decode of the previous batch, which runs concurrently on its own stream       */
 #define POPNET_TUNE_CHAIN 0x100u            /* the four 64 -> 64 layers of the 112 x 112 block as ONE spatially pipelined launch
                                                (CTA slices linked by per-tile progress counters; tensors travel through the L2)
                                                instead of four launches: bit-identical, measured 3 % slower per forward      */

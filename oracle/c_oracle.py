@@ -18,7 +18,8 @@ _lib = None
 
 def build(force=False):
     src = os.path.join(_HERE, "popnet_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    hdr = os.path.join(_HERE, "..", "include", "popnet_b200.h")          # the oracle shares the ABI's structs
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, stdout=subprocess.DEVNULL)
     return _SO
 

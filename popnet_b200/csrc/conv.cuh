@@ -72,7 +72,8 @@ struct ConvArgs {
                                 //   starts on the positions its producer wrote last, which are the ones still in the L2)
   int mc;                       // 1 = cluster-of-two kernel with multicast weight stages (conv_kernels.cu, "MC")
   int pair, pair_res;           // tuning (PopnetNetConfig.tuning): CTA-pair kernel for the 64 -> 64 layers, 0 = off, 3 / 4 = tile size / 128
-  unsigned long long* trace;    // optional [3] globaltimer stamps {first CTA in, first CTA past griddepcontrol.wait, last CTA out}
+  unsigned long long* trace;    // optional [4] globaltimer stamps {first CTA in, first CTA past griddepcontrol.wait, last CTA out, sum of CTA lifetimes}
+  int grid_cap;                 // persistent grid size limit (0 = all 148 SMs): tuning, leaves SMs to the concurrently running decode
 };
 
 struct StemArgs {

@@ -1408,7 +1408,8 @@ int launch_tc_inst(const ConvArgs& a, size_t smem, cudaStream_t st) {
   const int MT = NACC * 128;
   if (a.cout_pad != NT) return POPNET_ERR_UNSUPPORTED;     // one N tile per layer (true for every rtpose layer)
   const int tiles = (a.P + MT - 1) / MT;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;        // persistent: one CTA per SM walks the tiles
+  const int cap = (a.grid_cap > 0 && a.grid_cap < kNumSMs) ? a.grid_cap : kNumSMs;
+  const int grid = tiles < cap ? tiles : cap;                // persistent: one CTA per SM walks the tiles
   PdlConfig pc(dim3(grid), dim3(kTcThreads), smem, st);
   ConvArgs at = a;
   at.trace = next_trace_slot(NT * 1000 + NACC * 100 + TAPS * 10);

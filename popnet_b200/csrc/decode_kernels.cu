@@ -546,6 +546,445 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FUSED decode: one CTA walks whole frames through all phases (D1 .. D9) with the frame's maps, peaks and connections in
+// shared memory -- no global round trip between the phases, no 15 + 14 + 1 CTAs per frame passing through the SMs while
+// the next batch's convolutions want them (the decode of batch i runs under the forward of batch i + 1).
+//   A  heat maps -> shared memory (float4 loads)                              whole CTA
+//   B  4-neighbour NMS, ordered compaction                                    one warp per joint type
+//   C  bicubic refinement of every peak (first arg-max of the 8x patch)       one warp per peak
+//   D  PAF maps -> shared memory; pair scores, greedy matching                one warp per limb; the score matrices live in a
+//                                                                             pool that overlays the heat maps (several passes
+//                                                                             if the frame's pairs exceed the pool)
+//   E  serial person assembly + pruning                                       warp 0
+//   F  lift, rescale, back-projection, records (and the peer push)           whole CTA
+// The arithmetic of every phase is the three-kernel path's, statement for statement (both are compared byte for byte with
+// the oracle by tests/test_gpu_decode.py).  Used when the frame fits (fused_smem_bytes() <= 227 KB: the 15 / 14 topology on
+// a 28 x 28 grid takes 199 KB); larger grids / topologies take the three kernels.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 512;
+constexpr int kFusedWarps = kFusedThreads / 32;
+
+struct FusedLayout {
+  size_t heat, paf, pool_extra, fixed, total;    // byte offsets of the regions / total bytes
+  int pool_doubles;                              // score pool = heat region + pool_extra, contiguous
+};
+struct FusedFixed {                              // small per-frame tables (one instance in dynamic shared memory)
+  double cs[POPNET_MAX_LIMBS][POPNET_MAX_PEAKS];
+  double ps[POPNET_MAX_PERSONS];
+  float pk[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS];
+  float tmp[kFusedWarps][5 * 40];
+  int cell[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS];
+  int pc[POPNET_MAX_PERSONS], keep[POPNET_MAX_PERSONS];
+  int nc[POPNET_MAX_LIMBS], npk[POPNET_MAX_JOINTS], off[POPNET_MAX_LIMBS + 1];
+  int nout;
+  unsigned int flags;
+  int16_t pj[POPNET_MAX_PERSONS][POPNET_MAX_JOINTS];
+  int16_t ci[POPNET_MAX_LIMBS][POPNET_MAX_PEAKS][2];
+  int16_t xy[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS][2];
+  unsigned char used[kFusedWarps][2][POPNET_MAX_PEAKS];
+};
+__host__ __device__ inline FusedLayout fused_layout(int K, int L, int cells, size_t limit) {
+  FusedLayout f;
+  f.heat = 0;
+  size_t heat_bytes = ((size_t)K * cells * sizeof(float) + 15) & ~(size_t)15;
+  f.pool_extra = heat_bytes;
+  const size_t paf_bytes = ((size_t)2 * L * cells * sizeof(float) + 15) & ~(size_t)15;
+  const size_t fixed_bytes = (sizeof(FusedFixed) + 15) & ~(size_t)15;
+  const size_t need = heat_bytes + paf_bytes + fixed_bytes;
+  // whatever is left under the limit extends the score pool (it must hold at least one full max_peaks^2 matrix)
+  size_t extra = need < limit ? ((limit - need) & ~(size_t)15) : 0;
+  if (extra > 64 * 1024) extra = 64 * 1024;
+  f.paf = heat_bytes + extra;
+  f.fixed = f.paf + paf_bytes;
+  f.total = f.fixed + fixed_bytes;
+  f.pool_doubles = (int)((heat_bytes + extra) / sizeof(double));
+  return f;
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1) decode_fused_kernel(const float* __restrict__ heat, const float* __restrict__ paf,
+                                                                        const float* __restrict__ depth, int batch,
+                                                                        PopnetDecodeParams p, PopnetDecodeOut o, PopnetPeerPush push,
+                                                                        FusedLayout lay) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  float* s_heat = reinterpret_cast<float*>(s_dyn + lay.heat);
+  double* s_pool = reinterpret_cast<double*>(s_dyn + lay.heat);
+  float* s_paf = reinterpret_cast<float*>(s_dyn + lay.paf);
+  FusedFixed& S = *reinterpret_cast<FusedFixed*>(s_dyn + lay.fixed);
+
+  PushCtx pc;
+  pc.world = push.world; pc.rank = push.rank;
+  pc.local_chunk = nullptr;
+  if (push.world > 1) {
+    for (int q = 0; q < push.world; ++q)
+      pc.peer_chunk[q] = static_cast<char*>(push.gather_base[q]) + (size_t)push.rank * push.records_bytes;
+    pc.local_chunk = pc.peer_chunk[push.rank];
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = p.num_joints, L = p.num_limbs, MP = p.max_peaks, MM = p.max_persons, NP = p.num_intermed_pts;
+  const int H = p.grid_h, W = p.grid_w, cells = H * W;
+  const int dch = p.depth_channels > 0 ? p.depth_channels : K;
+
+  for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+    // ---- A: the frame's K heat maps (contiguous in the [B][K+1][cells] tensor)
+    {
+      const float* src = heat + (size_t)b * (K + 1) * cells;
+      const int n = K * cells;
+      if ((cells & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(s_heat);
+        for (int i = tid; i < n / 4; i += kFusedThreads) d4[i] = __ldg(s4 + i);
+      } else {
+        for (int i = tid; i < n; i += kFusedThreads) s_heat[i] = src[i];
+      }
+      if (tid == 0) S.flags = 0u;
+    }
+    __syncthreads();
+
+    // ---- B: peak cells of joint type k in row-major order (one warp per type)
+    for (int k = warp; k < K; k += kFusedWarps) {
+      const float* m = s_heat + (size_t)k * cells;
+      int cnt = 0;
+      for (int base = 0; base < cells; base += 32) {
+        const int i = base + lane;
+        bool pk = false;
+        if (i < cells) {
+          const int y = i / W, x = i - y * W;
+          const float v = m[i];
+          pk = v > p.thresh_heat;
+          if (pk && y > 0) pk = !(m[i - W] > v);
+          if (pk && y < H - 1) pk = !(m[i + W] > v);
+          if (pk && x > 0) pk = !(m[i - 1] > v);
+          if (pk && x < W - 1) pk = !(m[i + 1] > v);
+        }
+        const unsigned bal = __ballot_sync(kFull, pk);
+        if (pk) {
+          const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
+          if (slot < MP) S.cell[k][slot] = i;
+        }
+        cnt += __popc(bal);
+      }
+      if (lane == 0) {
+        if (cnt > MP) { atomicOr(&S.flags, POPNET_FLAG_PEAK_OVERFLOW); cnt = MP; }
+        S.npk[k] = cnt;
+        o.peak_count[(size_t)b * K + k] = cnt;
+      }
+    }
+    __syncthreads();
+
+    // ---- C: refinement, one warp per peak (flat index over the types)
+    {
+      int total = 0;
+      for (int k = 0; k < K; ++k) total += S.npk[k];
+      float* tmp = S.tmp[warp];
+      for (int t = warp; t < total; t += kFusedWarps) {
+        int k = 0, pi = t;
+        while (pi >= S.npk[k]) { pi -= S.npk[k]; ++k; }
+        const float* s_map = s_heat + (size_t)k * cells;
+        const int cell = S.cell[k][pi];
+        const int y = cell / W, x = cell - y * W;
+        const int x0 = max(x - 2, 0), y0 = max(y - 2, 0), x1 = min(x + 2, W - 1), y1 = min(y + 2, H - 1);
+        const int pw = x1 - x0 + 1, ph = y1 - y0 + 1, uw = pw * 8, uh = ph * 8;
+        const float* patch = s_map + y0 * W + x0;
+        for (int i = lane; i < ph * uw; i += 32) {
+          const int r = i / uw, dx = i - r * uw;
+          const int rx = dx & 7, bx = (dx >> 3) + c_ofs[rx];
+          const float* row = patch + r * W;
+          tmp[r * 40 + dx] = ((row[clampi(bx - 1, 0, pw - 1)] * c_coef[rx][0] + row[clampi(bx, 0, pw - 1)] * c_coef[rx][1]) +
+                              row[clampi(bx + 1, 0, pw - 1)] * c_coef[rx][2]) + row[clampi(bx + 2, 0, pw - 1)] * c_coef[rx][3];
+        }
+        __syncwarp();
+        float best = -CUDART_INF_F;
+        int bidx = 0x7fffffff;
+        for (int i = lane; i < uh * uw; i += 32) {
+          const int dy = i / uw, dx = i - dy * uw;
+          const int ry = dy & 7, by = (dy >> 3) + c_ofs[ry];
+          const float v = tmp[clampi(by - 1, 0, ph - 1) * 40 + dx] * c_coef[ry][0] +
+                          (tmp[clampi(by, 0, ph - 1) * 40 + dx] * c_coef[ry][1] +
+                           (tmp[clampi(by + 1, 0, ph - 1) * 40 + dx] * c_coef[ry][2] +
+                            tmp[clampi(by + 2, 0, ph - 1) * 40 + dx] * c_coef[ry][3]));
+          if (v > best) { best = v; bidx = i; }
+        }
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+          const float ov = __shfl_xor_sync(kFull, best, ofs);
+          const int oi = __shfl_xor_sync(kFull, bidx, ofs);
+          if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+        }
+        if (lane == 0) {
+          const int ay = bidx / uw, ax = bidx - ay * uw;
+          const int16_t X = (int16_t)(8 * x0 + ax), Y = (int16_t)(8 * y0 + ay);
+          S.xy[k][pi][0] = X; S.xy[k][pi][1] = Y; S.pk[k][pi] = best;
+          const size_t slot = ((size_t)b * K + k) * MP + pi;
+          o.peak_xy[slot * 2] = X;
+          o.peak_xy[slot * 2 + 1] = Y;
+          o.peak_score[slot] = best;
+        }
+        __syncwarp();
+      }
+    }
+    // ---- D: PAF maps -> shared memory (they do not overlap the heat region, which phase C may still be reading)
+    {
+      const float* src = paf + (size_t)b * 2 * L * cells;
+      const int n = 2 * L * cells;
+      if ((cells & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(s_paf);
+        for (int i = tid; i < n / 4; i += kFusedThreads) d4[i] = __ldg(s4 + i);
+      } else {
+        for (int i = tid; i < n; i += kFusedThreads) s_paf[i] = src[i];
+      }
+    }
+    __syncthreads();                      // heat maps are dead from here on: their region becomes the score pool
+    const double Hup = (double)(H * p.stride);
+    for (int l0 = 0; l0 < L;) {
+      // limbs [l0, l1) whose na x nb score matrices fit into the pool together (every thread computes the same split)
+      int l1 = l0, used = 0;
+      while (l1 < L) {
+        const int need = S.npk[p.limbs[l1][0]] * S.npk[p.limbs[l1][1]];
+        if (l1 > l0 && used + need > lay.pool_doubles) break;
+        if (tid == 0) S.off[l1] = used;
+        used += need;
+        ++l1;
+      }
+      __syncthreads();
+      for (int l = l0 + warp; l < l1; l += kFusedWarps) {
+        const int ta = p.limbs[l][0], tb = p.limbs[l][1];
+        const int na = S.npk[ta], nb = S.npk[tb];
+        if (na == 0 || nb == 0) {
+          if (lane == 0) { S.nc[l] = 0; o.conn_count[(size_t)b * L + l] = 0; }
+          continue;
+        }
+        double* s_score = s_pool + S.off[l];                 // [na][nb]
+        const float* s_px = s_paf + (size_t)(2 * l) * cells;
+        const float* s_py = s_px + cells;
+        unsigned char* used_a = S.used[warp][0];
+        unsigned char* used_b = S.used[warp][1];
+        for (int i = lane; i < POPNET_MAX_PEAKS; i += 32) { used_a[i] = 0; used_b[i] = 0; }
+        const int npairs = na * nb;
+        for (int pr = lane; pr < npairs; pr += 32) {
+          const int i = pr / nb, j = pr - i * nb;
+          const int ax = S.xy[ta][i][0], ay = S.xy[ta][i][1], bx = S.xy[tb][j][0], by = S.xy[tb][j][1];
+          const double dx = (double)bx - (double)ax, dy = (double)by - (double)ay;
+          const double dist = sqrt(dx * dx + dy * dy) + 1e-8;
+          const double ux = dx / dist, uy = dy / dist;
+          double s[32];
+          int above = 0;
+          const int body = NP & ~3;
+          for (int t = 0; t < NP; ++t) {
+            const int X = line_point(ax, bx, t, NP), Y = line_point(ay, by, t, NP);
+            const double px = (double)bicubic_at(s_px, W, H, W, X, Y), py = (double)bicubic_at(s_py, W, H, W, X, Y);
+            s[t] = (t < body) ? fma(px, ux, py * uy) : fma(py, uy, px * ux);
+            above += s[t] > p.thresh_paf;
+          }
+          double sum;
+          if (NP < 8) {
+            sum = 0.0;
+            for (int t = 0; t < NP; ++t) sum += s[t];
+          } else {
+            double r8[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) r8[t] = s[t];
+            int t = 8;
+            for (; t + 8 <= NP; t += 8)
+#pragma unroll
+              for (int u = 0; u < 8; ++u) r8[u] += s[t + u];
+            sum = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+            for (; t < NP; ++t) sum += s[t];
+          }
+          double pen = 0.5 * Hup / dist - 1;
+          if (!(pen < 0)) pen = 0;
+          const double sc = sum / (double)NP + pen;
+          s_score[pr] = ((double)above > 0.8 * (double)NP && sc > 0) ? sc : -CUDART_INF;
+        }
+        __syncwarp();
+        // greedy: repeatedly the best remaining pair whose ends are both free, ties to the smallest (i, j)
+        const int maxc = min(na, nb);
+        int nconn = 0;
+        while (nconn < maxc) {
+          double bv = -CUDART_INF;
+          int bi = 0x7fffffff;
+          for (int pr = lane; pr < npairs; pr += 32) {
+            const int i = pr / nb, j = pr - i * nb;
+            if (used_a[i] || used_b[j]) continue;
+            const double v = s_score[pr];
+            if (v > bv) { bv = v; bi = pr; }
+          }
+#pragma unroll
+          for (int ofs = 16; ofs > 0; ofs >>= 1) {
+            const double ov = __shfl_xor_sync(kFull, bv, ofs);
+            const int oi = __shfl_xor_sync(kFull, bi, ofs);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          }
+          if (bi == 0x7fffffff) break;
+          const int i = bi / nb, j = bi - i * nb;
+          if (lane == 0) {
+            used_a[i] = 1; used_b[j] = 1;
+            S.ci[l][nconn][0] = (int16_t)i; S.ci[l][nconn][1] = (int16_t)j; S.cs[l][nconn] = bv;
+            const size_t slot = ((size_t)b * L + l) * MP + nconn;
+            o.conn_ij[slot * 2] = (int16_t)i;
+            o.conn_ij[slot * 2 + 1] = (int16_t)j;
+            o.conn_score[slot] = bv;
+          }
+          ++nconn;
+          __syncwarp();
+        }
+        if (lane == 0) { S.nc[l] = nconn; o.conn_count[(size_t)b * L + l] = nconn; }
+      }
+      __syncthreads();
+      l0 = l1;
+    }
+
+    // ---- E: serial assembly by warp 0 (paf_to_pose.py:267-351), as in assemble_kernel
+    if (warp == 0) {
+      int np_ = 0;
+      unsigned flags = 0;
+      for (int l = 0; l < L; ++l) {
+        const int ta = p.limbs[l][0], tb = p.limbs[l][1];
+        const int nc = S.nc[l];
+        for (int c = 0; c < nc; ++c) {
+          const int ia = S.ci[l][c][0], ib = S.ci[l][c][1];
+          const double ls = S.cs[l][c];
+          unsigned long long hits = 0;
+          for (int q0 = 0; q0 < np_; q0 += 32) {
+            const int q = q0 + lane;
+            const bool h = q < np_ && (S.pj[q][ta] == ia || S.pj[q][tb] == ib);
+            hits |= (unsigned long long)__ballot_sync(kFull, h) << q0;
+          }
+          const int nh = __popcll(hits);
+          const double sb = (double)S.pk[tb][ib];
+          if (nh == 1) {
+            const int q = __ffsll((long long)hits) - 1;
+            if (lane == 0 && S.pj[q][tb] != ib) {
+              S.pj[q][tb] = (int16_t)ib;
+              S.pc[q] += 1;
+              S.ps[q] += sb + ls;
+            }
+          } else if (nh == 2) {
+            const int q1 = __ffsll((long long)hits) - 1;
+            const int q2 = __ffsll((long long)(hits & (hits - 1))) - 1;
+            const bool ov = lane < K && S.pj[q1][lane] >= 0 && S.pj[q2][lane] >= 0;
+            if (!__any_sync(kFull, ov)) {
+              if (lane < K) S.pj[q1][lane] = (int16_t)(S.pj[q1][lane] + S.pj[q2][lane] + 1);
+              if (lane == 0) {
+                S.ps[q1] += S.ps[q2];
+                S.pc[q1] += S.pc[q2];
+                S.ps[q1] += ls;
+              }
+              __syncwarp();
+              for (int q = q2; q + 1 < np_; ++q) {
+                if (lane < K) S.pj[q][lane] = S.pj[q + 1][lane];
+                if (lane == 0) { S.ps[q] = S.ps[q + 1]; S.pc[q] = S.pc[q + 1]; }
+                __syncwarp();
+              }
+              --np_;
+            } else if (lane == 0) {
+              S.pj[q1][tb] = (int16_t)ib;
+              S.pc[q1] += 1;
+              S.ps[q1] += sb + ls;
+            }
+          } else {
+            if (np_ >= MM) flags |= POPNET_FLAG_PERSON_OVERFLOW;
+            else {
+              if (lane < POPNET_MAX_JOINTS) S.pj[np_][lane] = (lane == ta) ? (int16_t)ia : (lane == tb) ? (int16_t)ib : (int16_t)-1;
+              if (lane == 0) {
+                const double sa = (double)S.pk[ta][ia];
+                S.pc[np_] = 2;
+                S.ps[np_] = ((0 + sa) + sb) + ls;
+              }
+              ++np_;
+            }
+          }
+          __syncwarp();
+        }
+      }
+      int nout = 0;
+      for (int q0 = 0; q0 < np_; q0 += 32) {
+        const int q = q0 + lane;
+        bool keep = false;
+        if (q < np_) {
+          const double cnt = (double)S.pc[q], sc = S.ps[q];
+          keep = !(cnt < 3 || sc / cnt < 0.2);
+        }
+        const unsigned bal = __ballot_sync(kFull, keep);
+        if (keep) S.keep[nout + __popc(bal & ((1u << lane) - 1u))] = q;
+        nout += __popc(bal);
+      }
+      if (lane == 0) {
+        S.nout = nout;
+        rec_store(pc, o.n_person + b, nout);
+        rec_store(pc, o.flags + b, (uint32_t)(S.flags | flags));
+      }
+    }
+    __syncthreads();
+
+    // ---- F: lift, rescale, back-projection, records (assemble_kernel's tail)
+    const int nout = S.nout;
+    for (int i = tid; i < nout; i += kFusedThreads) {
+      const size_t row = (size_t)b * MM + i;
+      const int q = S.keep[i];
+      if (o.person_score) rec_store(pc, o.person_score + row, S.ps[q]);
+      if (o.person_njoint) rec_store(pc, o.person_njoint + row, (int32_t)S.pc[q]);
+    }
+    for (int i = tid; i < nout * K; i += kFusedThreads) {
+      const int pi_ = i / K, k = i - pi_ * K;
+      const int q = S.keep[pi_], idx = S.pj[q][k];
+      const size_t row = (size_t)b * MM + pi_;
+      if (o.person_peak) rec_store(pc, o.person_peak + row * K + k, (int16_t)idx);
+      double x2 = -1, y2 = -1, Z = -1, conf = 0;
+      if (idx >= 0) {
+        const int X = S.xy[k][idx][0], Y = S.xy[k][idx][1];
+        conf = (double)S.pk[k][idx];
+        if (depth) {
+          const int cx = X / p.stride, cy = Y / p.stride;
+          const int x0 = clampi(cx - 1, 0, W - 1), x1 = clampi(cx + 1, 0, W - 1);
+          const int y0 = clampi(cy - 1, 0, H - 1), y1 = clampi(cy + 1, 0, H - 1);
+          const float* hm = heat + ((size_t)b * (K + 1) + k) * cells;
+          const float* dm = depth + ((size_t)b * dch + k) * cells;
+          float wv[9], dv[9];
+          int n = 0;
+          for (int yy = y0; yy <= y1; ++yy)
+            for (int xx = x0; xx <= x1; ++xx) {
+              float hv = hm[yy * W + xx];
+              if (hv < 0) hv = 0;
+              const float w = hv + 0.000000001f;
+              float d = dm[yy * W + xx] * p.depth_std;
+              d = d + p.depth_mean;
+              wv[n] = w; dv[n] = d * w; ++n;
+            }
+          Z = (double)(sum_pairwise_f32(dv, n) / sum_pairwise_f32(wv, n));
+        }
+        x2 = (double)X / p.input_size * p.w_org;
+        y2 = (double)Y / p.input_size * p.h_org;
+      }
+      if (o.pose2d) { rec_store(pc, o.pose2d + (row * K + k) * 2, x2); rec_store(pc, o.pose2d + (row * K + k) * 2 + 1, y2); }
+      if (o.pose_conf) rec_store(pc, o.pose_conf + row * K + k, conf);
+      if (o.pose3d && depth) {
+        double X3 = (x2 - p.cx) * Z / p.fx, Y3 = (y2 - p.cy) * Z / p.fy;
+        if (p.flip_y) Y3 = -Y3;
+        double* d3 = o.pose3d + (row * K + k) * 3;
+        rec_store(pc, d3, X3); rec_store(pc, d3 + 1, Y3); rec_store(pc, d3 + 2, Z);
+      }
+    }
+    __syncthreads();                      // the tables are rewritten by the next frame
+  }
+  if (push.world > 1) {
+    // publish: when the LAST CTA of the grid has pushed its frames, tag this rank's slot in every rank's arrive[] array
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int ticket = atomicAdd(push.done_counter, 1u);
+      if (ticket == gridDim.x - 1) {
+        *push.done_counter = 0u;
+        const unsigned long long tag = *push.step + 1ull;
+        *push.step = tag;
+        __threadfence_system();
+        for (int q = 0; q < push.world; ++q) st_release_sys(push.arrive[q] + push.rank, tag);
+      }
+    }
+  }
+}
+
 // one warp: lane q waits for rank q's tag of the current step (bounded: a dead peer sets *status instead of hanging)
 __global__ void __launch_bounds__(32) p2p_wait_kernel(const unsigned long long* arrive, int world, const unsigned long long* step,
                                                       unsigned int* status, unsigned long long timeout_ns) {
@@ -655,10 +1094,28 @@ int decode_impl(const float* heat, const float* paf, const float* depth, int bat
   for (int l = 0; l < p->num_limbs; ++l)
     if (p->limbs[l][0] < 0 || p->limbs[l][0] >= p->num_joints || p->limbs[l][1] < 0 || p->limbs[l][1] >= p->num_joints)
       return POPNET_ERR_INVALID_ARG;
+  if (p->schedule != POPNET_DECODE_AUTO && p->schedule != POPNET_DECODE_THREE_KERNELS && p->schedule != POPNET_DECODE_FUSED)
+    return POPNET_ERR_INVALID_ARG;
   if (batch == 0) return POPNET_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  POPNET_CUDA_TRY(cudaMemsetAsync(o->flags, 0, sizeof(uint32_t) * batch, st));
   const int cells = p->grid_h * p->grid_w;
+  if (p->schedule != POPNET_DECODE_THREE_KERNELS) {
+    constexpr size_t kLimit = 227 * 1024;
+    const FusedLayout lay = fused_layout(p->num_joints, p->num_limbs, cells, kLimit);
+    const bool fits = lay.total <= kLimit && lay.pool_doubles >= p->max_peaks * p->max_peaks;
+    if (fits) {
+      int dev = 0, sms = 148;
+      POPNET_CUDA_TRY(cudaGetDevice(&dev));
+      POPNET_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      POPNET_CUDA_TRY(cudaFuncSetAttribute(decode_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+      const int grid = batch < sms ? batch : sms;
+      decode_fused_kernel<<<grid, kFusedThreads, lay.total, st>>>(heat, paf, depth, batch, *p, *o, pp, lay);
+      POPNET_AFTER_LAUNCH();
+      return POPNET_OK;
+    }
+    if (p->schedule == POPNET_DECODE_FUSED) return POPNET_ERR_UNSUPPORTED;
+  }
+  POPNET_CUDA_TRY(cudaMemsetAsync(o->flags, 0, sizeof(uint32_t) * batch, st));
   const size_t smem_peaks = sizeof(float) * cells;
   const size_t smem_limbs = sizeof(double) * p->max_peaks * p->max_peaks + 2 * sizeof(float) * cells;
   if (smem_limbs > 48 * 1024)

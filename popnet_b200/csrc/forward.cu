@@ -370,6 +370,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     a.reverse = (zigzag && li >= 1 && li <= 4) ? (chain ? 1 : (li & 1)) : 0;
     a.pair = (int)((cfg->tuning >> 4) & 7u);
     a.pair_res = (cfg->tuning & POPNET_TUNE_PAIR_RES) ? 1 : 0;
+    a.grid_cap = 148 - 4 * (int)((cfg->tuning >> 9) & 7u);
   };
   auto run_conv = [&](int li) -> int {
     const Layer& l = p.layers[li];

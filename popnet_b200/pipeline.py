@@ -35,7 +35,7 @@ class PoseEstimator:
 
     def __init__(self, model, camera: Camera = MP3DHP, config: DecodeConfig | None = None, *, input_size=224,
                  max_persons: int = 32, max_peaks: int = _abi.MAX_PEAKS, strict: bool = True, use_graphs: bool = True,
-                 peers=None):
+                 peers=None, decode_priority: int = 0):
         from ._cuda_backend import CudaBackend          # raises without CUDA / the library
         self.backend = CudaBackend()
         self.model = model
@@ -53,6 +53,7 @@ class PoseEstimator:
         #: leaves the check of out["flags"] to the caller.
         self.strict = strict
         self.use_graphs = use_graphs
+        self.decode_priority = decode_priority      # CUDA stream priority of the decode stream (0 = default, -1 = high)
         self.peers = peers          # optional p2p.PeerGather: the multi-GPU record exchange, fused into the decode
         self._slots = None
         self._B = None
@@ -78,8 +79,10 @@ class PoseEstimator:
             })
         self._B = B
         self._copy_stream = torch.cuda.Stream()
-        self.decode_stream = torch.cuda.Stream()
+        self.decode_stream = torch.cuda.Stream(priority=self.decode_priority)
         self._capture_stream = torch.cuda.Stream()
+        # (kernel nodes of a graph keep the priority of the stream they were captured on)
+        self._capture_stream_dec = torch.cuda.Stream(priority=self.decode_priority) if self.decode_priority else self._capture_stream
         self._next = 0
         return self._slots
 
@@ -118,7 +121,7 @@ class PoseEstimator:
         gf, gd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(gf, stream=s, capture_error_mode="thread_local"):
             self._launch_forward(slot)
-        with torch.cuda.graph(gd, stream=s, capture_error_mode="thread_local"):
+        with torch.cuda.graph(gd, stream=self._capture_stream_dec, capture_error_mode="thread_local"):
             self._launch_decode(slot)
         slot["graphs"] = (gf, gd)
 

@@ -8,12 +8,19 @@ from popnet_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
+# Both launch schedules of popnet_decode compute every record byte for byte like the oracle: the fused per-frame kernel
+# (POPNET_DECODE_FUSED; what POPNET_DECODE_AUTO picks whenever a frame's maps fit in shared memory -- asserting FUSED here
+# also proves that it is the path that runs for the 28 x 28 / 15-joint configuration) and the three-kernel schedule.
+SCHEDULES = [("fused", 2), ("three_kernels", 1)]
+schedules = pytest.mark.parametrize("schedule", [v for _, v in SCHEDULES], ids=[n for n, _ in SCHEDULES])
 
+
+@schedules
 @pytest.mark.parametrize("case", DECODE_CASES, ids=[c[0] for c in DECODE_CASES])
-def test_decode_bitwise_vs_oracle_and_reference(case, cuda_backend, oracle_lib):
+def test_decode_bitwise_vs_oracle_and_reference(case, schedule, cuda_backend, oracle_lib):
     g = golden("decode_golden")
     heat, paf, depth = helpers.decode_case_inputs(case)
-    params = helpers.params_for(case[5])
+    params = helpers.params_for(case[5], schedule=schedule)
     dev = cuda_backend.decode(heat, paf, depth, params)
     ora = oracle_lib.decode(heat, paf, depth, params)
     assert helpers.records_equal(dev, ora) == []
@@ -26,10 +33,11 @@ def test_decode_bitwise_vs_oracle_and_reference(case, cuda_backend, oracle_lib):
 
 @pytest.mark.parametrize("batch,persons,seed", [(64, (1, 6), 1234), (256, (12, 16), 4242), (512, (1, 6), 77)],
                          ids=["C2-b64", "C5-crowd-b256", "C4-b512"])
-def test_decode_full_size_vs_oracle(batch, persons, seed, cuda_backend, oracle_lib):
+@schedules
+def test_decode_full_size_vs_oracle(batch, persons, seed, schedule, cuda_backend, oracle_lib):
     """BASELINE.json configs C2 / C5 / C4 at their full batch sizes, byte-for-byte against the oracle."""
     heat, paf, depth, _ = synth.map_batch(batch, seed=seed, persons=persons, noise=0.01)
-    params = helpers.params_for("MP3DHP")
+    params = helpers.params_for("MP3DHP", schedule=schedule)
     dev = cuda_backend.decode(heat, paf, depth, params)
     ora = oracle_lib.decode(heat, paf, depth, params)
     assert helpers.records_equal(dev, ora) == []
@@ -46,7 +54,8 @@ def test_decode_shard_invariance(cuda_backend):
     assert helpers.records_equal(full, cat) == []
 
 
-def test_decode_degenerate_overflow_flags(cuda_backend, oracle_lib):
+@schedules
+def test_decode_degenerate_overflow_flags(schedule, cuda_backend, oracle_lib):
     """Untrained-network-like maps (heat ~ 0.5 everywhere): hundreds of plateau peaks per joint
     type.  Capacities overflow; flags and the truncated records must match the oracle's."""
     rng = np.random.default_rng(0)
@@ -54,7 +63,7 @@ def test_decode_degenerate_overflow_flags(cuda_backend, oracle_lib):
     heat[2] = 0.5                                         # one giant plateau: every cell is a peak
     paf = (0.05 * rng.standard_normal((3, 28, 28, 28))).astype(np.float32)
     depth = rng.standard_normal((3, 15, 28, 28)).astype(np.float32)
-    params = helpers.params_for("MP3DHP")
+    params = helpers.params_for("MP3DHP", schedule=schedule)
     dev = cuda_backend.decode(heat, paf, depth, params)
     ora = oracle_lib.decode(heat, paf, depth, params)
     assert (dev["flags"] & 1).all()

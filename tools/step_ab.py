@@ -16,6 +16,8 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--seconds", type=float, default=2.0)
 ap.add_argument("--tuning", type=lambda v: int(v, 0), default=0)
 ap.add_argument("--rounds", type=int, default=2)
+ap.add_argument("--decode-priority", type=int, default=0)
+ap.add_argument("--only", default="", help="comma-separated variant names to run (default: all)")
 a = ap.parse_args()
 
 z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "fixture_ckpt.npz"))
@@ -24,7 +26,7 @@ m = network.rtpose_light3d(15, 14, 2, input_dim=1)
 m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
 m.operand_dtype = _abi.OPERAND_FP16
 m.tuning = a.tuning
-est = pipeline.PoseEstimator(m, max_persons=32, strict=False)
+est = pipeline.PoseEstimator(m, max_persons=32, strict=False, decode_priority=a.decode_priority)
 B = a.batch
 NS = est.NSLOT
 for i in range(NS):
@@ -67,7 +69,9 @@ def timed(fn, n):
 
 for r in range(a.rounds):
     for name, fn in (("forward only", fwd_only), ("overlapped (product)", overlapped), ("serialised", serial), ("decode only", dec_only)):
+        if a.only and name.split(" ")[0] not in a.only.split(","):
+            continue
         t = timed(fn, 50)
         n = max(50, int(a.seconds * 1e3 / t))
         t = timed(fn, n)
-        print("%-22s %.4f ms per step  (%6.0f frames/s)  [%d steps]" % (name, t, B / t * 1e3, n), flush=True)
+        print("tuning 0x%x prio %d: %-22s %.4f ms per step  (%6.0f frames/s)  [%d steps]" % (a.tuning, a.decode_priority, name, t, B / t * 1e3, n), flush=True)

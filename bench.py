@@ -413,6 +413,30 @@ def run_ours(args, rank, local_rank, world):
             check["gather_equals_one_gpu"] = check["gather_sha"] == check["one_gpu_sha"]
         check["p2p_timed_out"] = bool(timed_out)
         barrier()
+        # evaluator over frame shards on NCCL: all-reduced PCK counters and the AP of the variable-length (score, label) gather
+        # must equal rank 0's single-GPU evaluation of the whole set
+        import contextlib
+        import io as _io
+        from popnet_b200 import evaluate, synth
+        ds = synth.eval_set(400, seed=9)
+        names = ["j%d" % i for i in range(15)]
+        cut = [round(400 * r / world * (0.9 if 0 < r < world else 1.0)) for r in range(world + 1)]     # unequal shards
+        sl = slice(cut[rank], cut[rank + 1])
+        with contextlib.redirect_stdout(_io.StringIO()):
+            part = evaluate.match_counts(ds["pred2d"][sl], ds["gt2d"][sl], pred3d=ds["pred3d"][sl], gt3d=ds["gt3d"][sl],
+                                         num_joints=15, dist_th=0.1)
+            red = pipeline.reduce_counts({"hit_cnt": torch.as_tensor(part["hit_cnt"]).cuda(),
+                                          "valid_cnt": torch.as_tensor(part["valid_cnt"]).cuda()})
+            ap = evaluate.eval_ap_3D_sharded(ds["pred3d"][sl], ds["conf"][sl], ds["gt3d"][sl], [], names, thresh=0.1)
+            if rank == 0:
+                whole = evaluate.match_counts(ds["pred2d"], ds["gt2d"], pred3d=ds["pred3d"], gt3d=ds["gt3d"], num_joints=15, dist_th=0.1)
+                ap1 = evaluate.eval_ap_3D(ds["pred3d"], ds["conf"], ds["gt3d"], [], names, thresh=0.1)
+        if rank == 0:
+            check["evaluator_sharded"] = {
+                "pck_counters_equal_one_gpu": bool(np.array_equal(red["hit_cnt"].cpu().numpy(), whole["hit_cnt"]) and
+                                                   np.array_equal(red["valid_cnt"].cpu().numpy(), whole["valid_cnt"])),
+                "ap_equals_one_gpu": bool(np.array_equal(np.asarray(ap), np.asarray(ap1))), "mAP": float(ap1[-1])}
+        barrier()
     if rank != 0:
         if world > 1:
             peers.close()

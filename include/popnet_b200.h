@@ -101,10 +101,10 @@ typedef struct PopnetDecodeParams {
  * Strides use the capacities in PopnetDecodeParams (P = max_peaks, M = max_persons, K, L). */
 typedef struct PopnetDecodeOut {
   int32_t* peak_count;     /* [B][K]                                                              */
-  int16_t* peak_xy;        /* [B][K][P][2]   refined (X, Y) in input pixels, integers              */
+  int16_t* peak_xy;        /* [B][K][P][2]   refined (X, Y) in input pixels, integers; 4-byte aligned */
   float* peak_score;       /* [B][K][P]      bicubic value at the refined maximum                  */
   int32_t* conn_count;     /* [B][L]                                                              */
-  int16_t* conn_ij;        /* [B][L][P][2]   (src index, dst index) within their joint types       */
+  int16_t* conn_ij;        /* [B][L][P][2]   (src index, dst index) within their joint types; 4-byte aligned */
   double* conn_score;      /* [B][L][P]                                                           */
   int32_t* n_person;       /* [B]            persons that survive pruning                          */
   int16_t* person_peak;    /* [B][M][K]      peak index within the joint type, -1 = missing        */
@@ -301,6 +301,7 @@ typedef struct PopnetNetConfig {
 #define POPNET_TUNE_PAIR_RES 0x80u          /* ... including the residual layers                                           */
 #define POPNET_TUNE_RESERVE_SMS(v) (((uint32_t)(v) & 7u) << 9)  /* persistent conv grids use 148 - 4 v SMs: the rest stays free for the
                                                decode of the previous batch, which runs concurrently on its own stream       */
+#define POPNET_TUNE_BALANCE 0x1000u         /* persistent grids sized so that every CTA walks the same number of tiles        */
 #define POPNET_TUNE_CHAIN 0x100u            /* the four 64 -> 64 layers of the 112 x 112 block as ONE spatially pipelined launch
                                                (CTA slices linked by per-tile progress counters; tensors travel through the L2)
                                                instead of four launches: bit-identical, measured 3 % slower per forward      */

@@ -26,6 +26,7 @@ TUNE_NO_ZIGZAG = 0x1
 TUNE_MC = 0x2
 TUNE_PAIR_RES = 0x80
 TUNE_CHAIN = 0x100
+TUNE_BALANCE = 0x1000
 
 
 def TUNE_RESERVE_SMS(v):

@@ -74,6 +74,7 @@ struct ConvArgs {
   int pair, pair_res;           // tuning (PopnetNetConfig.tuning): CTA-pair kernel for the 64 -> 64 layers, 0 = off, 3 / 4 = tile size / 128
   unsigned long long* trace;    // optional [4] globaltimer stamps {first CTA in, first CTA past griddepcontrol.wait, last CTA out, sum of CTA lifetimes}
   int grid_cap;                 // persistent grid size limit (0 = all 148 SMs): tuning, leaves SMs to the concurrently running decode
+  int balance;                  // tuning: size the persistent grid so that every CTA walks the same number of tiles
 };
 
 struct StemArgs {

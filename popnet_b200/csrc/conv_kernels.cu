@@ -1409,7 +1409,13 @@ int launch_tc_inst(const ConvArgs& a, size_t smem, cudaStream_t st) {
   if (a.cout_pad != NT) return POPNET_ERR_UNSUPPORTED;     // one N tile per layer (true for every rtpose layer)
   const int tiles = (a.P + MT - 1) / MT;
   const int cap = (a.grid_cap > 0 && a.grid_cap < kNumSMs) ? a.grid_cap : kNumSMs;
-  const int grid = tiles < cap ? tiles : cap;                // persistent: one CTA per SM walks the tiles
+  int grid = tiles < cap ? tiles : cap;                      // persistent: one CTA per SM walks the tiles
+  if (a.balance && tiles > cap) {
+    // equal tile counts: ceil(tiles / cap) tiles in every CTA (211 tiles: 106 CTAs x 2 instead of 63 x 2 + 85 x 1) -- the layer
+    // takes as long either way, but the SMs a launch does not need are free for the concurrent branches of the stage
+    const int per = (tiles + cap - 1) / cap;
+    grid = (tiles + per - 1) / per;
+  }
   PdlConfig pc(dim3(grid), dim3(kTcThreads), smem, st);
   ConvArgs at = a;
   at.trace = next_trace_slot(NT * 1000 + NACC * 100 + TAPS * 10);

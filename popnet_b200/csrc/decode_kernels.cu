@@ -68,6 +68,63 @@ __device__ __forceinline__ float bicubic_at(const float* m, int pitch, int H, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// D2 for ONE peak by one warp (paf_to_pose.py:96-118): the 8x bicubic of the clipped 5x5 patch around `cell` and the FIRST
+// arg-max of the (<= 40 x 40) result in row-major order.
+// Lane = output column (dx = lane, and lane + 32 for the last 8 columns of a 40-wide patch): its horizontal phase
+// rx = dx & 7 = lane & 7 never changes, so the four horizontal weights `hc` and the tap offset `hofs` are per-lane constants
+// of the kernel; the column's (<= 5) horizontally interpolated values go to the warp's scratch `tmp` [5][40] and the same
+// lane walks down the column: per source row cy the five scratch rows cy-2 .. cy+2 (clamped) give the 8 output rows
+// 8 cy .. 8 cy + 7, whose vertical weights are compile-time constants after unrolling.  Same expressions and association as
+// cv::resize (see bicubic_at), so every value is bit-identical to the full upsample's.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void refine_peak(const float* __restrict__ s_map, int W, int H, int cell, float* __restrict__ tmp,
+                                            int lane, const float hc0, const float hc1, const float hc2, const float hc3,
+                                            const int hofs, int& X, int& Y, float& score) {
+  const int y = cell / W, x = cell - y * W;
+  const int x0 = max(x - 2, 0), y0 = max(y - 2, 0), x1 = min(x + 2, W - 1), y1 = min(y + 2, H - 1);
+  const int pw = x1 - x0 + 1, ph = y1 - y0 + 1, uw = pw * 8;
+  const float* patch = s_map + y0 * W + x0;
+  const int nset = (uw > 32 && lane + 32 < uw) ? 2 : ((lane < uw) ? 1 : 0);
+  for (int s = 0; s < nset; ++s) {
+    const int dx = lane + 32 * s;
+    const int bx = (dx >> 3) + hofs;
+    const int i0 = clampi(bx - 1, 0, pw - 1), i1 = clampi(bx, 0, pw - 1), i2 = clampi(bx + 1, 0, pw - 1), i3 = clampi(bx + 2, 0, pw - 1);
+    for (int r = 0; r < ph; ++r) {
+      const float* row = patch + r * W;
+      tmp[r * 40 + dx] = ((row[i0] * hc0 + row[i1] * hc1) + row[i2] * hc2) + row[i3] * hc3;
+    }
+  }
+  __syncwarp();
+  float best = -CUDART_INF_F;
+  int bidx = 0x7fffffff;
+  for (int s = 0; s < nset; ++s) {
+    const int dx = lane + 32 * s;
+    for (int cy = 0; cy < ph; ++cy) {
+      const float tm2 = tmp[clampi(cy - 2, 0, ph - 1) * 40 + dx], tm1 = tmp[clampi(cy - 1, 0, ph - 1) * 40 + dx];
+      const float t00 = tmp[cy * 40 + dx];
+      const float tp1 = tmp[clampi(cy + 1, 0, ph - 1) * 40 + dx], tp2 = tmp[clampi(cy + 2, 0, ph - 1) * 40 + dx];
+      int i = (8 * cy) * uw + dx;
+#pragma unroll
+      for (int ry = 0; ry < 8; ++ry, i += uw) {
+        // ry < 4: first tap row cy - 2 (c_ofs = -1); ry >= 4: first tap row cy - 1
+        const float r0 = ry < 4 ? tm2 : tm1, r1 = ry < 4 ? tm1 : t00, r2 = ry < 4 ? t00 : tp1, r3 = ry < 4 ? tp1 : tp2;
+        const float v = r0 * c_coef[ry][0] + (r1 * c_coef[ry][1] + (r2 * c_coef[ry][2] + r3 * c_coef[ry][3]));
+        if (v > best || (v == best && i < bidx)) { best = v; bidx = i; }
+      }
+    }
+  }
+#pragma unroll
+  for (int ofs = 16; ofs > 0; ofs >>= 1) {
+    const float ov = __shfl_xor_sync(kFull, best, ofs);
+    const int oi = __shfl_xor_sync(kFull, bidx, ofs);
+    if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+  }
+  const int ay = bidx / uw, ax = bidx - ay * uw;
+  X = 8 * x0 + ax; Y = 8 * y0 + ay; score = best;
+  __syncwarp();                  // `tmp` is rewritten by the next peak
+}
+
+// ------------------------------------------------------------------------------------------------
 // D1 + D2: peaks
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) peaks_kernel(const float* __restrict__ heat, PopnetDecodeParams p,
@@ -126,46 +183,18 @@ __global__ void __launch_bounds__(kThreads) peaks_kernel(const float* __restrict
 
   // refinement: one warp per peak
   float* tmp = s_tmp[warp];
+  const float hc0 = c_coef[lane & 7][0], hc1 = c_coef[lane & 7][1], hc2 = c_coef[lane & 7][2], hc3 = c_coef[lane & 7][3];
+  const int hofs = c_ofs[lane & 7];
   for (int pi = warp; pi < n; pi += kThreads / 32) {
-    const int cell = s_cell[pi];
-    const int y = cell / W, x = cell - y * W;
-    const int x0 = max(x - 2, 0), y0 = max(y - 2, 0), x1 = min(x + 2, W - 1), y1 = min(y + 2, H - 1);
-    const int pw = x1 - x0 + 1, ph = y1 - y0 + 1, uw = pw * 8, uh = ph * 8;
-    const float* patch = s_map + y0 * W + x0;
-    // horizontal pass: tmp[r][dx], r < ph, dx < uw
-    for (int i = lane; i < ph * uw; i += 32) {
-      const int r = i / uw, dx = i - r * uw;
-      const int rx = dx & 7, bx = (dx >> 3) + c_ofs[rx];
-      const float* row = patch + r * W;
-      tmp[r * 40 + dx] = ((row[clampi(bx - 1, 0, pw - 1)] * c_coef[rx][0] + row[clampi(bx, 0, pw - 1)] * c_coef[rx][1]) +
-                          row[clampi(bx + 1, 0, pw - 1)] * c_coef[rx][2]) + row[clampi(bx + 2, 0, pw - 1)] * c_coef[rx][3];
-    }
-    __syncwarp();
-    float best = -CUDART_INF_F;
-    int bidx = 0x7fffffff;
-    for (int i = lane; i < uh * uw; i += 32) {
-      const int dy = i / uw, dx = i - dy * uw;
-      const int ry = dy & 7, by = (dy >> 3) + c_ofs[ry];
-      const float v = tmp[clampi(by - 1, 0, ph - 1) * 40 + dx] * c_coef[ry][0] +
-                      (tmp[clampi(by, 0, ph - 1) * 40 + dx] * c_coef[ry][1] +
-                       (tmp[clampi(by + 1, 0, ph - 1) * 40 + dx] * c_coef[ry][2] +
-                        tmp[clampi(by + 2, 0, ph - 1) * 40 + dx] * c_coef[ry][3]));
-      if (v > best) { best = v; bidx = i; }          // ascending i per lane: first maximum
-    }
-#pragma unroll
-    for (int ofs = 16; ofs > 0; ofs >>= 1) {
-      const float ov = __shfl_xor_sync(kFull, best, ofs);
-      const int oi = __shfl_xor_sync(kFull, bidx, ofs);
-      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
-    }
+    int X, Y;
+    float best;
+    refine_peak(s_map, W, H, s_cell[pi], tmp, lane, hc0, hc1, hc2, hc3, hofs, X, Y, best);
     if (lane == 0) {
-      const int ay = bidx / uw, ax = bidx - ay * uw;
       const size_t slot = ((size_t)b * K + k) * MP + pi;
-      o.peak_xy[slot * 2] = (int16_t)(8 * x0 + ax);
-      o.peak_xy[slot * 2 + 1] = (int16_t)(8 * y0 + ay);
+      o.peak_xy[slot * 2] = (int16_t)X;
+      o.peak_xy[slot * 2 + 1] = (int16_t)Y;
       o.peak_score[slot] = best;
     }
-    __syncwarp();
   }
 }
 
@@ -186,6 +215,67 @@ __device__ __forceinline__ int line_point(int a, int b, int i, int n) {
   return (int)rint(v);
 }
 
+// Scores of one limb's candidate pairs (paf_to_pose.py:196-239) by `nwarps` warps (this is warp `warp` of them).
+// Lane = (pair, intermediate point): a warp takes 32 / NP pairs per round (3 for the reference's 10 points), every lane
+// evaluates ONE point of its pair -- two on-the-fly bicubic PAF samples and the dot product with the unit vector -- and parks
+// it in the warp's scratch; the pair's first lane then sums the NP values in NumPy's pairwise order, counts those above the
+// threshold and applies the length penalty.  (One lane per pair, as before, left 28 of 32 lanes idle for the typical 6 x 6
+// candidates and made the 20 samples of a pair a serial chain.)  s_score[i * pitch + j] = score or -inf (not a candidate).
+__device__ __forceinline__ void score_pairs(const float* __restrict__ s_px, const float* __restrict__ s_py, int W, int H,
+                                            const int16_t (*xa)[2], const int16_t (*xb)[2], int na, int nb, int NP,
+                                            double thresh_paf, double Hup, double* __restrict__ s_score, int pitch,
+                                            double* __restrict__ scratch, int warp, int nwarps, int lane) {
+  const int G = 32 / NP;                             // NP <= 32 (checked on the host): G >= 1
+  const int pl = lane / NP, t = lane - pl * NP;
+  const int npairs = na * nb;
+  const int body = NP & ~3;
+  for (int base = warp * G; base < npairs; base += nwarps * G) {
+    const int pr = base + pl;
+    const bool act = pl < G && pr < npairs;
+    int i = 0, j = 0;
+    double dist = 1.0, sv = 0.0;
+    if (act) {
+      i = pr / nb; j = pr - i * nb;
+      const int ax = xa[i][0], ay = xa[i][1], bx = xb[j][0], by = xb[j][1];
+      const double dx = (double)bx - (double)ax, dy = (double)by - (double)ay;
+      dist = sqrt(dx * dx + dy * dy) + 1e-8;
+      const double ux = dx / dist, uy = dy / dist;
+      const int X = line_point(ax, bx, t, NP), Y = line_point(ay, by, t, NP);
+      const double px = (double)bicubic_at(s_px, W, H, W, X, Y), py = (double)bicubic_at(s_py, W, H, W, X, Y);
+      // ndarray.dot -> OpenBLAS dgemv: vector body fma(px,ux,py*uy), scalar tail fma(py,uy,px*ux)
+      sv = (t < body) ? fma(px, ux, py * uy) : fma(py, uy, px * ux);
+    }
+    scratch[lane] = sv;
+    __syncwarp();
+    if (act && t == 0) {
+      const double* sp = scratch + pl * NP;
+      int above = 0;
+      for (int u = 0; u < NP; ++u) above += sp[u] > thresh_paf;
+      // np.mean: NumPy pairwise sum (plain loop below 8 elements, else 8 running sums + tail)
+      double sum;
+      if (NP < 8) {
+        sum = 0.0;
+        for (int u = 0; u < NP; ++u) sum += sp[u];
+      } else {
+        double r8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r8[u] = sp[u];
+        int u0 = 8;
+        for (; u0 + 8 <= NP; u0 += 8)
+#pragma unroll
+          for (int u = 0; u < 8; ++u) r8[u] += sp[u0 + u];
+        sum = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+        for (; u0 < NP; ++u0) sum += sp[u0];
+      }
+      double pen = 0.5 * Hup / dist - 1;
+      if (!(pen < 0)) pen = 0;
+      const double sc = sum / (double)NP + pen;
+      s_score[i * pitch + j] = ((double)above > 0.8 * (double)NP && sc > 0) ? sc : -CUDART_INF;
+    }
+    __syncwarp();
+  }
+}
+
 struct Best { double v; int idx; };
 
 __global__ void __launch_bounds__(kThreads) limbs_kernel(const float* __restrict__ paf, PopnetDecodeParams p,
@@ -204,7 +294,8 @@ __global__ void __launch_bounds__(kThreads) limbs_kernel(const float* __restrict
   double* s_score = reinterpret_cast<double*>(s_raw);                       // [na][nb]
   float* s_px = reinterpret_cast<float*>(s_raw + sizeof(double) * MP * MP); // [cells]
   float* s_py = s_px + cells;
-  __shared__ int16_t s_ax[POPNET_MAX_PEAKS], s_ay[POPNET_MAX_PEAKS], s_bx[POPNET_MAX_PEAKS], s_by[POPNET_MAX_PEAKS];
+  __shared__ int16_t s_xa[POPNET_MAX_PEAKS][2], s_xb[POPNET_MAX_PEAKS][2];
+  __shared__ double s_dot[kThreads / 32][32];
   __shared__ unsigned char s_used_a[POPNET_MAX_PEAKS], s_used_b[POPNET_MAX_PEAKS];
   __shared__ Best s_best[kThreads / 32];
 
@@ -212,53 +303,17 @@ __global__ void __launch_bounds__(kThreads) limbs_kernel(const float* __restrict
   for (int i = tid; i < cells; i += kThreads) { s_px[i] = mx[i]; s_py[i] = mx[cells + i]; }
   for (int i = tid; i < na; i += kThreads) {
     const int16_t* q = o.peak_xy + (((size_t)b * K + ta) * MP + i) * 2;
-    s_ax[i] = q[0]; s_ay[i] = q[1]; s_used_a[i] = 0;
+    s_xa[i][0] = q[0]; s_xa[i][1] = q[1]; s_used_a[i] = 0;
   }
   for (int i = tid; i < nb; i += kThreads) {
     const int16_t* q = o.peak_xy + (((size_t)b * K + tb) * MP + i) * 2;
-    s_bx[i] = q[0]; s_by[i] = q[1]; s_used_b[i] = 0;
+    s_xb[i][0] = q[0]; s_xb[i][1] = q[1]; s_used_b[i] = 0;
   }
   __syncthreads();
 
   const double Hup = (double)(H * p.stride);
   const int npairs = na * nb;
-  for (int pr = tid; pr < npairs; pr += kThreads) {
-    const int i = pr / nb, j = pr - i * nb;
-    const int ax = s_ax[i], ay = s_ay[i], bx = s_bx[j], by = s_by[j];
-    const double dx = (double)bx - (double)ax, dy = (double)by - (double)ay;
-    const double dist = sqrt(dx * dx + dy * dy) + 1e-8;
-    const double ux = dx / dist, uy = dy / dist;
-    double s[32];                                      // NP <= 32 (checked on the host)
-    int above = 0;
-    const int body = NP & ~3;
-    for (int t = 0; t < NP; ++t) {
-      const int X = line_point(ax, bx, t, NP), Y = line_point(ay, by, t, NP);
-      const double px = (double)bicubic_at(s_px, W, H, W, X, Y), py = (double)bicubic_at(s_py, W, H, W, X, Y);
-      // ndarray.dot -> OpenBLAS dgemv: vector body fma(px,ux,py*uy), scalar tail fma(py,uy,px*ux)
-      s[t] = (t < body) ? fma(px, ux, py * uy) : fma(py, uy, px * ux);
-      above += s[t] > p.thresh_paf;
-    }
-    // np.mean: NumPy pairwise sum (plain loop below 8 elements, else 8 running sums + tail)
-    double sum;
-    if (NP < 8) {
-      sum = 0.0;
-      for (int t = 0; t < NP; ++t) sum += s[t];
-    } else {
-      double r8[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) r8[t] = s[t];
-      int t = 8;
-      for (; t + 8 <= NP; t += 8)
-#pragma unroll
-        for (int u = 0; u < 8; ++u) r8[u] += s[t + u];
-      sum = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
-      for (; t < NP; ++t) sum += s[t];
-    }
-    double pen = 0.5 * Hup / dist - 1;
-    if (!(pen < 0)) pen = 0;
-    const double sc = sum / (double)NP + pen;
-    s_score[i * MP + j] = ((double)above > 0.8 * (double)NP && sc > 0) ? sc : -CUDART_INF;
-  }
+  score_pairs(s_px, s_py, W, H, s_xa, s_xb, na, nb, NP, p.thresh_paf, Hup, s_score, MP, s_dot[warp], warp, kThreads / 32, lane);
   __syncthreads();
 
   // Stable descending sort + greedy (paf_to_pose.py:241-261) == repeatedly take the best remaining
@@ -318,7 +373,6 @@ __device__ __forceinline__ float sum_pairwise_f32(const float* a, int n) {
   return r;
 }
 
-constexpr int kAsmThreads = 128;
 
 // Multi-GPU record push (PopnetPeerPush, include/popnet_b200.h): every record value is stored locally AND at the same
 // offset of this rank's chunk in every peer's gather buffer -- plain stores to peer-mapped memory (NVLink).
@@ -346,8 +400,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-__global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const float* __restrict__ heat, const float* __restrict__ depth,
-                                                               PopnetDecodeParams p, PopnetDecodeOut o, PopnetPeerPush push) {
+
+__device__ __forceinline__ PushCtx make_push_ctx(const PopnetPeerPush& push) {
   PushCtx pc;
   pc.world = push.world; pc.rank = push.rank;
   pc.local_chunk = nullptr;
@@ -356,166 +410,211 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const float* __re
       pc.peer_chunk[q] = static_cast<char*>(push.gather_base[q]) + (size_t)push.rank * push.records_bytes;
     pc.local_chunk = pc.peer_chunk[push.rank];
   }
-  __shared__ int16_t s_pj[POPNET_MAX_PERSONS][POPNET_MAX_JOINTS];
-  __shared__ double s_ps[POPNET_MAX_PERSONS];
-  __shared__ int s_pc[POPNET_MAX_PERSONS];
-  // the frame's connection lists and peaks, staged once by the whole CTA (the assembly itself is a serial chain
-  // of dependent steps; it must not pay a global-memory round trip per step)
-  __shared__ int s_nc[POPNET_MAX_LIMBS], s_npk[POPNET_MAX_JOINTS];
-  __shared__ int16_t s_ci[POPNET_MAX_LIMBS][POPNET_MAX_PEAKS][2];
-  __shared__ double s_cs[POPNET_MAX_LIMBS][POPNET_MAX_PEAKS];
-  __shared__ float s_pk[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS];
-  __shared__ int16_t s_xy[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS][2];
-  __shared__ int s_keep[POPNET_MAX_PERSONS];
-  __shared__ int s_nout;
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int K = p.num_joints, L = p.num_limbs, MP = p.max_peaks, MM = p.max_persons;
-  const int H = p.grid_h, W = p.grid_w, cells = H * W;
-  if (tid < L) s_nc[tid] = o.conn_count[(size_t)b * L + tid];
-  if (tid >= 32 && tid - 32 < K) s_npk[tid - 32] = o.peak_count[(size_t)b * K + tid - 32];
-  __syncthreads();
-  for (int i = tid; i < L * MP; i += kAsmThreads) {
-    const int l = i / MP, c = i - l * MP;
-    if (c < s_nc[l]) {
-      const size_t slot = ((size_t)b * L + l) * MP + c;
-      s_ci[l][c][0] = o.conn_ij[slot * 2];
-      s_ci[l][c][1] = o.conn_ij[slot * 2 + 1];
-      s_cs[l][c] = o.conn_score[slot];
-    }
-  }
-  for (int i = tid; i < K * MP; i += kAsmThreads) {
-    const int k = i / MP, c = i - k * MP;
-    if (c < s_npk[k]) {
-      const size_t ps = ((size_t)b * K + k) * MP + c;
-      s_pk[k][c] = o.peak_score[ps];
-      s_xy[k][c][0] = o.peak_xy[ps * 2];
-      s_xy[k][c][1] = o.peak_xy[ps * 2 + 1];
-    }
-  }
-  __syncthreads();
+  return pc;
+}
 
-  if (warp == 0) {
-    // ---- D5: serial assembly by one warp (paf_to_pose.py:267-351)
-    int np_ = 0;
-    unsigned flags = 0;
-    for (int l = 0; l < L; ++l) {
-      const int ta = p.limbs[l][0], tb = p.limbs[l][1];
-      const int nc = s_nc[l];
-      for (int c = 0; c < nc; ++c) {
-        const int ia = s_ci[l][c][0], ib = s_ci[l][c][1];
-        const double ls = s_cs[l][c];
+// publish (multi-GPU): when the LAST CTA of the grid has pushed its frames, tag this rank's slot in every rank's arrive[]
+// array.  Called by all threads of the CTA after their last record store.
+__device__ __forceinline__ void publish_push(const PopnetPeerPush& push) {
+  if (push.world <= 1) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(push.done_counter, 1u);
+    if (ticket == gridDim.x - 1) {
+      *push.done_counter = 0u;
+      const unsigned long long tag = *push.step + 1ull;
+      *push.step = tag;
+      __threadfence_system();
+      for (int q = 0; q < push.world; ++q) st_release_sys(push.arrive[q] + push.rank, tag);
+    }
+  }
+}
+
+// Shared-memory views of ONE frame's tables (row pitches in elements): what the assembly and the lift read and write.
+struct FrameTables {
+  double* cs;        // [L][MP]       connection scores
+  int16_t* ci;       // [L][MP][2]    connection (src peak, dst peak)
+  float* pk;         // [K][MP]       peak scores
+  int16_t* xy;       // [K][MP][2]    peak coordinates (upsampled pixels)
+  int* nc;           // [L]
+  int* npk;          // [K]
+  int16_t* pj;       // [MM][POPNET_MAX_JOINTS]  person -> peak index per joint type, -1 = none
+  double* ps;        // [MM]          person score
+  int* pc;           // [MM]          person joint count
+  int* keep;         // [MM]          surviving persons, in order
+  int MP;           // row pitch of the [..][MP] tables (elements)
+};
+
+// D5 + pruning by ONE warp (paf_to_pose.py:267-351): the frame's connections are taken limb by limb in list order; the
+// chain of dependent steps is what bounds a frame, so it is kept short:
+//   * lane c pre-loads connection c of the limb (ends, score, end-point peak scores) and the steps get them by shuffle -- no
+//     shared-memory load sits between two steps except the person rows themselves;
+//   * lane q OWNS person q (and q + 32): it tests its own row, and in the common step (exactly one person matches) the owner
+//     alone updates row, count and score -- no other lane reads them before the next warp-wide event, so no barrier;
+//   * merges and new persons touch rows across lanes and are fenced with __syncwarp().
+// Returns the number of surviving persons (T.keep[0..n)); *flags_out gets POPNET_FLAG_PERSON_OVERFLOW if the table filled.
+__device__ __forceinline__ int assemble_persons(const FrameTables& T, const PopnetDecodeParams& p, int lane, unsigned* flags_out) {
+  const int K = p.num_joints, L = p.num_limbs, MM = p.max_persons, MP = T.MP;
+  constexpr int PJ = POPNET_MAX_JOINTS;
+  int np_ = 0;
+  unsigned flags = 0;
+  for (int l = 0; l < L; ++l) {
+    const int ta = p.limbs[l][0], tb = p.limbs[l][1];
+    const int nc = T.nc[l];
+    for (int c0 = 0; c0 < nc; c0 += 32) {
+      int my_ia = 0, my_ib = 0;
+      double my_ls = 0.0, my_sa = 0.0, my_sb = 0.0;
+      if (c0 + lane < nc) {
+        const int c = l * MP + c0 + lane;
+        my_ia = T.ci[c * 2]; my_ib = T.ci[c * 2 + 1];
+        my_ls = T.cs[c];
+        my_sa = (double)T.pk[ta * MP + my_ia];
+        my_sb = (double)T.pk[tb * MP + my_ib];
+      }
+      const int n = min(32, nc - c0);
+      for (int c = 0; c < n; ++c) {
+        const int ia = __shfl_sync(kFull, my_ia, c), ib = __shfl_sync(kFull, my_ib, c);
+        const double ls = __shfl_sync(kFull, my_ls, c), sa = __shfl_sync(kFull, my_sa, c), sb = __shfl_sync(kFull, my_sb, c);
         // persons whose src or dst slot already holds this joint (paf_to_pose.py:285-287)
         unsigned long long hits = 0;
         for (int q0 = 0; q0 < np_; q0 += 32) {
           const int q = q0 + lane;
-          const bool h = q < np_ && (s_pj[q][ta] == ia || s_pj[q][tb] == ib);
+          const bool h = q < np_ && (T.pj[q * PJ + ta] == ia || T.pj[q * PJ + tb] == ib);
           hits |= (unsigned long long)__ballot_sync(kFull, h) << q0;
         }
         const int nh = __popcll(hits);
-        const double sb = (double)s_pk[tb][ib];
         if (nh == 1) {
           const int q = __ffsll((long long)hits) - 1;
-          if (lane == 0 && s_pj[q][tb] != ib) {
-            s_pj[q][tb] = (int16_t)ib;
-            s_pc[q] += 1;
-            s_ps[q] += sb + ls;
+          if (lane == (q & 31) && T.pj[q * PJ + tb] != ib) {
+            T.pj[q * PJ + tb] = (int16_t)ib;
+            T.pc[q] += 1;
+            T.ps[q] += sb + ls;
           }
         } else if (nh == 2) {
+          __syncwarp();                                   // the owners' updates are visible to the lanes that merge
           const int q1 = __ffsll((long long)hits) - 1;
           const int q2 = __ffsll((long long)(hits & (hits - 1))) - 1;
-          const bool ov = lane < K && s_pj[q1][lane] >= 0 && s_pj[q2][lane] >= 0;
+          const bool ov = lane < K && T.pj[q1 * PJ + lane] >= 0 && T.pj[q2 * PJ + lane] >= 0;
           if (!__any_sync(kFull, ov)) {
-            if (lane < K) s_pj[q1][lane] = (int16_t)(s_pj[q1][lane] + s_pj[q2][lane] + 1);
+            if (lane < K) T.pj[q1 * PJ + lane] = (int16_t)(T.pj[q1 * PJ + lane] + T.pj[q2 * PJ + lane] + 1);
             if (lane == 0) {
-              s_ps[q1] += s_ps[q2];
-              s_pc[q1] += s_pc[q2];
-              s_ps[q1] += ls;
+              T.ps[q1] += T.ps[q2];
+              T.pc[q1] += T.pc[q2];
+              T.ps[q1] += ls;
             }
             __syncwarp();
             for (int q = q2; q + 1 < np_; ++q) {        // list.pop(q2): later persons move up
-              if (lane < K) s_pj[q][lane] = s_pj[q + 1][lane];
-              if (lane == 0) { s_ps[q] = s_ps[q + 1]; s_pc[q] = s_pc[q + 1]; }
+              if (lane < K) T.pj[q * PJ + lane] = T.pj[(q + 1) * PJ + lane];
+              if (lane == 0) { T.ps[q] = T.ps[q + 1]; T.pc[q] = T.pc[q + 1]; }
               __syncwarp();
             }
             --np_;
           } else if (lane == 0) {
-            s_pj[q1][tb] = (int16_t)ib;
-            s_pc[q1] += 1;
-            s_ps[q1] += sb + ls;
+            T.pj[q1 * PJ + tb] = (int16_t)ib;
+            T.pc[q1] += 1;
+            T.ps[q1] += sb + ls;
           }
+          __syncwarp();
         } else {                                          // 0 or >= 3 matches: a new person
           if (np_ >= MM) flags |= POPNET_FLAG_PERSON_OVERFLOW;
           else {
-            if (lane < POPNET_MAX_JOINTS) s_pj[np_][lane] = (lane == ta) ? (int16_t)ia : (lane == tb) ? (int16_t)ib : (int16_t)-1;
+            if (lane < PJ) T.pj[np_ * PJ + lane] = (lane == ta) ? (int16_t)ia : (lane == tb) ? (int16_t)ib : (int16_t)-1;
             if (lane == 0) {
-              const double sa = (double)s_pk[ta][ia];
-              s_pc[np_] = 2;
-              s_ps[np_] = ((0 + sa) + sb) + ls;
+              T.pc[np_] = 2;
+              T.ps[np_] = ((0 + sa) + sb) + ls;
             }
             ++np_;
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
-    }
-    // prune (paf_to_pose.py:338-346): ordered compaction of the survivors
-    int nout = 0;
-    for (int q0 = 0; q0 < np_; q0 += 32) {
-      const int q = q0 + lane;
-      bool keep = false;
-      if (q < np_) {
-        const double cnt = (double)s_pc[q], sc = s_ps[q];
-        keep = !(cnt < 3 || sc / cnt < 0.2);
-      }
-      const unsigned bal = __ballot_sync(kFull, keep);
-      if (keep) s_keep[nout + __popc(bal & ((1u << lane) - 1u))] = q;
-      nout += __popc(bal);
-    }
-    if (lane == 0) {
-      s_nout = nout;
-      rec_store(pc, o.n_person + b, nout);
-      // the frame's flag word is complete here (peaks / limbs kernels have finished): fold in this kernel's bits
-      const uint32_t fl = o.flags[b] | flags;
-      rec_store(pc, o.flags + b, fl);
     }
   }
-  __syncthreads();
+  __syncwarp();
+  // prune (paf_to_pose.py:338-346): ordered compaction of the survivors
+  int nout = 0;
+  for (int q0 = 0; q0 < np_; q0 += 32) {
+    const int q = q0 + lane;
+    bool keep = false;
+    if (q < np_) {
+      const double cnt = (double)T.pc[q], sc = T.ps[q];
+      keep = !(cnt < 3 || sc / cnt < 0.2);
+    }
+    const unsigned bal = __ballot_sync(kFull, keep);
+    if (keep) T.keep[nout + __popc(bal & ((1u << lane) - 1u))] = q;
+    nout += __popc(bal);
+  }
+  __syncwarp();
+  *flags_out = flags;
+  return nout;
+}
 
-  // ---- D7..D9: every (surviving person, joint) pair is independent -> whole CTA
-  const int nout = s_nout;
-  for (int i = tid; i < nout; i += kAsmThreads) {
+// D7 .. D9 for the frame's `nout` surviving persons by threads t = tid, tid + nthreads, ...: every (person, joint) pair is
+// independent.  Heat-weighted depth over the clipped 3 x 3 window (common.py:272-293, fp32, NumPy pairwise order), rescale to
+// the original image, pinhole back-projection; all record values go through rec_store (local + peers).
+__device__ __forceinline__ void lift_and_store(const FrameTables& T, const PopnetDecodeParams& p, const PopnetDecodeOut& o,
+                                               const PushCtx& pc, const float* __restrict__ heat, const float* __restrict__ depth,
+                                               int b, int nout, int tid, int nthreads) {
+  const int K = p.num_joints, MP = T.MP, MM = p.max_persons;
+  const int H = p.grid_h, W = p.grid_w, cells = H * W;
+  constexpr int PJ = POPNET_MAX_JOINTS;
+  for (int i = tid; i < nout; i += nthreads) {
     const size_t row = (size_t)b * MM + i;
-    const int q = s_keep[i];
-    if (o.person_score) rec_store(pc, o.person_score + row, s_ps[q]);
-    if (o.person_njoint) rec_store(pc, o.person_njoint + row, (int32_t)s_pc[q]);
+    const int q = T.keep[i];
+    if (o.person_score) rec_store(pc, o.person_score + row, T.ps[q]);
+    if (o.person_njoint) rec_store(pc, o.person_njoint + row, (int32_t)T.pc[q]);
   }
-  for (int i = tid; i < nout * K; i += kAsmThreads) {
+  for (int i = tid; i < nout * K; i += nthreads) {
     const int pi_ = i / K, k = i - pi_ * K;
-    const int q = s_keep[pi_], idx = s_pj[q][k];
+    const int q = T.keep[pi_], idx = T.pj[q * PJ + k];
     const size_t row = (size_t)b * MM + pi_;
     if (o.person_peak) rec_store(pc, o.person_peak + row * K + k, (int16_t)idx);
     double x2 = -1, y2 = -1, Z = -1, conf = 0;
     if (idx >= 0) {
-      const int X = s_xy[k][idx][0], Y = s_xy[k][idx][1];
-      conf = (double)s_pk[k][idx];
-      if (depth) {                                     // common.py:272-293, fp32, NumPy pairwise order
+      const int X = T.xy[(k * MP + idx) * 2], Y = T.xy[(k * MP + idx) * 2 + 1];
+      conf = (double)T.pk[k * MP + idx];
+      if (depth) {
         const int cx = X / p.stride, cy = Y / p.stride;
-        const int x0 = clampi(cx - 1, 0, W - 1), x1 = clampi(cx + 1, 0, W - 1);
-        const int y0 = clampi(cy - 1, 0, H - 1), y1 = clampi(cy + 1, 0, H - 1);
         const float* hm = heat + ((size_t)b * (K + 1) + k) * cells;
         const float* dm = depth + ((size_t)b * (p.depth_channels > 0 ? p.depth_channels : K) + k) * cells;
-        float wv[9], dv[9];
-        int n = 0;
-        for (int yy = y0; yy <= y1; ++yy)
-          for (int xx = x0; xx <= x1; ++xx) {
-            float hv = hm[yy * W + xx];
-            if (hv < 0) hv = 0;
-            const float w = hv + 0.000000001f;
-            float d = dm[yy * W + xx] * p.depth_std;
-            d = d + p.depth_mean;
-            wv[n] = w; dv[n] = d * w; ++n;
+        if (cx >= 1 && cx <= W - 2 && cy >= 1 && cy <= H - 2) {
+          // interior window (the usual case): all 18 loads are issued before the first use
+          float hv[9], dd[9];
+#pragma unroll
+          for (int u = 0; u < 9; ++u) {
+            const int at = (cy - 1 + u / 3) * W + cx - 1 + u % 3;
+            hv[u] = __ldg(hm + at); dd[u] = __ldg(dm + at);
           }
-        Z = (double)(sum_pairwise_f32(dv, n) / sum_pairwise_f32(wv, n));
+          float wv[9], dv[9];
+#pragma unroll
+          for (int u = 0; u < 9; ++u) {
+            float h = hv[u];
+            if (h < 0) h = 0;
+            const float w = h + 0.000000001f;
+            float d = dd[u] * p.depth_std;
+            d = d + p.depth_mean;
+            wv[u] = w; dv[u] = d * w;
+          }
+          const float sd = (((dv[0] + dv[1]) + (dv[2] + dv[3])) + ((dv[4] + dv[5]) + (dv[6] + dv[7]))) + dv[8];
+          const float sw = (((wv[0] + wv[1]) + (wv[2] + wv[3])) + ((wv[4] + wv[5]) + (wv[6] + wv[7]))) + wv[8];
+          Z = (double)(sd / sw);
+        } else {
+          const int x0 = clampi(cx - 1, 0, W - 1), x1 = clampi(cx + 1, 0, W - 1);
+          const int y0 = clampi(cy - 1, 0, H - 1), y1 = clampi(cy + 1, 0, H - 1);
+          float wv[9], dv[9];
+          int n = 0;
+          for (int yy = y0; yy <= y1; ++yy)
+            for (int xx = x0; xx <= x1; ++xx) {
+              float hv = hm[yy * W + xx];
+              if (hv < 0) hv = 0;
+              const float w = hv + 0.000000001f;
+              float d = dm[yy * W + xx] * p.depth_std;
+              d = d + p.depth_mean;
+              wv[n] = w; dv[n] = d * w; ++n;
+            }
+          Z = (double)(sum_pairwise_f32(dv, n) / sum_pairwise_f32(wv, n));
+        }
       }
       x2 = (double)X / p.input_size * p.w_org;
       y2 = (double)Y / p.input_size * p.h_org;
@@ -529,21 +628,111 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const float* __re
       rec_store(pc, d3, X3); rec_store(pc, d3 + 1, Y3); rec_store(pc, d3 + 2, Z);
     }
   }
-  if (push.world > 1) {
-    // publish: when the LAST CTA of the batch has pushed its frame, tag this rank's slot in every rank's arrive[] array
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned int ticket = atomicAdd(push.done_counter, 1u);
-      if (ticket == gridDim.x - 1) {
-        *push.done_counter = 0u;
-        const unsigned long long tag = *push.step + 1ull;
-        *push.step = tag;
-        __threadfence_system();
-        for (int q = 0; q < push.world; ++q) st_release_sys(push.arrive[q] + push.rank, tag);
-      }
+}
+
+// bytes of one frame's tables in the assembly kernel's dynamic shared memory (8-byte fields first)
+__host__ __device__ inline size_t asm_frame_bytes(int K, int L, int MP, int MM) {
+  size_t n = 0;
+  n += (size_t)L * MP * sizeof(double);                  // cs
+  n += (size_t)MM * sizeof(double);                      // ps
+  n += (size_t)K * MP * sizeof(float);                   // pk
+  n += (size_t)(MM + MM + L + K) * sizeof(int);          // pc, keep, nc, npk
+  n += (size_t)L * MP * 2 * sizeof(int16_t);             // ci
+  n += (size_t)K * MP * 2 * sizeof(int16_t);             // xy
+  n += (size_t)MM * POPNET_MAX_JOINTS * sizeof(int16_t); // pj
+  return (n + 15) & ~(size_t)15;
+}
+
+// One WARP per frame, `blockDim.x / 32` frames per CTA: the assembly of a frame is a serial chain that one warp runs at
+// its latency; what counts is how many SMs the kernel holds while it does so (its CTAs share the GPU with the next
+// batch's convolutions, which cannot co-reside with anything: they fill the register file).  Eight frames per CTA: a batch
+// of 64 is 8 CTAs instead of 64.
+__global__ void __launch_bounds__(256) assemble_kernel(const float* __restrict__ heat, const float* __restrict__ depth, int batch,
+                                                       PopnetDecodeParams p, PopnetDecodeOut o, PopnetPeerPush push,
+                                                       unsigned int frame_bytes) {
+  extern __shared__ __align__(16) unsigned char s_asm[];
+  const PushCtx pc = make_push_ctx(push);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K = p.num_joints, L = p.num_limbs, MP = p.max_peaks, MM = p.max_persons;
+  const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (b < batch) {
+    FrameTables T;
+    unsigned char* base = s_asm + (size_t)warp * frame_bytes;
+    T.cs = reinterpret_cast<double*>(base); base += (size_t)L * MP * sizeof(double);
+    T.ps = reinterpret_cast<double*>(base); base += (size_t)MM * sizeof(double);
+    T.pk = reinterpret_cast<float*>(base); base += (size_t)K * MP * sizeof(float);
+    T.pc = reinterpret_cast<int*>(base); base += (size_t)MM * sizeof(int);
+    T.keep = reinterpret_cast<int*>(base); base += (size_t)MM * sizeof(int);
+    T.nc = reinterpret_cast<int*>(base); base += (size_t)L * sizeof(int);
+    T.npk = reinterpret_cast<int*>(base); base += (size_t)K * sizeof(int);
+    T.ci = reinterpret_cast<int16_t*>(base); base += (size_t)L * MP * 2 * sizeof(int16_t);
+    T.xy = reinterpret_cast<int16_t*>(base); base += (size_t)K * MP * 2 * sizeof(int16_t);
+    T.pj = reinterpret_cast<int16_t*>(base);
+    T.MP = MP;
+    // ---- stage the frame's connection lists and peaks (written by the two kernels before this one).  Items are (list,
+    // entry) pairs up to the longest list; four per lane are LOADED before the first is stored, so a round costs one
+    // global-memory latency, not four.
+    int mc = 0, mk = 0;
+    for (int l = lane; l < L; l += 32) { const int v = o.conn_count[(size_t)b * L + l]; T.nc[l] = v; mc = max(mc, v); }
+    for (int k = lane; k < K; k += 32) { const int v = o.peak_count[(size_t)b * K + k]; T.npk[k] = v; mk = max(mk, v); }
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+      mc = max(mc, __shfl_xor_sync(kFull, mc, ofs));
+      mk = max(mk, __shfl_xor_sync(kFull, mk, ofs));
     }
+    __syncwarp();
+    for (int i0 = 0; i0 < L * mc; i0 += 128) {
+      int cij[4]; double csv[4]; int at[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        at[u] = -1;
+        if (i < L * mc) {
+          const int l = i / mc, c = i - l * mc;
+          if (c < T.nc[l]) {
+            const size_t slot = ((size_t)b * L + l) * MP + c;
+            at[u] = l * MP + c;
+            cij[u] = *reinterpret_cast<const int*>(o.conn_ij + slot * 2);
+            csv[u] = o.conn_score[slot];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (at[u] >= 0) { *reinterpret_cast<int*>(T.ci + at[u] * 2) = cij[u]; T.cs[at[u]] = csv[u]; }
+    }
+    for (int i0 = 0; i0 < K * mk; i0 += 128) {
+      int pxy[4]; float pkv[4]; int at[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        at[u] = -1;
+        if (i < K * mk) {
+          const int k = i / mk, c = i - k * mk;
+          if (c < T.npk[k]) {
+            const size_t slot = ((size_t)b * K + k) * MP + c;
+            at[u] = k * MP + c;
+            pxy[u] = *reinterpret_cast<const int*>(o.peak_xy + slot * 2);
+            pkv[u] = o.peak_score[slot];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (at[u] >= 0) { *reinterpret_cast<int*>(T.xy + at[u] * 2) = pxy[u]; T.pk[at[u]] = pkv[u]; }
+    }
+    __syncwarp();
+    unsigned flags = 0;
+    const int nout = assemble_persons(T, p, lane, &flags);
+    if (lane == 0) {
+      rec_store(pc, o.n_person + b, nout);
+      // the frame's flag word is complete here (peaks / limbs kernels have finished): fold in this kernel's bits
+      const uint32_t fl = o.flags[b] | flags;
+      rec_store(pc, o.flags + b, fl);
+    }
+    lift_and_store(T, p, o, pc, heat, depth, b, nout, lane, 32);
   }
+  publish_push(push);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -574,6 +763,7 @@ struct FusedFixed {                              // small per-frame tables (one 
   double ps[POPNET_MAX_PERSONS];
   float pk[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS];
   float tmp[kFusedWarps][5 * 40];
+  double dot[kFusedWarps][32];
   int cell[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS];
   int pc[POPNET_MAX_PERSONS], keep[POPNET_MAX_PERSONS];
   int nc[POPNET_MAX_LIMBS], npk[POPNET_MAX_JOINTS], off[POPNET_MAX_LIMBS + 1];
@@ -612,16 +802,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_fused_kernel(const fl
   float* s_paf = reinterpret_cast<float*>(s_dyn + lay.paf);
   FusedFixed& S = *reinterpret_cast<FusedFixed*>(s_dyn + lay.fixed);
 
-  PushCtx pc;
-  pc.world = push.world; pc.rank = push.rank;
-  pc.local_chunk = nullptr;
-  if (push.world > 1) {
-    for (int q = 0; q < push.world; ++q)
-      pc.peer_chunk[q] = static_cast<char*>(push.gather_base[q]) + (size_t)push.rank * push.records_bytes;
-    pc.local_chunk = pc.peer_chunk[push.rank];
-  }
+  const PushCtx pc = make_push_ctx(push);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int K = p.num_joints, L = p.num_limbs, MP = p.max_peaks, MM = p.max_persons, NP = p.num_intermed_pts;
+  const int K = p.num_joints, L = p.num_limbs, MP = p.max_peaks, NP = p.num_intermed_pts;
   const int H = p.grid_h, W = p.grid_w, cells = H * W;
   const int dch = p.depth_channels > 0 ? p.depth_channels : K;
 
@@ -677,50 +860,21 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_fused_kernel(const fl
       int total = 0;
       for (int k = 0; k < K; ++k) total += S.npk[k];
       float* tmp = S.tmp[warp];
+      const float hc0 = c_coef[lane & 7][0], hc1 = c_coef[lane & 7][1], hc2 = c_coef[lane & 7][2], hc3 = c_coef[lane & 7][3];
+      const int hofs = c_ofs[lane & 7];
       for (int t = warp; t < total; t += kFusedWarps) {
         int k = 0, pi = t;
         while (pi >= S.npk[k]) { pi -= S.npk[k]; ++k; }
-        const float* s_map = s_heat + (size_t)k * cells;
-        const int cell = S.cell[k][pi];
-        const int y = cell / W, x = cell - y * W;
-        const int x0 = max(x - 2, 0), y0 = max(y - 2, 0), x1 = min(x + 2, W - 1), y1 = min(y + 2, H - 1);
-        const int pw = x1 - x0 + 1, ph = y1 - y0 + 1, uw = pw * 8, uh = ph * 8;
-        const float* patch = s_map + y0 * W + x0;
-        for (int i = lane; i < ph * uw; i += 32) {
-          const int r = i / uw, dx = i - r * uw;
-          const int rx = dx & 7, bx = (dx >> 3) + c_ofs[rx];
-          const float* row = patch + r * W;
-          tmp[r * 40 + dx] = ((row[clampi(bx - 1, 0, pw - 1)] * c_coef[rx][0] + row[clampi(bx, 0, pw - 1)] * c_coef[rx][1]) +
-                              row[clampi(bx + 1, 0, pw - 1)] * c_coef[rx][2]) + row[clampi(bx + 2, 0, pw - 1)] * c_coef[rx][3];
-        }
-        __syncwarp();
-        float best = -CUDART_INF_F;
-        int bidx = 0x7fffffff;
-        for (int i = lane; i < uh * uw; i += 32) {
-          const int dy = i / uw, dx = i - dy * uw;
-          const int ry = dy & 7, by = (dy >> 3) + c_ofs[ry];
-          const float v = tmp[clampi(by - 1, 0, ph - 1) * 40 + dx] * c_coef[ry][0] +
-                          (tmp[clampi(by, 0, ph - 1) * 40 + dx] * c_coef[ry][1] +
-                           (tmp[clampi(by + 1, 0, ph - 1) * 40 + dx] * c_coef[ry][2] +
-                            tmp[clampi(by + 2, 0, ph - 1) * 40 + dx] * c_coef[ry][3]));
-          if (v > best) { best = v; bidx = i; }
-        }
-#pragma unroll
-        for (int ofs = 16; ofs > 0; ofs >>= 1) {
-          const float ov = __shfl_xor_sync(kFull, best, ofs);
-          const int oi = __shfl_xor_sync(kFull, bidx, ofs);
-          if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
-        }
+        int X, Y;
+        float best;
+        refine_peak(s_heat + (size_t)k * cells, W, H, S.cell[k][pi], tmp, lane, hc0, hc1, hc2, hc3, hofs, X, Y, best);
         if (lane == 0) {
-          const int ay = bidx / uw, ax = bidx - ay * uw;
-          const int16_t X = (int16_t)(8 * x0 + ax), Y = (int16_t)(8 * y0 + ay);
-          S.xy[k][pi][0] = X; S.xy[k][pi][1] = Y; S.pk[k][pi] = best;
+          S.xy[k][pi][0] = (int16_t)X; S.xy[k][pi][1] = (int16_t)Y; S.pk[k][pi] = best;
           const size_t slot = ((size_t)b * K + k) * MP + pi;
-          o.peak_xy[slot * 2] = X;
-          o.peak_xy[slot * 2 + 1] = Y;
+          o.peak_xy[slot * 2] = (int16_t)X;
+          o.peak_xy[slot * 2 + 1] = (int16_t)Y;
           o.peak_score[slot] = best;
         }
-        __syncwarp();
       }
     }
     // ---- D: PAF maps -> shared memory (they do not overlap the heat region, which phase C may still be reading)
@@ -762,42 +916,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_fused_kernel(const fl
         unsigned char* used_b = S.used[warp][1];
         for (int i = lane; i < POPNET_MAX_PEAKS; i += 32) { used_a[i] = 0; used_b[i] = 0; }
         const int npairs = na * nb;
-        for (int pr = lane; pr < npairs; pr += 32) {
-          const int i = pr / nb, j = pr - i * nb;
-          const int ax = S.xy[ta][i][0], ay = S.xy[ta][i][1], bx = S.xy[tb][j][0], by = S.xy[tb][j][1];
-          const double dx = (double)bx - (double)ax, dy = (double)by - (double)ay;
-          const double dist = sqrt(dx * dx + dy * dy) + 1e-8;
-          const double ux = dx / dist, uy = dy / dist;
-          double s[32];
-          int above = 0;
-          const int body = NP & ~3;
-          for (int t = 0; t < NP; ++t) {
-            const int X = line_point(ax, bx, t, NP), Y = line_point(ay, by, t, NP);
-            const double px = (double)bicubic_at(s_px, W, H, W, X, Y), py = (double)bicubic_at(s_py, W, H, W, X, Y);
-            s[t] = (t < body) ? fma(px, ux, py * uy) : fma(py, uy, px * ux);
-            above += s[t] > p.thresh_paf;
-          }
-          double sum;
-          if (NP < 8) {
-            sum = 0.0;
-            for (int t = 0; t < NP; ++t) sum += s[t];
-          } else {
-            double r8[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) r8[t] = s[t];
-            int t = 8;
-            for (; t + 8 <= NP; t += 8)
-#pragma unroll
-              for (int u = 0; u < 8; ++u) r8[u] += s[t + u];
-            sum = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
-            for (; t < NP; ++t) sum += s[t];
-          }
-          double pen = 0.5 * Hup / dist - 1;
-          if (!(pen < 0)) pen = 0;
-          const double sc = sum / (double)NP + pen;
-          s_score[pr] = ((double)above > 0.8 * (double)NP && sc > 0) ? sc : -CUDART_INF;
-        }
-        __syncwarp();
+        score_pairs(s_px, s_py, W, H, S.xy[ta], S.xy[tb], na, nb, NP, p.thresh_paf, Hup, s_score, nb, S.dot[warp], 0, 1, lane);
         // greedy: repeatedly the best remaining pair whose ends are both free, ties to the smallest (i, j)
         const int maxc = min(na, nb);
         int nconn = 0;
@@ -835,154 +954,26 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_fused_kernel(const fl
       l0 = l1;
     }
 
-    // ---- E: serial assembly by warp 0 (paf_to_pose.py:267-351), as in assemble_kernel
+    // ---- E: serial assembly by warp 0 (paf_to_pose.py:267-351), F: lift + records by the whole CTA -- the functions
+    // the three-kernel schedule's assemble_kernel runs
+    FrameTables T;
+    T.cs = &S.cs[0][0]; T.ci = &S.ci[0][0][0]; T.pk = &S.pk[0][0]; T.xy = &S.xy[0][0][0];
+    T.nc = S.nc; T.npk = S.npk; T.pj = &S.pj[0][0]; T.ps = S.ps; T.pc = S.pc; T.keep = S.keep;
+    T.MP = POPNET_MAX_PEAKS;
     if (warp == 0) {
-      int np_ = 0;
       unsigned flags = 0;
-      for (int l = 0; l < L; ++l) {
-        const int ta = p.limbs[l][0], tb = p.limbs[l][1];
-        const int nc = S.nc[l];
-        for (int c = 0; c < nc; ++c) {
-          const int ia = S.ci[l][c][0], ib = S.ci[l][c][1];
-          const double ls = S.cs[l][c];
-          unsigned long long hits = 0;
-          for (int q0 = 0; q0 < np_; q0 += 32) {
-            const int q = q0 + lane;
-            const bool h = q < np_ && (S.pj[q][ta] == ia || S.pj[q][tb] == ib);
-            hits |= (unsigned long long)__ballot_sync(kFull, h) << q0;
-          }
-          const int nh = __popcll(hits);
-          const double sb = (double)S.pk[tb][ib];
-          if (nh == 1) {
-            const int q = __ffsll((long long)hits) - 1;
-            if (lane == 0 && S.pj[q][tb] != ib) {
-              S.pj[q][tb] = (int16_t)ib;
-              S.pc[q] += 1;
-              S.ps[q] += sb + ls;
-            }
-          } else if (nh == 2) {
-            const int q1 = __ffsll((long long)hits) - 1;
-            const int q2 = __ffsll((long long)(hits & (hits - 1))) - 1;
-            const bool ov = lane < K && S.pj[q1][lane] >= 0 && S.pj[q2][lane] >= 0;
-            if (!__any_sync(kFull, ov)) {
-              if (lane < K) S.pj[q1][lane] = (int16_t)(S.pj[q1][lane] + S.pj[q2][lane] + 1);
-              if (lane == 0) {
-                S.ps[q1] += S.ps[q2];
-                S.pc[q1] += S.pc[q2];
-                S.ps[q1] += ls;
-              }
-              __syncwarp();
-              for (int q = q2; q + 1 < np_; ++q) {
-                if (lane < K) S.pj[q][lane] = S.pj[q + 1][lane];
-                if (lane == 0) { S.ps[q] = S.ps[q + 1]; S.pc[q] = S.pc[q + 1]; }
-                __syncwarp();
-              }
-              --np_;
-            } else if (lane == 0) {
-              S.pj[q1][tb] = (int16_t)ib;
-              S.pc[q1] += 1;
-              S.ps[q1] += sb + ls;
-            }
-          } else {
-            if (np_ >= MM) flags |= POPNET_FLAG_PERSON_OVERFLOW;
-            else {
-              if (lane < POPNET_MAX_JOINTS) S.pj[np_][lane] = (lane == ta) ? (int16_t)ia : (lane == tb) ? (int16_t)ib : (int16_t)-1;
-              if (lane == 0) {
-                const double sa = (double)S.pk[ta][ia];
-                S.pc[np_] = 2;
-                S.ps[np_] = ((0 + sa) + sb) + ls;
-              }
-              ++np_;
-            }
-          }
-          __syncwarp();
-        }
-      }
-      int nout = 0;
-      for (int q0 = 0; q0 < np_; q0 += 32) {
-        const int q = q0 + lane;
-        bool keep = false;
-        if (q < np_) {
-          const double cnt = (double)S.pc[q], sc = S.ps[q];
-          keep = !(cnt < 3 || sc / cnt < 0.2);
-        }
-        const unsigned bal = __ballot_sync(kFull, keep);
-        if (keep) S.keep[nout + __popc(bal & ((1u << lane) - 1u))] = q;
-        nout += __popc(bal);
-      }
+      const int n = assemble_persons(T, p, lane, &flags);
       if (lane == 0) {
-        S.nout = nout;
-        rec_store(pc, o.n_person + b, nout);
+        S.nout = n;
+        rec_store(pc, o.n_person + b, n);
         rec_store(pc, o.flags + b, (uint32_t)(S.flags | flags));
       }
     }
     __syncthreads();
-
-    // ---- F: lift, rescale, back-projection, records (assemble_kernel's tail)
-    const int nout = S.nout;
-    for (int i = tid; i < nout; i += kFusedThreads) {
-      const size_t row = (size_t)b * MM + i;
-      const int q = S.keep[i];
-      if (o.person_score) rec_store(pc, o.person_score + row, S.ps[q]);
-      if (o.person_njoint) rec_store(pc, o.person_njoint + row, (int32_t)S.pc[q]);
-    }
-    for (int i = tid; i < nout * K; i += kFusedThreads) {
-      const int pi_ = i / K, k = i - pi_ * K;
-      const int q = S.keep[pi_], idx = S.pj[q][k];
-      const size_t row = (size_t)b * MM + pi_;
-      if (o.person_peak) rec_store(pc, o.person_peak + row * K + k, (int16_t)idx);
-      double x2 = -1, y2 = -1, Z = -1, conf = 0;
-      if (idx >= 0) {
-        const int X = S.xy[k][idx][0], Y = S.xy[k][idx][1];
-        conf = (double)S.pk[k][idx];
-        if (depth) {
-          const int cx = X / p.stride, cy = Y / p.stride;
-          const int x0 = clampi(cx - 1, 0, W - 1), x1 = clampi(cx + 1, 0, W - 1);
-          const int y0 = clampi(cy - 1, 0, H - 1), y1 = clampi(cy + 1, 0, H - 1);
-          const float* hm = heat + ((size_t)b * (K + 1) + k) * cells;
-          const float* dm = depth + ((size_t)b * dch + k) * cells;
-          float wv[9], dv[9];
-          int n = 0;
-          for (int yy = y0; yy <= y1; ++yy)
-            for (int xx = x0; xx <= x1; ++xx) {
-              float hv = hm[yy * W + xx];
-              if (hv < 0) hv = 0;
-              const float w = hv + 0.000000001f;
-              float d = dm[yy * W + xx] * p.depth_std;
-              d = d + p.depth_mean;
-              wv[n] = w; dv[n] = d * w; ++n;
-            }
-          Z = (double)(sum_pairwise_f32(dv, n) / sum_pairwise_f32(wv, n));
-        }
-        x2 = (double)X / p.input_size * p.w_org;
-        y2 = (double)Y / p.input_size * p.h_org;
-      }
-      if (o.pose2d) { rec_store(pc, o.pose2d + (row * K + k) * 2, x2); rec_store(pc, o.pose2d + (row * K + k) * 2 + 1, y2); }
-      if (o.pose_conf) rec_store(pc, o.pose_conf + row * K + k, conf);
-      if (o.pose3d && depth) {
-        double X3 = (x2 - p.cx) * Z / p.fx, Y3 = (y2 - p.cy) * Z / p.fy;
-        if (p.flip_y) Y3 = -Y3;
-        double* d3 = o.pose3d + (row * K + k) * 3;
-        rec_store(pc, d3, X3); rec_store(pc, d3 + 1, Y3); rec_store(pc, d3 + 2, Z);
-      }
-    }
+    lift_and_store(T, p, o, pc, heat, depth, b, S.nout, tid, kFusedThreads);
     __syncthreads();                      // the tables are rewritten by the next frame
   }
-  if (push.world > 1) {
-    // publish: when the LAST CTA of the grid has pushed its frames, tag this rank's slot in every rank's arrive[] array
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned int ticket = atomicAdd(push.done_counter, 1u);
-      if (ticket == gridDim.x - 1) {
-        *push.done_counter = 0u;
-        const unsigned long long tag = *push.step + 1ull;
-        *push.step = tag;
-        __threadfence_system();
-        for (int q = 0; q < push.world; ++q) st_release_sys(push.arrive[q] + push.rank, tag);
-      }
-    }
-  }
+  publish_push(push);
 }
 
 // one warp: lane q waits for rank q's tag of the current step (bounded: a dead peer sets *status instead of hanging)
@@ -1085,6 +1076,8 @@ int decode_impl(const float* heat, const float* paf, const float* depth, int bat
   if (!o->peak_count || !o->peak_xy || !o->peak_score || !o->conn_count || !o->conn_ij || !o->conn_score ||
       !o->n_person || !o->flags)
     return POPNET_ERR_INVALID_ARG;
+  // (x, y) / (src, dst) int16 pairs are moved as one 32-bit word
+  if ((reinterpret_cast<uintptr_t>(o->peak_xy) & 3u) || (reinterpret_cast<uintptr_t>(o->conn_ij) & 3u)) return POPNET_ERR_INVALID_ARG;
   if (p->num_joints < 1 || p->num_joints > POPNET_MAX_JOINTS || p->num_limbs < 1 || p->num_limbs > POPNET_MAX_LIMBS ||
       p->stride != 8 || p->max_peaks < 1 || p->max_peaks > POPNET_MAX_PEAKS || p->max_persons < 1 ||
       p->max_persons > POPNET_MAX_PERSONS || p->grid_h < 1 || p->grid_w < 1 || p->grid_h * p->grid_w > kMaxCells ||
@@ -1124,7 +1117,15 @@ int decode_impl(const float* heat, const float* paf, const float* depth, int bat
   POPNET_AFTER_LAUNCH();
   limbs_kernel<<<dim3(p->num_limbs, batch), kThreads, smem_limbs, st>>>(paf, *p, *o);
   POPNET_AFTER_LAUNCH();
-  assemble_kernel<<<batch, kAsmThreads, 0, st>>>(heat, depth, *p, *o, pp);
+  {
+    // frames per CTA (one warp each): as many as fit into 200 KB of tables, at most 8
+    const size_t fb = asm_frame_bytes(p->num_joints, p->num_limbs, p->max_peaks, p->max_persons);
+    int fpc = 8;
+    while (fpc > 1 && fb * fpc > 200 * 1024) fpc >>= 1;
+    if (fb * fpc > 48 * 1024)
+      POPNET_CUDA_TRY(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fb * fpc)));
+    assemble_kernel<<<(batch + fpc - 1) / fpc, 32 * fpc, fb * fpc, st>>>(heat, depth, batch, *p, *o, pp, (unsigned int)fb);
+  }
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;
 }

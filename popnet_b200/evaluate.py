@@ -27,7 +27,8 @@ import numpy as np
 from . import _abi
 
 __all__ = ["eval_human_dataset_2d", "eval_human_dataset_2d_PCKh", "eval_human_dataset_3d",
-           "eval_ap_mpii_v2", "eval_ap_3D", "match_counts", "pack_humans", "Packed"]
+           "eval_ap_mpii_v2", "eval_ap_3D", "eval_ap_3D_sharded", "eval_ap_mpii_v2_sharded", "match_counts", "pack_humans",
+           "Packed"]
 
 _backend = None   # object with .pck(arrs, dist_th, iou_th, K) and .map_assign(arrs, thresh, K, D)
 
@@ -348,3 +349,29 @@ def eval_ap_3D(humans_pred_set, conf_pred_set, humans_gt_set, gt_visibility_set,
     out, conf = _assign(humans_pred_set, conf_in, humans_gt_set, vis_in, _ALL_ONES, K, 3, thresh)
     ap = _ap_from_labels(out, conf, joint_names)
     return (ap, out) if _return_counts else ap
+
+
+def eval_ap_3D_sharded(humans_pred_shard, conf_pred_shard, humans_gt_shard, gt_visibility_shard, joint_names, thresh=0.1,
+                       group=None):
+    """eval_ap_3D over a data set sharded across the ranks of a process group (contiguous frame shards,
+    pipeline.shard): GT assignment on each rank's shard (device), then ``pipeline.gather_ap_rows`` and the AP tail on the
+    gathered rows.  Every rank returns the AP vector of the WHOLE set, equal to the single-process eval_ap_3D's
+    (util/eval_mAP.py:335-395 on the concatenated lists)."""
+    from . import pipeline
+    K = len(joint_names)
+    conf_in, vis_in = _fill_defaults(humans_pred_shard, conf_pred_shard, humans_gt_shard, gt_visibility_shard, K)
+    out, conf = _assign(humans_pred_shard, conf_in, humans_gt_shard, vis_in, _ALL_ONES, K, 3, thresh)
+    conf_all, labels_all, n_gt = pipeline.gather_ap_rows(conf, out["labels"], out["n_gt"], group)
+    return _ap_from_labels({"labels": labels_all, "n_gt": n_gt}, conf_all, joint_names)
+
+
+def eval_ap_mpii_v2_sharded(humans_pred_shard, conf_pred_shard, humans_gt_shard, gt_visibility_shard, head_id, neck_id,
+                            joint_names, thresh=0.5, group=None):
+    """eval_ap_mpii_v2 (util/eval_mAP.py:272-332) over contiguous frame shards; see eval_ap_3D_sharded."""
+    from . import pipeline
+    K = len(joint_names)
+    ref_dist_set = [_head_sizes([g], head_id, neck_id) for g in humans_gt_shard]
+    conf_in, vis_in = _fill_defaults(humans_pred_shard, conf_pred_shard, humans_gt_shard, gt_visibility_shard, K)
+    out, conf = _assign(humans_pred_shard, conf_in, humans_gt_shard, vis_in, ref_dist_set, K, 2, thresh)
+    conf_all, labels_all, n_gt = pipeline.gather_ap_rows(conf, out["labels"], out["n_gt"], group)
+    return _ap_from_labels({"labels": labels_all, "n_gt": n_gt}, conf_all, joint_names)

@@ -35,7 +35,7 @@ class PoseEstimator:
 
     def __init__(self, model, camera: Camera = MP3DHP, config: DecodeConfig | None = None, *, input_size=224,
                  max_persons: int = 32, max_peaks: int = _abi.MAX_PEAKS, strict: bool = True, use_graphs: bool = True,
-                 peers=None, decode_priority: int = 0):
+                 peers=None, decode_priority: int = 0, decode_schedule: int = _abi.DECODE_AUTO, reserve_sms: int = 8):
         from ._cuda_backend import CudaBackend          # raises without CUDA / the library
         self.backend = CudaBackend()
         self.model = model
@@ -46,13 +46,20 @@ class PoseEstimator:
         ds = self.config.downsample
         # the network's third head has num_limbs + 1 planes; joint j reads plane j (...mpreal_ablation.py:212-215)
         self.params = _abi.make_decode_params(self.config, camera, input_size=self.input_hw[1], max_peaks=max_peaks,
-                                              max_persons=max_persons, depth_channels=model.num_limbs + 1,
+                                              max_persons=max_persons, depth_channels=model.num_limbs + 1, schedule=decode_schedule,
                                               grid_hw=(self.input_hw[0] // ds, self.input_hw[1] // ds))
         #: the reference's lists are unbounded; max_peaks / max_persons are device capacities.  strict: collect() raises
         #: OverflowError when a frame hit one of them (its poses would differ from the reference's); strict=False
         #: leaves the check of out["flags"] to the caller.
         self.strict = strict
         self.use_graphs = use_graphs
+        #: the decode of batch i runs under the forward of batch i + 1, and a convolution CTA fills an SM's register file: a
+        #: decode CTA on an SM keeps the next layer's CTA off it and the whole layer waits.  The persistent conv grids
+        #: therefore leave `reserve_sms` SMs (a multiple of 4, 0..28) to the decode (POPNET_TUNE_RESERVE_SMS; measured, same
+        #: box: 1.060 vs 1.084 ms per step with 8, forward alone 1.016 vs 1.009 ms).  Only set if the model's tuning
+        #: word does not choose a reserve itself.
+        if reserve_sms and not (model.tuning & _abi.TUNE_RESERVE_SMS(7)):
+            model.tuning |= _abi.TUNE_RESERVE_SMS(reserve_sms // 4)
         self.decode_priority = decode_priority      # CUDA stream priority of the decode stream (0 = default, -1 = high)
         self.peers = peers          # optional p2p.PeerGather: the multi-GPU record exchange, fused into the decode
         self._slots = None
@@ -280,6 +287,41 @@ def reduce_counts(counts, group=None):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         out[k] = t
     return out
+
+
+def gather_ap_rows(conf, labels, n_gt, group=None):
+    """Multi-GPU AP (SURVEY.md 5 iii): every rank has run the GT assignment (popnet_eval_map_assign) on its contiguous
+    shard of frames and holds one (score[K], label[K]) row per PREDICTED human of the shard plus its nGT[K] counts; the AP
+    of the whole set needs all rows in one list (the reference appends them frame by frame, util/eval_mAP.py:132-155,
+    and sorts once per joint, :160-191).  Row counts differ per rank: ONE all-gather of the counts, ONE all-gather of the
+    rows packed as bytes and padded to the longest shard, one all-reduce of nGT.  Returns (conf[R, K] float64,
+    labels[R, K] int32, n_gt[K] int64) with rank r's rows before rank r+1's -- the single-process row order, so the AP tail
+    (NumPy or popnet_eval_ap) sees exactly the single-process input.  NCCL on CUDA tensors, gloo on CPU tensors."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    conf = np.ascontiguousarray(np.asarray(conf, np.float64))
+    labels = np.ascontiguousarray(np.asarray(labels).astype(np.int32))
+    if conf.shape != labels.shape or conf.ndim != 2:
+        raise ValueError("conf and labels must both be [rows, K]")
+    rows, K = conf.shape
+    dev = torch.device("cuda") if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    counts = torch.zeros((world,), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, torch.tensor([rows], dtype=torch.int64, device=dev), group=group)
+    counts = counts.cpu().numpy()
+    per = int(counts.max()) * K * 12                                  # 8 B score + 4 B label per (row, joint)
+    mine = np.zeros((per,), np.uint8)
+    mine[:rows * K * 8] = conf.view(np.uint8).reshape(-1)
+    mine[int(counts.max()) * K * 8:int(counts.max()) * K * 8 + rows * K * 4] = labels.view(np.uint8).reshape(-1)
+    full = torch.empty((world * per,), dtype=torch.uint8, device=dev)
+    if per:
+        dist.all_gather_into_tensor(full, torch.from_numpy(mine).to(dev), group=group)
+    full = full.cpu().numpy().reshape(world, per)
+    cm = int(counts.max())
+    confs = [full[r, :cm * K * 8].view(np.float64).reshape(cm, K)[:int(counts[r])] for r in range(world)]
+    labs = [full[r, cm * K * 8:].view(np.int32).reshape(cm, K)[:int(counts[r])] for r in range(world)]
+    tot = reduce_counts({"n_gt": np.asarray(n_gt, np.int64)} if dev.type == "cpu"
+                        else {"n_gt": torch.as_tensor(np.asarray(n_gt, np.int64), device=dev)}, group)["n_gt"]
+    return np.concatenate(confs, 0), np.concatenate(labs, 0), tot.cpu().numpy()
 
 
 def shard(n_items: int, rank: int, world: int):

@@ -46,8 +46,14 @@ def _worker(rank, world, port, q):
                                  num_joints=15, dist_th=0.1)
     red = pipeline.reduce_counts({"hit_cnt": part["hit_cnt"], "valid_cnt": part["valid_cnt"],
                                   "samples": np.array([part["samples_cnt"]])})
+    # AP over frame shards of UNEQUAL size (60 frames, shards of 37 / 23): variable-length gather of the (score, label) rows
+    names = ["j%d" % i for i in range(15)]
+    cut = [0, 37, 60]
+    ap_slice = slice(cut[rank], cut[rank + 1])
+    evaluate.AP_TAIL = "numpy"
+    ap = evaluate.eval_ap_3D_sharded(ds["pred3d"][ap_slice], ds["conf"][ap_slice], ds["gt3d"][ap_slice], [], names, thresh=0.1)
     if rank == 0:
-        q.put(({k: np.asarray(v) for k, v in full.items()}, {k: v.numpy() for k, v in red.items()}))
+        q.put(({k: np.asarray(v) for k, v in full.items()}, {k: v.numpy() for k, v in red.items()}, np.asarray(ap)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -61,7 +67,7 @@ def test_gather_and_reduce_match_single_process(oracle_lib):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    full, red = q.get(timeout=120)
+    full, red, ap = q.get(timeout=120)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
@@ -74,8 +80,12 @@ def test_gather_and_reduce_match_single_process(oracle_lib):
     evaluate._backend = OracleBackend()
     try:
         whole = evaluate.match_counts(ds["pred2d"], ds["gt2d"], pred3d=ds["pred3d"], gt3d=ds["gt3d"], num_joints=15, dist_th=0.1)
+        evaluate.AP_TAIL = "numpy"
+        ap_whole = evaluate.eval_ap_3D(ds["pred3d"], ds["conf"], ds["gt3d"], [], ["j%d" % i for i in range(15)], thresh=0.1)
     finally:
         evaluate._backend = None
+        evaluate.AP_TAIL = "device"
+    assert np.array_equal(ap, np.asarray(ap_whole)) and ap_whole[-1] > 0          # sharded AP == single-process AP, bit for bit
     assert np.array_equal(red["hit_cnt"], whole["hit_cnt"]) and np.array_equal(red["valid_cnt"], whole["valid_cnt"])
     assert int(red["samples"][0]) == whole["samples_cnt"]
 

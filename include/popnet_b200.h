@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define POPNET_ABI_VERSION 4
+#define POPNET_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define POPNET_API __attribute__((visibility("default")))
@@ -89,13 +89,10 @@ typedef struct PopnetDecodeParams {
   int32_t max_persons;                      /* <= POPNET_MAX_PERSONS                               */
   int32_t depth_channels;                   /* planes per frame in `depth`: the network's third head has L + 1
                                                (rtpose_light3d.py:299-309), joint j reads plane j; 0 means K        */
-  int32_t schedule;                         /* POPNET_DECODE_*: which launch schedule computes the (identical) result */
+  int32_t max_ctas;                         /* 0: every decode kernel may use all SMs; n > 0: at most n CTAs per kernel -- the
+                                               pipelined step passes 8, the SMs its convolution grids leave free
+                                               (POPNET_TUNE_RESERVE_SMS): same records either way                    */
 } PopnetDecodeParams;
-
-#define POPNET_DECODE_AUTO 0           /* one fused kernel (a CTA walks whole frames through every phase with the frame's maps in
-                                          shared memory) when a frame fits, else the three-kernel schedule          */
-#define POPNET_DECODE_THREE_KERNELS 1  /* peaks (K x B CTAs) -> limbs (L x B CTAs) -> assembly + lift (B CTAs)         */
-#define POPNET_DECODE_FUSED 2          /* the fused kernel or POPNET_ERR_UNSUPPORTED                                 */
 
 /* Output buffers (see popnet_decode for which may be NULL).
  * Strides use the capacities in PopnetDecodeParams (P = max_peaks, M = max_persons, K, L). */

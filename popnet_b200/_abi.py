@@ -9,7 +9,7 @@ MAX_LIMBS = 24
 LIFT_HEAT_WEIGHTED, LIFT_MEAN, LIFT_HEAT_MAX = 0, 1, 2
 MAX_PEAKS = 64
 MAX_PERSONS = 64
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_PEERS = 8
 
 OK = 0
@@ -56,7 +56,7 @@ class DecodeParams(C.Structure):
         ("w_org", C.c_double), ("h_org", C.c_double),
         ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
         ("flip_y", C.c_int32), ("max_peaks", C.c_int32), ("max_persons", C.c_int32),
-        ("depth_channels", C.c_int32), ("schedule", C.c_int32),
+        ("depth_channels", C.c_int32), ("max_ctas", C.c_int32),
     ]
 
 
@@ -150,15 +150,12 @@ def bind(lib):
     return lib
 
 
-# PopnetDecodeParams.schedule (include/popnet_b200.h, POPNET_DECODE_*)
-DECODE_AUTO, DECODE_THREE_KERNELS, DECODE_FUSED = 0, 1, 2
-
-
 def make_decode_params(cfg, cam, *, input_size=224, grid_hw=None, depth_channels=0, max_peaks=MAX_PEAKS,
-                       max_persons=MAX_PERSONS, schedule=DECODE_AUTO):
+                       max_persons=MAX_PERSONS, max_ctas=0):
     """DecodeParams from a topology.DecodeConfig and a topology.Camera.  ``grid_hw``: (rows, columns) of the maps --
     default: the square grid of a square ``input_size`` network input; ``depth_channels``: planes per frame of the
-    depth tensor handed to the decode (0 = num_keypoints; the network's third head emits num_limbs + 1)."""
+    depth tensor handed to the decode (0 = num_keypoints; the network's third head emits num_limbs + 1); ``max_ctas``: CTA
+    limit per decode kernel (0 = all SMs; the pipelined step passes the SMs its convolution grids leave free)."""
     p = DecodeParams()
     p.num_joints = cfg.num_keypoints
     p.num_limbs = len(cfg.limbs)
@@ -169,7 +166,7 @@ def make_decode_params(cfg, cam, *, input_size=224, grid_hw=None, depth_channels
         grid_hw = (input_size // cfg.downsample, input_size // cfg.downsample)
     p.grid_h, p.grid_w = int(grid_hw[0]), int(grid_hw[1])
     p.depth_channels = int(depth_channels)
-    p.schedule = int(schedule)
+    p.max_ctas = int(max_ctas)
     p.stride = cfg.downsample
     p.num_intermed_pts = cfg.num_intermed_pts
     p.thresh_heat = cfg.thresh_heatmap

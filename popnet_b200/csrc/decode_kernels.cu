@@ -5,22 +5,26 @@
 // 272-293 (paf_to_human_list, retrieve_depth_heat_weighted) and the per-frame glue of
 // evaluate/evaluation_rtpose_light3d_kdh3d_mpreal_ablation.py:179-263.
 //
-// Three kernels per batch, all reading the network's channel-major fp32 maps in place:
-//   peaks_kernel     grid (K, B)  one CTA per (frame, joint type): 4-neighbour NMS with ordered
-//                                 compaction, then one warp per peak evaluates the 8x bicubic of the
-//                                 clipped 5x5 patch and takes the first arg-max.
-//   limbs_kernel     grid (L, B)  one CTA per (frame, limb): every (src, dst) pair is scored from 10
-//                                 on-the-fly bicubic PAF samples (the 224x224x28 upsample the reference
-//                                 materialises is never built), then greedy one-to-one matching.
-//   assemble_kernel  grid (B)     one warp per frame: sequential person assembly, pruning, depth lift,
-//                                 rescale and back-projection; writes the pose records.
+// Three kernels per batch, all reading the network's channel-major fp32 maps in place; each is PERSISTENT with one WARP
+// per work item and at most `max_ctas` CTAs (PopnetDecodeParams.max_ctas):
+//   peaks_kernel     item = (frame, joint type): the map goes to the warp's shared-memory slice, 4-neighbour NMS with
+//                    ordered compaction, then the 8x bicubic of the clipped 5x5 patch of every peak and its first arg-max.
+//   limbs_kernel     item = (frame, limb): the limb's two PAF planes go to the warp's slice, every (src, dst) pair is scored
+//                    from 10 on-the-fly bicubic PAF samples (the 224x224x28 upsample the reference materialises is never
+//                    built), then greedy one-to-one matching.  Items whose score matrix exceeds the warp's pool are done by
+//                    the whole CTA afterwards.
+//   assemble_kernel  item = frame: sequential person assembly, pruning, depth lift, rescale and back-projection; writes the
+//                    pose records (and pushes them to the peers).
+// Why few, fat CTAs: the work per frame is tiny and latency-bound, and in the pipelined step the decode of batch i runs
+// under the forward of batch i + 1, whose convolution CTAs fill an SM's register file -- every SM that holds a decode CTA
+// at a layer boundary delays that layer.  With max_ctas = 8 the decode lives on the 8 SMs the conv grids leave free.
 // Compiled with -fmad=false so fp32/fp64 expressions round exactly like OpenCV's C++ path and NumPy;
 // the two places the reference goes through BLAS use explicit fma().
 //
-// Bound: HBM in principle (181,888 B of maps per frame); the work per frame is tiny,
-// so throughput comes from frames in flight (B x 15 / B x 14 / B CTAs), not from any single CTA.
+// Bound: HBM in principle (181,888 B of maps per frame); in practice latency.
 #include <math_constants.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "common.cuh"
@@ -28,7 +32,6 @@
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kThreads = 128;
 constexpr int kMaxCells = 64 * 64;      // largest supported grid_h * grid_w
 
 // OpenCV INTER_CUBIC at scale 8: phase r = dst % 8 -> first-tap offset and the four Keys(A=-0.75)
@@ -127,74 +130,73 @@ __device__ __forceinline__ void refine_peak(const float* __restrict__ s_map, int
 // ------------------------------------------------------------------------------------------------
 // D1 + D2: peaks
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) peaks_kernel(const float* __restrict__ heat, PopnetDecodeParams p,
-                                                         PopnetDecodeOut o) {
-  extern __shared__ float s_map[];                       // H*W
-  __shared__ int s_cell[POPNET_MAX_PEAKS];
-  __shared__ int s_warp_cnt[kThreads / 32];
-  __shared__ int s_total;
-  __shared__ float s_tmp[kThreads / 32][5 * 40];         // per-warp horizontal pass of a <=5x5 patch
+// per-warp shared-memory slice of peaks_kernel: [cells (padded to 4)] map | [5*40] scratch | [MP] peak cells
+__host__ __device__ inline size_t peaks_warp_bytes(int cells, int MP) {
+  return ((((size_t)cells + 3) & ~(size_t)3) + 200 + (size_t)MP) * 4;
+}
 
-  const int k = blockIdx.x, b = blockIdx.y;
-  const int H = p.grid_h, W = p.grid_w, cells = H * W;
+__global__ void __launch_bounds__(1024) peaks_kernel(const float* __restrict__ heat, int batch, PopnetDecodeParams p,
+                                                     PopnetDecodeOut o) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  const int H = p.grid_h, W = p.grid_w, cells = H * W, cells4 = (cells + 3) & ~3;
   const int K = p.num_joints, MP = p.max_peaks;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* m = heat + ((size_t)b * (K + 1) + k) * cells;
-  for (int i = tid; i < cells; i += kThreads) s_map[i] = m[i];
-  if (tid == 0) s_total = 0;
-  __syncthreads();
-
-  // ordered (row-major) compaction of the peak cells
-  for (int base = 0; base < cells; base += kThreads) {
-    const int i = base + tid;
-    bool pk = false;
-    if (i < cells) {
-      const int y = i / W, x = i - y * W;
-      const float v = s_map[i];
-      pk = v > p.thresh_heat;
-      if (pk && y > 0) pk = !(s_map[i - W] > v);
-      if (pk && y < H - 1) pk = !(s_map[i + W] > v);
-      if (pk && x > 0) pk = !(s_map[i - 1] > v);
-      if (pk && x < W - 1) pk = !(s_map[i + 1] > v);
-    }
-    const unsigned bal = __ballot_sync(kFull, pk);
-    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-    __syncthreads();
-    int before = s_total;
-    for (int w = 0; w < warp; ++w) before += s_warp_cnt[w];
-    if (pk) {
-      const int slot = before + __popc(bal & ((1u << lane) - 1u));
-      if (slot < MP) s_cell[slot] = i;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int t = s_total;
-      for (int w = 0; w < kThreads / 32; ++w) t += s_warp_cnt[w];
-      s_total = t;
-    }
-    __syncthreads();
-  }
-  int n = s_total;
-  if (n > MP) {
-    if (tid == 0) atomicOr(o.flags + b, POPNET_FLAG_PEAK_OVERFLOW);
-    n = MP;
-  }
-  if (tid == 0) o.peak_count[(size_t)b * K + k] = n;
-
-  // refinement: one warp per peak
-  float* tmp = s_tmp[warp];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  float* s_map = reinterpret_cast<float*>(s_dyn + (size_t)warp * peaks_warp_bytes(cells, MP));
+  float* tmp = s_map + cells4;
+  int* s_cell = reinterpret_cast<int*>(tmp + 200);
   const float hc0 = c_coef[lane & 7][0], hc1 = c_coef[lane & 7][1], hc2 = c_coef[lane & 7][2], hc3 = c_coef[lane & 7][3];
   const int hofs = c_ofs[lane & 7];
-  for (int pi = warp; pi < n; pi += kThreads / 32) {
-    int X, Y;
-    float best;
-    refine_peak(s_map, W, H, s_cell[pi], tmp, lane, hc0, hc1, hc2, hc3, hofs, X, Y, best);
-    if (lane == 0) {
-      const size_t slot = ((size_t)b * K + k) * MP + pi;
-      o.peak_xy[slot * 2] = (int16_t)X;
-      o.peak_xy[slot * 2 + 1] = (int16_t)Y;
-      o.peak_score[slot] = best;
+  const int items = batch * K;
+  for (int it = blockIdx.x * wpc + warp; it < items; it += gridDim.x * wpc) {
+    const int b = it / K, k = it - b * K;
+    const float* m = heat + ((size_t)b * (K + 1) + k) * cells;
+    if ((cells & 3) == 0 && (reinterpret_cast<uintptr_t>(m) & 15u) == 0) {
+      const float4* m4 = reinterpret_cast<const float4*>(m);
+      float4* d4 = reinterpret_cast<float4*>(s_map);
+      for (int i = lane; i < cells / 4; i += 32) d4[i] = __ldg(m4 + i);
+    } else {
+      for (int i = lane; i < cells; i += 32) s_map[i] = m[i];
     }
+    __syncwarp();
+    // D1: peak cells in row-major order (ordered compaction by ballot)
+    int cnt = 0;
+    for (int base = 0; base < cells; base += 32) {
+      const int i = base + lane;
+      bool pk = false;
+      if (i < cells) {
+        const int y = i / W, x = i - y * W;
+        const float v = s_map[i];
+        pk = v > p.thresh_heat;
+        if (pk && y > 0) pk = !(s_map[i - W] > v);
+        if (pk && y < H - 1) pk = !(s_map[i + W] > v);
+        if (pk && x > 0) pk = !(s_map[i - 1] > v);
+        if (pk && x < W - 1) pk = !(s_map[i + 1] > v);
+      }
+      const unsigned bal = __ballot_sync(kFull, pk);
+      if (pk) {
+        const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
+        if (slot < MP) s_cell[slot] = i;
+      }
+      cnt += __popc(bal);
+    }
+    if (cnt > MP) {
+      if (lane == 0) atomicOr(o.flags + b, POPNET_FLAG_PEAK_OVERFLOW);
+      cnt = MP;
+    }
+    if (lane == 0) o.peak_count[(size_t)b * K + k] = cnt;
+    __syncwarp();
+    // D2: refinement, peak by peak
+    for (int pi = 0; pi < cnt; ++pi) {
+      int X, Y;
+      float best;
+      refine_peak(s_map, W, H, s_cell[pi], tmp, lane, hc0, hc1, hc2, hc3, hofs, X, Y, best);
+      if (lane == 0) {
+        const size_t slot = ((size_t)b * K + k) * MP + pi;
+        *reinterpret_cast<int*>(o.peak_xy + slot * 2) = (X & 0xffff) | (Y << 16);
+        o.peak_score[slot] = best;
+      }
+    }
+    __syncwarp();                    // the slice is refilled by the warp's next item
   }
 }
 
@@ -278,85 +280,194 @@ __device__ __forceinline__ void score_pairs(const float* __restrict__ s_px, cons
 
 struct Best { double v; int idx; };
 
-__global__ void __launch_bounds__(kThreads) limbs_kernel(const float* __restrict__ paf, PopnetDecodeParams p,
-                                                         PopnetDecodeOut o) {
-  extern __shared__ unsigned char s_raw[];
-  const int l = blockIdx.x, b = blockIdx.y;
-  const int H = p.grid_h, W = p.grid_w, cells = H * W;
+// Shared-memory layout of limbs_kernel (bytes from the start of the dynamic block), computed on the host:
+//   planes  [wpc][2][cells4] float    the limb's x / y PAF planes of each warp's current item
+//   pool    [wpc][pool_doubles] double the warp's score matrix [na][nb]; all pools together hold one max_peaks^2 matrix
+//   dot     [wpc][32] double           score_pairs scratch
+//   xab     [wpc][2][MP][2] int16      end-point coordinates of the src / dst peaks
+//   used    [wpc][2][MP] uint8         greedy: peak already connected
+//   best    [wpc] Best                 block-wide arg-max (big items)
+//   big     [big_words] uint32         bitmap over the CTA's items (local index n * wpc + warp): left to the whole CTA
+struct LimbsLayout {
+  unsigned planes, pool, dot, xab, used, best, big, total;
+  int pool_doubles, big_words, cells4;
+};
+inline LimbsLayout limbs_layout(int cells, int MP, int wpc, int items_per_cta) {
+  LimbsLayout y{};
+  y.cells4 = (cells + 3) & ~3;
+  y.pool_doubles = 512;
+  while ((long long)y.pool_doubles * wpc < (long long)MP * MP) y.pool_doubles *= 2;
+  size_t off = 0;
+  y.planes = (unsigned)off; off += (size_t)wpc * 2 * y.cells4 * sizeof(float);
+  off = (off + 15) & ~(size_t)15;
+  y.pool = (unsigned)off; off += (size_t)wpc * y.pool_doubles * sizeof(double);
+  y.dot = (unsigned)off; off += (size_t)wpc * 32 * sizeof(double);
+  y.best = (unsigned)off; off += (size_t)wpc * sizeof(Best);
+  y.xab = (unsigned)off; off += (size_t)wpc * 2 * MP * 2 * sizeof(int16_t);
+  y.used = (unsigned)off; off += (size_t)wpc * 2 * MP;
+  off = (off + 3) & ~(size_t)3;
+  y.big_words = (items_per_cta + 31) / 32;
+  y.big = (unsigned)off; off += (size_t)y.big_words * sizeof(unsigned int);
+  y.total = (unsigned)((off + 15) & ~(size_t)15);
+  return y;
+}
+
+// stage one item's PAF planes and end-point coordinates with `nthr` threads (thread `t` of them)
+__device__ __forceinline__ void limbs_stage(const float* __restrict__ paf, const PopnetDecodeOut& o, int b, int l, int ta, int tb,
+                                            int na, int nb, int K, int L, int MP, int cells, int cells4, float* s_px,
+                                            int16_t (*xa)[2], int16_t (*xb)[2], unsigned char* used_a, unsigned char* used_b,
+                                            int t, int nthr) {
+  const float* mx = paf + ((size_t)b * 2 * L + 2 * l) * cells;             // planes 2l (x) and 2l + 1 (y) are adjacent
+  if ((cells & 3) == 0 && (reinterpret_cast<uintptr_t>(mx) & 15u) == 0) {
+    const float4* m4 = reinterpret_cast<const float4*>(mx);
+    float4* d4 = reinterpret_cast<float4*>(s_px);
+    for (int i = t; i < cells / 2; i += nthr) d4[i] = __ldg(m4 + i);       // 2 * cells / 4 vectors; cells4 == cells here
+  } else {
+    for (int i = t; i < cells; i += nthr) { s_px[i] = mx[i]; s_px[cells4 + i] = mx[cells + i]; }
+  }
+  for (int i = t; i < na; i += nthr) {
+    *reinterpret_cast<int*>(xa[i]) = *reinterpret_cast<const int*>(o.peak_xy + (((size_t)b * K + ta) * MP + i) * 2);
+    used_a[i] = 0;
+  }
+  for (int i = t; i < nb; i += nthr) {
+    *reinterpret_cast<int*>(xb[i]) = *reinterpret_cast<const int*>(o.peak_xy + (((size_t)b * K + tb) * MP + i) * 2);
+    used_b[i] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(512) limbs_kernel(const float* __restrict__ paf, int batch, PopnetDecodeParams p,
+                                                    PopnetDecodeOut o, LimbsLayout lay) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  const int H = p.grid_h, W = p.grid_w, cells = H * W, cells4 = lay.cells4;
   const int K = p.num_joints, L = p.num_limbs, MP = p.max_peaks, NP = p.num_intermed_pts;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ta = p.limbs[l][0], tb = p.limbs[l][1];
-  const int na = o.peak_count[(size_t)b * K + ta], nb = o.peak_count[(size_t)b * K + tb];
-  if (na == 0 || nb == 0) {
-    if (tid == 0) o.conn_count[(size_t)b * L + l] = 0;
-    return;
-  }
-  double* s_score = reinterpret_cast<double*>(s_raw);                       // [na][nb]
-  float* s_px = reinterpret_cast<float*>(s_raw + sizeof(double) * MP * MP); // [cells]
-  float* s_py = s_px + cells;
-  __shared__ int16_t s_xa[POPNET_MAX_PEAKS][2], s_xb[POPNET_MAX_PEAKS][2];
-  __shared__ double s_dot[kThreads / 32][32];
-  __shared__ unsigned char s_used_a[POPNET_MAX_PEAKS], s_used_b[POPNET_MAX_PEAKS];
-  __shared__ Best s_best[kThreads / 32];
-
-  const float* mx = paf + ((size_t)b * 2 * L + 2 * l) * cells;
-  for (int i = tid; i < cells; i += kThreads) { s_px[i] = mx[i]; s_py[i] = mx[cells + i]; }
-  for (int i = tid; i < na; i += kThreads) {
-    const int16_t* q = o.peak_xy + (((size_t)b * K + ta) * MP + i) * 2;
-    s_xa[i][0] = q[0]; s_xa[i][1] = q[1]; s_used_a[i] = 0;
-  }
-  for (int i = tid; i < nb; i += kThreads) {
-    const int16_t* q = o.peak_xy + (((size_t)b * K + tb) * MP + i) * 2;
-    s_xb[i][0] = q[0]; s_xb[i][1] = q[1]; s_used_b[i] = 0;
-  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
+  float* s_px = reinterpret_cast<float*>(s_dyn + lay.planes) + (size_t)warp * 2 * cells4;
+  double* s_pool = reinterpret_cast<double*>(s_dyn + lay.pool) + (size_t)warp * lay.pool_doubles;
+  double* s_dot = reinterpret_cast<double*>(s_dyn + lay.dot) + warp * 32;
+  int16_t (*xa)[2] = reinterpret_cast<int16_t (*)[2]>(s_dyn + lay.xab) + (size_t)warp * 2 * MP;
+  int16_t (*xb)[2] = xa + MP;
+  unsigned char* used_a = s_dyn + lay.used + (size_t)warp * 2 * MP;
+  unsigned char* used_b = used_a + MP;
+  Best* s_best = reinterpret_cast<Best*>(s_dyn + lay.best);
+  unsigned int* s_big = reinterpret_cast<unsigned int*>(s_dyn + lay.big);
+  for (int i = tid; i < lay.big_words; i += blockDim.x) s_big[i] = 0u;
   __syncthreads();
-
   const double Hup = (double)(H * p.stride);
-  const int npairs = na * nb;
-  score_pairs(s_px, s_py, W, H, s_xa, s_xb, na, nb, NP, p.thresh_paf, Hup, s_score, MP, s_dot[warp], warp, kThreads / 32, lane);
+  const int items = batch * L;
+
+  // ---- pass 1: one warp per item
+  int li = warp;                                         // local item index n * wpc + warp
+  for (int it = blockIdx.x * wpc + warp; it < items; it += gridDim.x * wpc, li += wpc) {
+    const int b = it / L, l = it - b * L;
+    const int ta = p.limbs[l][0], tb = p.limbs[l][1];
+    const int na = o.peak_count[(size_t)b * K + ta], nb = o.peak_count[(size_t)b * K + tb];
+    if (na == 0 || nb == 0) {
+      if (lane == 0) o.conn_count[(size_t)b * L + l] = 0;
+      continue;
+    }
+    const int npairs = na * nb;
+    if (npairs > lay.pool_doubles) {                   // too many candidates for one warp's pool: the whole CTA takes it in pass 2
+      if (lane == 0) atomicOr(&s_big[li >> 5], 1u << (li & 31));
+      continue;
+    }
+    limbs_stage(paf, o, b, l, ta, tb, na, nb, K, L, MP, cells, cells4, s_px, xa, xb, used_a, used_b, lane, 32);
+    __syncwarp();
+    score_pairs(s_px, s_px + cells4, W, H, xa, xb, na, nb, NP, p.thresh_paf, Hup, s_pool, nb, s_dot, 0, 1, lane);
+    // Stable descending sort + greedy (paf_to_pose.py:241-261) == repeatedly take the best remaining pair whose ends are
+    // both free, ties to the smallest (i, j)
+    const int maxc = min(na, nb);
+    int nconn = 0;
+    while (nconn < maxc) {
+      double bv = -CUDART_INF;
+      int bi = 0x7fffffff;
+      for (int pr = lane; pr < npairs; pr += 32) {
+        const int i = pr / nb, j = pr - i * nb;
+        if (used_a[i] || used_b[j]) continue;
+        const double v = s_pool[pr];
+        if (v > bv) { bv = v; bi = pr; }
+      }
+#pragma unroll
+      for (int ofs = 16; ofs > 0; ofs >>= 1) {
+        const double ov = __shfl_xor_sync(kFull, bv, ofs);
+        const int oi = __shfl_xor_sync(kFull, bi, ofs);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (bi == 0x7fffffff) break;
+      const int i = bi / nb, j = bi - i * nb;
+      if (lane == 0) {
+        used_a[i] = 1; used_b[j] = 1;
+        const size_t slot = ((size_t)b * L + l) * MP + nconn;
+        *reinterpret_cast<int*>(o.conn_ij + slot * 2) = (i & 0xffff) | (j << 16);
+        o.conn_score[slot] = bv;
+      }
+      ++nconn;
+      __syncwarp();
+    }
+    if (lane == 0) o.conn_count[(size_t)b * L + l] = nconn;
+    __syncwarp();
+  }
   __syncthreads();
 
-  // Stable descending sort + greedy (paf_to_pose.py:241-261) == repeatedly take the best remaining
-  // pair whose ends are both free, ties to the smallest (i, j).
-  const int maxc = min(na, nb);
-  int nconn = 0;
-  while (nconn < maxc) {
-    double bv = -CUDART_INF;
-    int bi = 0x7fffffff;
-    for (int pr = tid; pr < npairs; pr += kThreads) {
-      const int i = pr / nb, j = pr - i * nb;
-      if (s_used_a[i] || s_used_b[j]) continue;
-      const double v = s_score[i * MP + j];
-      if (v > bv) { bv = v; bi = pr; }
-    }
-#pragma unroll
-    for (int ofs = 16; ofs > 0; ofs >>= 1) {
-      const double ov = __shfl_xor_sync(kFull, bv, ofs);
-      const int oi = __shfl_xor_sync(kFull, bi, ofs);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    if (lane == 0) { s_best[warp].v = bv; s_best[warp].idx = bi; }
+  // ---- pass 2: items with more candidates than a warp's pool, one at a time by the whole CTA; the score matrix spans all
+  // pools (wpc * pool_doubles >= max_peaks^2), planes and tables are warp 0's
+  float* b_px = reinterpret_cast<float*>(s_dyn + lay.planes);
+  double* b_score = reinterpret_cast<double*>(s_dyn + lay.pool);
+  int16_t (*bxa)[2] = reinterpret_cast<int16_t (*)[2]>(s_dyn + lay.xab);
+  int16_t (*bxb)[2] = bxa + MP;
+  unsigned char* bused_a = s_dyn + lay.used;
+  unsigned char* bused_b = bused_a + MP;
+  for (int w = 0; w < lay.big_words; ++w)
+  for (unsigned int word = s_big[w]; word != 0u; word &= word - 1u) {
+    const int bli = w * 32 + __ffs((int)word) - 1;
+    const int it = blockIdx.x * wpc + bli % wpc + (bli / wpc) * (int)gridDim.x * wpc;
+    const int b = it / L, l = it - b * L;
+    const int ta = p.limbs[l][0], tb = p.limbs[l][1];
+    const int na = o.peak_count[(size_t)b * K + ta], nb = o.peak_count[(size_t)b * K + tb];
+    const int npairs = na * nb;
+    limbs_stage(paf, o, b, l, ta, tb, na, nb, K, L, MP, cells, cells4, b_px, bxa, bxb, bused_a, bused_b, tid, (int)blockDim.x);
     __syncthreads();
-    bv = s_best[0].v; bi = s_best[0].idx;
+    score_pairs(b_px, b_px + cells4, W, H, bxa, bxb, na, nb, NP, p.thresh_paf, Hup, b_score, nb,
+                reinterpret_cast<double*>(s_dyn + lay.dot) + warp * 32, warp, wpc, lane);
+    __syncthreads();
+    const int maxc = min(na, nb);
+    int nconn = 0;
+    while (nconn < maxc) {
+      double bv = -CUDART_INF;
+      int bi = 0x7fffffff;
+      for (int pr = tid; pr < npairs; pr += blockDim.x) {
+        const int i = pr / nb, j = pr - i * nb;
+        if (bused_a[i] || bused_b[j]) continue;
+        const double v = b_score[pr];
+        if (v > bv) { bv = v; bi = pr; }
+      }
 #pragma unroll
-    for (int w = 1; w < kThreads / 32; ++w) {
-      const double ov = s_best[w].v;
-      const int oi = s_best[w].idx;
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      for (int ofs = 16; ofs > 0; ofs >>= 1) {
+        const double ov = __shfl_xor_sync(kFull, bv, ofs);
+        const int oi = __shfl_xor_sync(kFull, bi, ofs);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { s_best[warp].v = bv; s_best[warp].idx = bi; }
+      __syncthreads();
+      bv = s_best[0].v; bi = s_best[0].idx;
+      for (int w = 1; w < wpc; ++w) {
+        const double ov = s_best[w].v;
+        const int oi = s_best[w].idx;
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (bi == 0x7fffffff) break;                       // uniform: nothing admissible is left
+      const int i = bi / nb, j = bi - i * nb;
+      if (tid == 0) {
+        bused_a[i] = 1; bused_b[j] = 1;
+        const size_t slot = ((size_t)b * L + l) * MP + nconn;
+        *reinterpret_cast<int*>(o.conn_ij + slot * 2) = (i & 0xffff) | (j << 16);
+        o.conn_score[slot] = bv;
+      }
+      ++nconn;
+      __syncthreads();
     }
-    if (bi == 0x7fffffff) break;                       // uniform: nothing admissible is left
-    const int i = bi / nb, j = bi - i * nb;
-    if (tid == 0) {
-      s_used_a[i] = 1; s_used_b[j] = 1;
-      const size_t slot = ((size_t)b * L + l) * MP + nconn;
-      o.conn_ij[slot * 2] = (int16_t)i;
-      o.conn_ij[slot * 2 + 1] = (int16_t)j;
-      o.conn_score[slot] = bv;
-    }
-    ++nconn;
+    if (tid == 0) o.conn_count[(size_t)b * L + l] = nconn;
     __syncthreads();
   }
-  if (tid == 0) o.conn_count[(size_t)b * L + l] = nconn;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -654,8 +765,8 @@ __global__ void __launch_bounds__(256) assemble_kernel(const float* __restrict__
   const PushCtx pc = make_push_ctx(push);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int K = p.num_joints, L = p.num_limbs, MP = p.max_peaks, MM = p.max_persons;
-  const int b = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (b < batch) {
+  const int wpc = blockDim.x >> 5;
+  for (int b = blockIdx.x * wpc + warp; b < batch; b += gridDim.x * wpc) {
     FrameTables T;
     unsigned char* base = s_asm + (size_t)warp * frame_bytes;
     T.cs = reinterpret_cast<double*>(base); base += (size_t)L * MP * sizeof(double);
@@ -731,247 +842,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const float* __restrict__
       rec_store(pc, o.flags + b, fl);
     }
     lift_and_store(T, p, o, pc, heat, depth, b, nout, lane, 32);
-  }
-  publish_push(push);
-}
-
-// ------------------------------------------------------------------------------------------------
-// FUSED decode: one CTA walks whole frames through all phases (D1 .. D9) with the frame's maps, peaks and connections in
-// shared memory -- no global round trip between the phases, no 15 + 14 + 1 CTAs per frame passing through the SMs while
-// the next batch's convolutions want them (the decode of batch i runs under the forward of batch i + 1).
-//   A  heat maps -> shared memory (float4 loads)                              whole CTA
-//   B  4-neighbour NMS, ordered compaction                                    one warp per joint type
-//   C  bicubic refinement of every peak (first arg-max of the 8x patch)       one warp per peak
-//   D  PAF maps -> shared memory; pair scores, greedy matching                one warp per limb; the score matrices live in a
-//                                                                             pool that overlays the heat maps (several passes
-//                                                                             if the frame's pairs exceed the pool)
-//   E  serial person assembly + pruning                                       warp 0
-//   F  lift, rescale, back-projection, records (and the peer push)           whole CTA
-// The arithmetic of every phase is the three-kernel path's, statement for statement (both are compared byte for byte with
-// the oracle by tests/test_gpu_decode.py).  Used when the frame fits (fused_smem_bytes() <= 227 KB: the 15 / 14 topology on
-// a 28 x 28 grid takes 199 KB); larger grids / topologies take the three kernels.
-// ------------------------------------------------------------------------------------------------
-constexpr int kFusedThreads = 512;
-constexpr int kFusedWarps = kFusedThreads / 32;
-
-struct FusedLayout {
-  size_t heat, paf, pool_extra, fixed, total;    // byte offsets of the regions / total bytes
-  int pool_doubles;                              // score pool = heat region + pool_extra, contiguous
-};
-struct FusedFixed {                              // small per-frame tables (one instance in dynamic shared memory)
-  double cs[POPNET_MAX_LIMBS][POPNET_MAX_PEAKS];
-  double ps[POPNET_MAX_PERSONS];
-  float pk[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS];
-  float tmp[kFusedWarps][5 * 40];
-  double dot[kFusedWarps][32];
-  int cell[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS];
-  int pc[POPNET_MAX_PERSONS], keep[POPNET_MAX_PERSONS];
-  int nc[POPNET_MAX_LIMBS], npk[POPNET_MAX_JOINTS], off[POPNET_MAX_LIMBS + 1];
-  int nout;
-  unsigned int flags;
-  int16_t pj[POPNET_MAX_PERSONS][POPNET_MAX_JOINTS];
-  int16_t ci[POPNET_MAX_LIMBS][POPNET_MAX_PEAKS][2];
-  int16_t xy[POPNET_MAX_JOINTS][POPNET_MAX_PEAKS][2];
-  unsigned char used[kFusedWarps][2][POPNET_MAX_PEAKS];
-};
-__host__ __device__ inline FusedLayout fused_layout(int K, int L, int cells, size_t limit) {
-  FusedLayout f;
-  f.heat = 0;
-  size_t heat_bytes = ((size_t)K * cells * sizeof(float) + 15) & ~(size_t)15;
-  f.pool_extra = heat_bytes;
-  const size_t paf_bytes = ((size_t)2 * L * cells * sizeof(float) + 15) & ~(size_t)15;
-  const size_t fixed_bytes = (sizeof(FusedFixed) + 15) & ~(size_t)15;
-  const size_t need = heat_bytes + paf_bytes + fixed_bytes;
-  // whatever is left under the limit extends the score pool (it must hold at least one full max_peaks^2 matrix)
-  size_t extra = need < limit ? ((limit - need) & ~(size_t)15) : 0;
-  if (extra > 64 * 1024) extra = 64 * 1024;
-  f.paf = heat_bytes + extra;
-  f.fixed = f.paf + paf_bytes;
-  f.total = f.fixed + fixed_bytes;
-  f.pool_doubles = (int)((heat_bytes + extra) / sizeof(double));
-  return f;
-}
-
-__global__ void __launch_bounds__(kFusedThreads, 1) decode_fused_kernel(const float* __restrict__ heat, const float* __restrict__ paf,
-                                                                        const float* __restrict__ depth, int batch,
-                                                                        PopnetDecodeParams p, PopnetDecodeOut o, PopnetPeerPush push,
-                                                                        FusedLayout lay) {
-  extern __shared__ __align__(16) unsigned char s_dyn[];
-  float* s_heat = reinterpret_cast<float*>(s_dyn + lay.heat);
-  double* s_pool = reinterpret_cast<double*>(s_dyn + lay.heat);
-  float* s_paf = reinterpret_cast<float*>(s_dyn + lay.paf);
-  FusedFixed& S = *reinterpret_cast<FusedFixed*>(s_dyn + lay.fixed);
-
-  const PushCtx pc = make_push_ctx(push);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int K = p.num_joints, L = p.num_limbs, MP = p.max_peaks, NP = p.num_intermed_pts;
-  const int H = p.grid_h, W = p.grid_w, cells = H * W;
-  const int dch = p.depth_channels > 0 ? p.depth_channels : K;
-
-  for (int b = blockIdx.x; b < batch; b += gridDim.x) {
-    // ---- A: the frame's K heat maps (contiguous in the [B][K+1][cells] tensor)
-    {
-      const float* src = heat + (size_t)b * (K + 1) * cells;
-      const int n = K * cells;
-      if ((cells & 3) == 0) {
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        float4* d4 = reinterpret_cast<float4*>(s_heat);
-        for (int i = tid; i < n / 4; i += kFusedThreads) d4[i] = __ldg(s4 + i);
-      } else {
-        for (int i = tid; i < n; i += kFusedThreads) s_heat[i] = src[i];
-      }
-      if (tid == 0) S.flags = 0u;
-    }
-    __syncthreads();
-
-    // ---- B: peak cells of joint type k in row-major order (one warp per type)
-    for (int k = warp; k < K; k += kFusedWarps) {
-      const float* m = s_heat + (size_t)k * cells;
-      int cnt = 0;
-      for (int base = 0; base < cells; base += 32) {
-        const int i = base + lane;
-        bool pk = false;
-        if (i < cells) {
-          const int y = i / W, x = i - y * W;
-          const float v = m[i];
-          pk = v > p.thresh_heat;
-          if (pk && y > 0) pk = !(m[i - W] > v);
-          if (pk && y < H - 1) pk = !(m[i + W] > v);
-          if (pk && x > 0) pk = !(m[i - 1] > v);
-          if (pk && x < W - 1) pk = !(m[i + 1] > v);
-        }
-        const unsigned bal = __ballot_sync(kFull, pk);
-        if (pk) {
-          const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
-          if (slot < MP) S.cell[k][slot] = i;
-        }
-        cnt += __popc(bal);
-      }
-      if (lane == 0) {
-        if (cnt > MP) { atomicOr(&S.flags, POPNET_FLAG_PEAK_OVERFLOW); cnt = MP; }
-        S.npk[k] = cnt;
-        o.peak_count[(size_t)b * K + k] = cnt;
-      }
-    }
-    __syncthreads();
-
-    // ---- C: refinement, one warp per peak (flat index over the types)
-    {
-      int total = 0;
-      for (int k = 0; k < K; ++k) total += S.npk[k];
-      float* tmp = S.tmp[warp];
-      const float hc0 = c_coef[lane & 7][0], hc1 = c_coef[lane & 7][1], hc2 = c_coef[lane & 7][2], hc3 = c_coef[lane & 7][3];
-      const int hofs = c_ofs[lane & 7];
-      for (int t = warp; t < total; t += kFusedWarps) {
-        int k = 0, pi = t;
-        while (pi >= S.npk[k]) { pi -= S.npk[k]; ++k; }
-        int X, Y;
-        float best;
-        refine_peak(s_heat + (size_t)k * cells, W, H, S.cell[k][pi], tmp, lane, hc0, hc1, hc2, hc3, hofs, X, Y, best);
-        if (lane == 0) {
-          S.xy[k][pi][0] = (int16_t)X; S.xy[k][pi][1] = (int16_t)Y; S.pk[k][pi] = best;
-          const size_t slot = ((size_t)b * K + k) * MP + pi;
-          o.peak_xy[slot * 2] = (int16_t)X;
-          o.peak_xy[slot * 2 + 1] = (int16_t)Y;
-          o.peak_score[slot] = best;
-        }
-      }
-    }
-    // ---- D: PAF maps -> shared memory (they do not overlap the heat region, which phase C may still be reading)
-    {
-      const float* src = paf + (size_t)b * 2 * L * cells;
-      const int n = 2 * L * cells;
-      if ((cells & 3) == 0) {
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        float4* d4 = reinterpret_cast<float4*>(s_paf);
-        for (int i = tid; i < n / 4; i += kFusedThreads) d4[i] = __ldg(s4 + i);
-      } else {
-        for (int i = tid; i < n; i += kFusedThreads) s_paf[i] = src[i];
-      }
-    }
-    __syncthreads();                      // heat maps are dead from here on: their region becomes the score pool
-    const double Hup = (double)(H * p.stride);
-    for (int l0 = 0; l0 < L;) {
-      // limbs [l0, l1) whose na x nb score matrices fit into the pool together (every thread computes the same split)
-      int l1 = l0, used = 0;
-      while (l1 < L) {
-        const int need = S.npk[p.limbs[l1][0]] * S.npk[p.limbs[l1][1]];
-        if (l1 > l0 && used + need > lay.pool_doubles) break;
-        if (tid == 0) S.off[l1] = used;
-        used += need;
-        ++l1;
-      }
-      __syncthreads();
-      for (int l = l0 + warp; l < l1; l += kFusedWarps) {
-        const int ta = p.limbs[l][0], tb = p.limbs[l][1];
-        const int na = S.npk[ta], nb = S.npk[tb];
-        if (na == 0 || nb == 0) {
-          if (lane == 0) { S.nc[l] = 0; o.conn_count[(size_t)b * L + l] = 0; }
-          continue;
-        }
-        double* s_score = s_pool + S.off[l];                 // [na][nb]
-        const float* s_px = s_paf + (size_t)(2 * l) * cells;
-        const float* s_py = s_px + cells;
-        unsigned char* used_a = S.used[warp][0];
-        unsigned char* used_b = S.used[warp][1];
-        for (int i = lane; i < POPNET_MAX_PEAKS; i += 32) { used_a[i] = 0; used_b[i] = 0; }
-        const int npairs = na * nb;
-        score_pairs(s_px, s_py, W, H, S.xy[ta], S.xy[tb], na, nb, NP, p.thresh_paf, Hup, s_score, nb, S.dot[warp], 0, 1, lane);
-        // greedy: repeatedly the best remaining pair whose ends are both free, ties to the smallest (i, j)
-        const int maxc = min(na, nb);
-        int nconn = 0;
-        while (nconn < maxc) {
-          double bv = -CUDART_INF;
-          int bi = 0x7fffffff;
-          for (int pr = lane; pr < npairs; pr += 32) {
-            const int i = pr / nb, j = pr - i * nb;
-            if (used_a[i] || used_b[j]) continue;
-            const double v = s_score[pr];
-            if (v > bv) { bv = v; bi = pr; }
-          }
-#pragma unroll
-          for (int ofs = 16; ofs > 0; ofs >>= 1) {
-            const double ov = __shfl_xor_sync(kFull, bv, ofs);
-            const int oi = __shfl_xor_sync(kFull, bi, ofs);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-          }
-          if (bi == 0x7fffffff) break;
-          const int i = bi / nb, j = bi - i * nb;
-          if (lane == 0) {
-            used_a[i] = 1; used_b[j] = 1;
-            S.ci[l][nconn][0] = (int16_t)i; S.ci[l][nconn][1] = (int16_t)j; S.cs[l][nconn] = bv;
-            const size_t slot = ((size_t)b * L + l) * MP + nconn;
-            o.conn_ij[slot * 2] = (int16_t)i;
-            o.conn_ij[slot * 2 + 1] = (int16_t)j;
-            o.conn_score[slot] = bv;
-          }
-          ++nconn;
-          __syncwarp();
-        }
-        if (lane == 0) { S.nc[l] = nconn; o.conn_count[(size_t)b * L + l] = nconn; }
-      }
-      __syncthreads();
-      l0 = l1;
-    }
-
-    // ---- E: serial assembly by warp 0 (paf_to_pose.py:267-351), F: lift + records by the whole CTA -- the functions
-    // the three-kernel schedule's assemble_kernel runs
-    FrameTables T;
-    T.cs = &S.cs[0][0]; T.ci = &S.ci[0][0][0]; T.pk = &S.pk[0][0]; T.xy = &S.xy[0][0][0];
-    T.nc = S.nc; T.npk = S.npk; T.pj = &S.pj[0][0]; T.ps = S.ps; T.pc = S.pc; T.keep = S.keep;
-    T.MP = POPNET_MAX_PEAKS;
-    if (warp == 0) {
-      unsigned flags = 0;
-      const int n = assemble_persons(T, p, lane, &flags);
-      if (lane == 0) {
-        S.nout = n;
-        rec_store(pc, o.n_person + b, n);
-        rec_store(pc, o.flags + b, (uint32_t)(S.flags | flags));
-      }
-    }
-    __syncthreads();
-    lift_and_store(T, p, o, pc, heat, depth, b, S.nout, tid, kFusedThreads);
-    __syncthreads();                      // the tables are rewritten by the next frame
+    __syncwarp();                  // the tables are rewritten by the warp's next frame
   }
   publish_push(push);
 }
@@ -1087,36 +958,44 @@ int decode_impl(const float* heat, const float* paf, const float* depth, int bat
   for (int l = 0; l < p->num_limbs; ++l)
     if (p->limbs[l][0] < 0 || p->limbs[l][0] >= p->num_joints || p->limbs[l][1] < 0 || p->limbs[l][1] >= p->num_joints)
       return POPNET_ERR_INVALID_ARG;
-  if (p->schedule != POPNET_DECODE_AUTO && p->schedule != POPNET_DECODE_THREE_KERNELS && p->schedule != POPNET_DECODE_FUSED)
-    return POPNET_ERR_INVALID_ARG;
+  if (p->max_ctas < 0) return POPNET_ERR_INVALID_ARG;
   if (batch == 0) return POPNET_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int cells = p->grid_h * p->grid_w;
-  if (p->schedule != POPNET_DECODE_THREE_KERNELS) {
-    constexpr size_t kLimit = 227 * 1024;
-    const FusedLayout lay = fused_layout(p->num_joints, p->num_limbs, cells, kLimit);
-    const bool fits = lay.total <= kLimit && lay.pool_doubles >= p->max_peaks * p->max_peaks;
-    if (fits) {
-      int dev = 0, sms = 148;
-      POPNET_CUDA_TRY(cudaGetDevice(&dev));
-      POPNET_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      POPNET_CUDA_TRY(cudaFuncSetAttribute(decode_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-      const int grid = batch < sms ? batch : sms;
-      decode_fused_kernel<<<grid, kFusedThreads, lay.total, st>>>(heat, paf, depth, batch, *p, *o, pp, lay);
-      POPNET_AFTER_LAUNCH();
-      return POPNET_OK;
-    }
-    if (p->schedule == POPNET_DECODE_FUSED) return POPNET_ERR_UNSUPPORTED;
-  }
+  int dev = 0, sms = 148;
+  POPNET_CUDA_TRY(cudaGetDevice(&dev));
+  POPNET_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int cap = p->max_ctas > 0 ? p->max_ctas : sms;
+  constexpr size_t kSmemBudget = 220 * 1024;
   POPNET_CUDA_TRY(cudaMemsetAsync(o->flags, 0, sizeof(uint32_t) * batch, st));
-  const size_t smem_peaks = sizeof(float) * cells;
-  const size_t smem_limbs = sizeof(double) * p->max_peaks * p->max_peaks + 2 * sizeof(float) * cells;
-  if (smem_limbs > 48 * 1024)
-    POPNET_CUDA_TRY(cudaFuncSetAttribute(limbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limbs));
-  peaks_kernel<<<dim3(p->num_joints, batch), kThreads, smem_peaks, st>>>(heat, *p, *o);
-  POPNET_AFTER_LAUNCH();
-  limbs_kernel<<<dim3(p->num_limbs, batch), kThreads, smem_limbs, st>>>(paf, *p, *o);
-  POPNET_AFTER_LAUNCH();
+  {
+    // warps (= items in flight) per CTA: as many map slices as fit, at most 32
+    const size_t wb = peaks_warp_bytes(cells, p->max_peaks);
+    int wpc = 32;
+    while (wpc > 1 && wb * wpc > kSmemBudget) wpc >>= 1;
+    const int items = batch * p->num_joints;
+    const int grid = std::min(cap, (items + wpc - 1) / wpc);
+    if (wb * wpc > 48 * 1024)
+      POPNET_CUDA_TRY(cudaFuncSetAttribute(peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wb * wpc)));
+    peaks_kernel<<<grid, 32 * wpc, wb * wpc, st>>>(heat, batch, *p, *o);
+    POPNET_AFTER_LAUNCH();
+  }
+  {
+    const int items = batch * p->num_limbs;
+    int wpc = 16, grid = 1;
+    LimbsLayout lay{};
+    for (;; wpc >>= 1) {
+      grid = std::min(cap, (items + wpc - 1) / wpc);
+      const int per_cta = (items + grid * wpc - 1) / (grid * wpc) * wpc;
+      lay = limbs_layout(cells, p->max_peaks, wpc, per_cta);
+      if (lay.total <= kSmemBudget || wpc == 1) break;
+    }
+    if (lay.total > 227 * 1024) return POPNET_ERR_UNSUPPORTED;
+    if (lay.total > 48 * 1024)
+      POPNET_CUDA_TRY(cudaFuncSetAttribute(limbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+    limbs_kernel<<<grid, 32 * wpc, lay.total, st>>>(paf, batch, *p, *o, lay);
+    POPNET_AFTER_LAUNCH();
+  }
   {
     // frames per CTA (one warp each): as many as fit into 200 KB of tables, at most 8
     const size_t fb = asm_frame_bytes(p->num_joints, p->num_limbs, p->max_peaks, p->max_persons);
@@ -1124,7 +1003,7 @@ int decode_impl(const float* heat, const float* paf, const float* depth, int bat
     while (fpc > 1 && fb * fpc > 200 * 1024) fpc >>= 1;
     if (fb * fpc > 48 * 1024)
       POPNET_CUDA_TRY(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fb * fpc)));
-    assemble_kernel<<<(batch + fpc - 1) / fpc, 32 * fpc, fb * fpc, st>>>(heat, depth, batch, *p, *o, pp, (unsigned int)fb);
+    assemble_kernel<<<std::min(cap, (batch + fpc - 1) / fpc), 32 * fpc, fb * fpc, st>>>(heat, depth, batch, *p, *o, pp, (unsigned int)fb);
   }
   POPNET_AFTER_LAUNCH();
   return POPNET_OK;

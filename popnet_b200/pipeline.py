@@ -35,7 +35,7 @@ class PoseEstimator:
 
     def __init__(self, model, camera: Camera = MP3DHP, config: DecodeConfig | None = None, *, input_size=224,
                  max_persons: int = 32, max_peaks: int = _abi.MAX_PEAKS, strict: bool = True, use_graphs: bool = True,
-                 peers=None, decode_priority: int = 0, decode_schedule: int = _abi.DECODE_AUTO, reserve_sms: int = 8):
+                 peers=None, decode_priority: int = 0, reserve_sms: int = 8, decode_ctas: int | None = None):
         from ._cuda_backend import CudaBackend          # raises without CUDA / the library
         self.backend = CudaBackend()
         self.model = model
@@ -46,7 +46,8 @@ class PoseEstimator:
         ds = self.config.downsample
         # the network's third head has num_limbs + 1 planes; joint j reads plane j (...mpreal_ablation.py:212-215)
         self.params = _abi.make_decode_params(self.config, camera, input_size=self.input_hw[1], max_peaks=max_peaks,
-                                              max_persons=max_persons, depth_channels=model.num_limbs + 1, schedule=decode_schedule,
+                                              max_persons=max_persons, depth_channels=model.num_limbs + 1,
+                                              max_ctas=reserve_sms if decode_ctas is None else decode_ctas,
                                               grid_hw=(self.input_hw[0] // ds, self.input_hw[1] // ds))
         #: the reference's lists are unbounded; max_peaks / max_persons are device capacities.  strict: collect() raises
         #: OverflowError when a frame hit one of them (its poses would differ from the reference's); strict=False

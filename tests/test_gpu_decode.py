@@ -8,10 +8,10 @@ from popnet_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-# Both launch schedules of popnet_decode compute every record byte for byte like the oracle: the fused per-frame kernel
-# (POPNET_DECODE_FUSED; what POPNET_DECODE_AUTO picks whenever a frame's maps fit in shared memory -- asserting FUSED here
-# also proves that it is the path that runs for the 28 x 28 / 15-joint configuration) and the three-kernel schedule.
-SCHEDULES = [("fused", 2), ("three_kernels", 1)]
+# popnet_decode computes every record byte for byte like the oracle whatever the CTA limit of its three persistent kernels:
+# 0 = all SMs (a stand-alone call), 8 = the pipelined step's setting (the SMs the convolution grids leave free), 1 = a single
+# CTA walks every item (the longest per-CTA item lists, the big-item pass of the limb kernel over many items).
+SCHEDULES = [("all_sms", 0), ("8_ctas", 8), ("1_cta", 1)]
 schedules = pytest.mark.parametrize("schedule", [v for _, v in SCHEDULES], ids=[n for n, _ in SCHEDULES])
 
 
@@ -20,7 +20,7 @@ schedules = pytest.mark.parametrize("schedule", [v for _, v in SCHEDULES], ids=[
 def test_decode_bitwise_vs_oracle_and_reference(case, schedule, cuda_backend, oracle_lib):
     g = golden("decode_golden")
     heat, paf, depth = helpers.decode_case_inputs(case)
-    params = helpers.params_for(case[5], schedule=schedule)
+    params = helpers.params_for(case[5], max_ctas=schedule)
     dev = cuda_backend.decode(heat, paf, depth, params)
     ora = oracle_lib.decode(heat, paf, depth, params)
     assert helpers.records_equal(dev, ora) == []
@@ -37,7 +37,7 @@ def test_decode_bitwise_vs_oracle_and_reference(case, schedule, cuda_backend, or
 def test_decode_full_size_vs_oracle(batch, persons, seed, schedule, cuda_backend, oracle_lib):
     """BASELINE.json configs C2 / C5 / C4 at their full batch sizes, byte-for-byte against the oracle."""
     heat, paf, depth, _ = synth.map_batch(batch, seed=seed, persons=persons, noise=0.01)
-    params = helpers.params_for("MP3DHP", schedule=schedule)
+    params = helpers.params_for("MP3DHP", max_ctas=schedule)
     dev = cuda_backend.decode(heat, paf, depth, params)
     ora = oracle_lib.decode(heat, paf, depth, params)
     assert helpers.records_equal(dev, ora) == []
@@ -63,7 +63,7 @@ def test_decode_degenerate_overflow_flags(schedule, cuda_backend, oracle_lib):
     heat[2] = 0.5                                         # one giant plateau: every cell is a peak
     paf = (0.05 * rng.standard_normal((3, 28, 28, 28))).astype(np.float32)
     depth = rng.standard_normal((3, 15, 28, 28)).astype(np.float32)
-    params = helpers.params_for("MP3DHP", schedule=schedule)
+    params = helpers.params_for("MP3DHP", max_ctas=schedule)
     dev = cuda_backend.decode(heat, paf, depth, params)
     ora = oracle_lib.decode(heat, paf, depth, params)
     assert (dev["flags"] & 1).all()

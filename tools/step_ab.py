@@ -17,7 +17,7 @@ ap.add_argument("--seconds", type=float, default=2.0)
 ap.add_argument("--tuning", type=lambda v: int(v, 0), default=0)
 ap.add_argument("--rounds", type=int, default=2)
 ap.add_argument("--decode-priority", type=int, default=0)
-ap.add_argument("--decode-schedule", type=int, default=0, help="0 auto, 1 three kernels, 2 fused")
+ap.add_argument("--decode-ctas", type=int, default=-1, help="CTA limit of the decode kernels (-1 = the reserve, 0 = all SMs)")
 ap.add_argument("--reserve", type=int, default=8, help="SMs the conv grids leave to the decode (0 = none)")
 ap.add_argument("--only", default="", help="comma-separated variant names to run (default: all)")
 a = ap.parse_args()
@@ -28,7 +28,7 @@ m = network.rtpose_light3d(15, 14, 2, input_dim=1)
 m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
 m.operand_dtype = _abi.OPERAND_FP16
 m.tuning = a.tuning
-est = pipeline.PoseEstimator(m, max_persons=32, strict=False, decode_priority=a.decode_priority, decode_schedule=a.decode_schedule, reserve_sms=a.reserve)
+est = pipeline.PoseEstimator(m, max_persons=32, strict=False, decode_priority=a.decode_priority, reserve_sms=a.reserve, decode_ctas=None if a.decode_ctas < 0 else a.decode_ctas)
 B = a.batch
 NS = est.NSLOT
 for i in range(NS):
@@ -76,4 +76,4 @@ for r in range(a.rounds):
         t = timed(fn, 50)
         n = max(50, int(a.seconds * 1e3 / t))
         t = timed(fn, n)
-        print("tuning 0x%x reserve %d sched %d: %-22s %.4f ms per step  (%6.0f frames/s)  [%d steps]" % (a.tuning, a.reserve, a.decode_schedule, name, t, B / t * 1e3, n), flush=True)
+        print("tuning 0x%x reserve %d decode ctas %d: %-22s %.4f ms per step  (%6.0f frames/s)  [%d steps]" % (a.tuning, a.reserve, a.decode_ctas, name, t, B / t * 1e3, n), flush=True)

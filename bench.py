@@ -321,6 +321,11 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=op)
         return float(t[0])
 
+    # ---- SM split between the forward and the overlapped decode, chosen by the product's own calibration on the first
+    # input set (part of the warm-up; crowded scenes need more decode SMs than the default 8)
+    calib = {}
+    if not args.no_calibrate:
+        calib = est.calibrate(host_frames[0].cuda(non_blocking=True))
     # ---- value leg: the NSLOT slot input buffers hold NSLOT different input sets, resident in HBM
     for i in range(NS):
         est.slot_input(i, B).copy_(host_frames[i % len(host_frames)])
@@ -345,7 +350,7 @@ def run_ours(args, rank, local_rank, world):
     t1.record()
     torch.cuda.synchronize()
     est_ms = agree(t0.elapsed_time(t1) / 20, dist.ReduceOp.MIN if world > 1 else None)
-    repeats = max(1, int(math.ceil(MIN_TIMED_S * 1e3 / (est_ms * args.steps))))
+    repeats = max(1, int(math.ceil(args.min_timed_s * 1e3 / (est_ms * args.steps))))
     total = args.steps * repeats
     barrier()
     sampler = ClockSampler(local_rank)
@@ -460,6 +465,9 @@ def run_ours(args, rank, local_rank, world):
     cfg["l2"] = ("%d rotating input sets; one step moves > 1.5 GB through the 126 MB L2 (activation workspace %.0f MB), "
                  "nothing survives from one step to the next" % (NS, lib.popnet_workspace_bytes(model._net_config(224, 224), B) / 1e6))
     cfg["cuda_graphs"] = bool(est.use_graphs)
+    cfg["decode_sms"] = int(est.reserve_sms)
+    if calib:
+        cfg["calibration_ms_per_step"] = {str(k): round(v, 4) for k, v in calib.items()}
     if args.tuning:
         cfg["tuning"] = "0x%x" % args.tuning
     line = {
@@ -516,6 +524,8 @@ def main():
     ap.add_argument("--rotate", type=int, default=3)
     ap.add_argument("--eager", action="store_true", help="issue every launch from the host instead of replaying CUDA graphs")
     ap.add_argument("--tuning", type=lambda v: int(v, 0), default=0, help="PopnetNetConfig.tuning bits (A/B of launch schedules; 0 = product defaults)")
+    ap.add_argument("--min-timed-s", type=float, default=MIN_TIMED_S, help="lower bound of the timed regions (0 under a profiler)")
+    ap.add_argument("--no-calibrate", action="store_true", help="keep the default 8 decode SMs instead of PoseEstimator.calibrate()")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-evaluator", action="store_true", help="skip the secondary evaluator metric")
     args = ap.parse_args()

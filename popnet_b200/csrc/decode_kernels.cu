@@ -73,10 +73,10 @@ __device__ __forceinline__ float bicubic_at(const float* m, int pitch, int H, in
 // ------------------------------------------------------------------------------------------------
 // D2 for ONE peak by one warp (paf_to_pose.py:96-118): the 8x bicubic of the clipped 5x5 patch around `cell` and the FIRST
 // arg-max of the (<= 40 x 40) result in row-major order.
-// Lane = output column (dx = lane, and lane + 32 for the last 8 columns of a 40-wide patch): its horizontal phase
-// rx = dx & 7 = lane & 7 never changes, so the four horizontal weights `hc` and the tap offset `hofs` are per-lane constants
-// of the kernel; the column's (<= 5) horizontally interpolated values go to the warp's scratch `tmp` [5][40] and the same
-// lane walks down the column: per source row cy the five scratch rows cy-2 .. cy+2 (clamped) give the 8 output rows
+// Lane = output column (dx = lane; the last 8 columns of a 40-wide patch are spread over all lanes, see below): its horizontal
+// phase rx = dx & 7 = lane & 7 never changes, so the four horizontal weights `hc` and the tap offset `hofs` are per-lane
+// constants of the kernel; the (<= 5) horizontally interpolated values of every column go to the warp's scratch `tmp` [5][40]
+// and a lane walks down its column: per source row cy the five scratch rows cy-2 .. cy+2 (clamped) give the 8 output rows
 // 8 cy .. 8 cy + 7, whose vertical weights are compile-time constants after unrolling.  Same expressions and association as
 // cv::resize (see bicubic_at), so every value is bit-identical to the full upsample's.
 // ------------------------------------------------------------------------------------------------
@@ -87,22 +87,25 @@ __device__ __forceinline__ void refine_peak(const float* __restrict__ s_map, int
   const int x0 = max(x - 2, 0), y0 = max(y - 2, 0), x1 = min(x + 2, W - 1), y1 = min(y + 2, H - 1);
   const int pw = x1 - x0 + 1, ph = y1 - y0 + 1, uw = pw * 8;
   const float* patch = s_map + y0 * W + x0;
-  const int nset = (uw > 32 && lane + 32 < uw) ? 2 : ((lane < uw) ? 1 : 0);
-  for (int s = 0; s < nset; ++s) {
-    const int dx = lane + 32 * s;
+  // horizontal pass: column dx of source row r -> tmp[r][dx]
+  auto hpass = [&](int dx, int r_first, int r_step) {
     const int bx = (dx >> 3) + hofs;
     const int i0 = clampi(bx - 1, 0, pw - 1), i1 = clampi(bx, 0, pw - 1), i2 = clampi(bx + 1, 0, pw - 1), i3 = clampi(bx + 2, 0, pw - 1);
-    for (int r = 0; r < ph; ++r) {
+    for (int r = r_first; r < ph; r += r_step) {
       const float* row = patch + r * W;
       tmp[r * 40 + dx] = ((row[i0] * hc0 + row[i1] * hc1) + row[i2] * hc2) + row[i3] * hc3;
     }
-  }
+  };
+  // columns 0 .. 31: lane = column, all rows; columns 32 .. 39 (a full 5-wide patch): lane = 8 g + c -> column 32 + c (the
+  // same phase c = lane & 7, hence the same weights), rows g, g + 4 -- all 32 lanes stay busy
+  if (lane < uw) hpass(lane, 0, 1);
+  if (uw > 32) hpass(32 + (lane & 7), lane >> 3, 4);
   __syncwarp();
   float best = -CUDART_INF_F;
   int bidx = 0x7fffffff;
-  for (int s = 0; s < nset; ++s) {
-    const int dx = lane + 32 * s;
-    for (int cy = 0; cy < ph; ++cy) {
+  // vertical pass: the 8 output rows 8 cy .. 8 cy + 7 of column dx from the scratch rows cy - 2 .. cy + 2 (clamped)
+  auto vpass = [&](int dx, int cy_first, int cy_step) {
+    for (int cy = cy_first; cy < ph; cy += cy_step) {
       const float tm2 = tmp[clampi(cy - 2, 0, ph - 1) * 40 + dx], tm1 = tmp[clampi(cy - 1, 0, ph - 1) * 40 + dx];
       const float t00 = tmp[cy * 40 + dx];
       const float tp1 = tmp[clampi(cy + 1, 0, ph - 1) * 40 + dx], tp2 = tmp[clampi(cy + 2, 0, ph - 1) * 40 + dx];
@@ -115,7 +118,9 @@ __device__ __forceinline__ void refine_peak(const float* __restrict__ s_map, int
         if (v > best || (v == best && i < bidx)) { best = v; bidx = i; }
       }
     }
-  }
+  };
+  if (lane < uw) vpass(lane, 0, 1);
+  if (uw > 32) vpass(32 + (lane & 7), lane >> 3, 4);
 #pragma unroll
   for (int ofs = 16; ofs > 0; ofs >>= 1) {
     const float ov = __shfl_xor_sync(kFull, best, ofs);
@@ -217,21 +222,73 @@ __device__ __forceinline__ int line_point(int a, int b, int i, int n) {
   return (int)rint(v);
 }
 
-// Scores of one limb's candidate pairs (paf_to_pose.py:196-239) by `nwarps` warps (this is warp `warp` of them).
-// Lane = (pair, intermediate point): a warp takes 32 / NP pairs per round (3 for the reference's 10 points), every lane
-// evaluates ONE point of its pair -- two on-the-fly bicubic PAF samples and the dot product with the unit vector -- and parks
-// it in the warp's scratch; the pair's first lane then sums the NP values in NumPy's pairwise order, counts those above the
-// threshold and applies the length penalty.  (One lane per pair, as before, left 28 of 32 lanes idle for the typical 6 x 6
-// candidates and made the 20 samples of a pair a serial chain.)  s_score[i * pitch + j] = score or -inf (not a candidate).
+// Scores of one limb's candidate pairs (paf_to_pose.py:196-239) by `nwarps` warps (this is warp `warp` of them);
+// s_score[i * pitch + j] = score or -inf (not a candidate).  Two lane mappings, chosen per 32 pairs:
+//   * full groups of 32 pairs: lane = pair.  The lane walks its NP intermediate points itself (two on-the-fly bicubic PAF
+//     samples and the dot product with the unit vector each), summing them in NumPy's pairwise order on the fly (8 running
+//     sums + tail, no per-point storage): the fewest instructions per pair -- what counts when the decode is limited to a
+//     few SMs and a crowded frame has hundreds of pairs per limb;
+//   * the remaining (< 32) pairs -- all of them for the typical 2 x 2 .. 6 x 6 candidates: lane = (pair, point), 32 / NP
+//     pairs per round (3 for the reference's 10 points); every lane evaluates ONE point and parks it in the warp's scratch,
+//     the pair's first lane sums.  One lane per pair would leave most lanes idle and make the 2 NP samples a serial chain.
+__device__ __forceinline__ double pair_point(const float* __restrict__ s_px, const float* __restrict__ s_py, int W, int H,
+                                             int ax, int ay, int bx, int by, double ux, double uy, int t, int NP, int body) {
+  const int X = line_point(ax, bx, t, NP), Y = line_point(ay, by, t, NP);
+  const double px = (double)bicubic_at(s_px, W, H, W, X, Y), py = (double)bicubic_at(s_py, W, H, W, X, Y);
+  // ndarray.dot -> OpenBLAS dgemv: vector body fma(px,ux,py*uy), scalar tail fma(py,uy,px*ux)
+  return (t < body) ? fma(px, ux, py * uy) : fma(py, uy, px * ux);
+}
+__device__ __forceinline__ double pair_finish(double sum, int above, int NP, double Hup, double dist) {
+  double pen = 0.5 * Hup / dist - 1;
+  if (!(pen < 0)) pen = 0;
+  const double sc = sum / (double)NP + pen;
+  return ((double)above > 0.8 * (double)NP && sc > 0) ? sc : -CUDART_INF;
+}
 __device__ __forceinline__ void score_pairs(const float* __restrict__ s_px, const float* __restrict__ s_py, int W, int H,
                                             const int16_t (*xa)[2], const int16_t (*xb)[2], int na, int nb, int NP,
                                             double thresh_paf, double Hup, double* __restrict__ s_score, int pitch,
                                             double* __restrict__ scratch, int warp, int nwarps, int lane) {
-  const int G = 32 / NP;                             // NP <= 32 (checked on the host): G >= 1
-  const int pl = lane / NP, t = lane - pl * NP;
   const int npairs = na * nb;
   const int body = NP & ~3;
-  for (int base = warp * G; base < npairs; base += nwarps * G) {
+  const int full = npairs & ~31;
+  // ---- lane = pair
+  for (int base = warp * 32; base < full; base += nwarps * 32) {
+    const int pr = base + lane;
+    const int i = pr / nb, j = pr - i * nb;
+    const int ax = xa[i][0], ay = xa[i][1], bx = xb[j][0], by = xb[j][1];
+    const double dx = (double)bx - (double)ax, dy = (double)by - (double)ay;
+    const double dist = sqrt(dx * dx + dy * dy) + 1e-8;
+    const double ux = dx / dist, uy = dy / dist;
+    int above = 0;
+    double sum = 0.0;
+    int t = 0;
+    if (NP >= 8) {                                   // np.mean: NumPy pairwise sum = 8 running sums over the 8-blocks ...
+      double r8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        r8[u] = pair_point(s_px, s_py, W, H, ax, ay, bx, by, ux, uy, u, NP, body);
+        above += r8[u] > thresh_paf;
+      }
+      for (t = 8; t + 8 <= NP; t += 8)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double v = pair_point(s_px, s_py, W, H, ax, ay, bx, by, ux, uy, t + u, NP, body);
+          above += v > thresh_paf;
+          r8[u] += v;
+        }
+      sum = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+    }
+    for (; t < NP; ++t) {                            // ... + tail (a plain loop below 8 elements)
+      const double v = pair_point(s_px, s_py, W, H, ax, ay, bx, by, ux, uy, t, NP, body);
+      above += v > thresh_paf;
+      sum += v;
+    }
+    s_score[i * pitch + j] = pair_finish(sum, above, NP, Hup, dist);
+  }
+  // ---- lane = (pair, point)
+  const int G = 32 / NP;                             // NP <= 32 (checked on the host): G >= 1
+  const int pl = lane / NP, t = lane - pl * NP;
+  for (int base = full + warp * G; base < npairs; base += nwarps * G) {
     const int pr = base + pl;
     const bool act = pl < G && pr < npairs;
     int i = 0, j = 0;
@@ -242,10 +299,7 @@ __device__ __forceinline__ void score_pairs(const float* __restrict__ s_px, cons
       const double dx = (double)bx - (double)ax, dy = (double)by - (double)ay;
       dist = sqrt(dx * dx + dy * dy) + 1e-8;
       const double ux = dx / dist, uy = dy / dist;
-      const int X = line_point(ax, bx, t, NP), Y = line_point(ay, by, t, NP);
-      const double px = (double)bicubic_at(s_px, W, H, W, X, Y), py = (double)bicubic_at(s_py, W, H, W, X, Y);
-      // ndarray.dot -> OpenBLAS dgemv: vector body fma(px,ux,py*uy), scalar tail fma(py,uy,px*ux)
-      sv = (t < body) ? fma(px, ux, py * uy) : fma(py, uy, px * ux);
+      sv = pair_point(s_px, s_py, W, H, ax, ay, bx, by, ux, uy, t, NP, body);
     }
     scratch[lane] = sv;
     __syncwarp();
@@ -253,7 +307,6 @@ __device__ __forceinline__ void score_pairs(const float* __restrict__ s_px, cons
       const double* sp = scratch + pl * NP;
       int above = 0;
       for (int u = 0; u < NP; ++u) above += sp[u] > thresh_paf;
-      // np.mean: NumPy pairwise sum (plain loop below 8 elements, else 8 running sums + tail)
       double sum;
       if (NP < 8) {
         sum = 0.0;
@@ -269,10 +322,7 @@ __device__ __forceinline__ void score_pairs(const float* __restrict__ s_px, cons
         sum = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
         for (; u0 < NP; ++u0) sum += sp[u0];
       }
-      double pen = 0.5 * Hup / dist - 1;
-      if (!(pen < 0)) pen = 0;
-      const double sc = sum / (double)NP + pen;
-      s_score[i * pitch + j] = ((double)above > 0.8 * (double)NP && sc > 0) ? sc : -CUDART_INF;
+      s_score[i * pitch + j] = pair_finish(sum, above, NP, Hup, dist);
     }
     __syncwarp();
   }

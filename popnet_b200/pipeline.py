@@ -61,6 +61,7 @@ class PoseEstimator:
         #: word does not choose a reserve itself.
         if reserve_sms and not (model.tuning & _abi.TUNE_RESERVE_SMS(7)):
             model.tuning |= _abi.TUNE_RESERVE_SMS(reserve_sms // 4)
+        self.reserve_sms = 4 * ((model.tuning >> 9) & 7)
         self.decode_priority = decode_priority      # CUDA stream priority of the decode stream (0 = default, -1 = high)
         self.peers = peers          # optional p2p.PeerGather: the multi-GPU record exchange, fused into the decode
         self._slots = None
@@ -97,6 +98,48 @@ class PoseEstimator:
     def refresh(self):
         """Drop the captured graphs and buffers (after editing the model's weights or changing operand_dtype)."""
         self._slots, self._B = None, None
+
+    # ---------------------------------------------------------------------------------------
+    def set_reserve(self, sms: int):
+        """SMs (a multiple of 4, 4..28) that the convolution grids leave to the decode = CTA limit of the decode kernels.
+        Results do not depend on it; captured graphs are dropped (they hold the old grids)."""
+        sms = max(4, min(28, int(sms) // 4 * 4))
+        self.model.tuning = (self.model.tuning & ~_abi.TUNE_RESERVE_SMS(7)) | _abi.TUNE_RESERVE_SMS(sms // 4)
+        self.params.max_ctas = sms
+        self.reserve_sms = sms
+        if self._slots is not None:
+            torch.cuda.synchronize()
+            self._prepared = self.model.prepare(self._B, *self.input_hw)      # the launch configuration carries the tuning word
+            for slot in self._slots:
+                slot["graphs"] = None
+
+    def calibrate(self, frames_dev, candidates=(4, 8, 12, 16, 24), steps=24):
+        """Choose the SM split between the forward and the overlapped decode for THIS workload: the decode's work grows with
+        the number of people per frame (peaks x pairs), the forward's does not, so crowded scenes need more than the default
+        8 SMs or the decode becomes the longer of the two (measured, 12-16 persons at batch 256: decode 5.3 ms on 8 SMs next to
+        a 3.6 ms forward).  Times `steps` pipelined steps per candidate on ``frames_dev`` [B,1,H,W] (device, representative
+        frames) and keeps the fastest; returns {sms: ms per step}.  Every rank of a multi-GPU job must call it (same
+        candidates, same step counts: the record exchange is part of the step)."""
+        B = frames_dev.shape[0]
+        slots = self._buffers(B)
+        for slot in slots:
+            slot["x"].copy_(frames_dev)
+        res = {}
+        for sms in candidates:
+            self.set_reserve(sms)
+            for i in range(2 * self.NSLOT):
+                self._run_slot(slots[i % self.NSLOT])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                self._run_slot(slots[i % self.NSLOT])
+            torch.cuda.current_stream().wait_stream(self.decode_stream)
+            e1.record()
+            torch.cuda.synchronize()
+            res[self.reserve_sms] = e0.elapsed_time(e1) / steps
+        self.set_reserve(min(res, key=res.get))
+        return res
 
     # the two halves of a step, as plain launch sequences on the current stream
     def _launch_forward(self, slot):

@@ -1,13 +1,13 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_decode.py tests/test_gpu_pipeline.py tests/test_gpu_next_rows.py -x -q -m gpu > gpurun_out/r2m_pytest.log 2>&1; tail -5 gpurun_out/r2m_pytest.log
-O=gpurun_out/r2m_step_ab.txt
+timeout 900 python -m pytest tests/test_gpu_decode.py tests/test_gpu_pipeline.py -x -q -m gpu > gpurun_out/r2o_pytest.log 2>&1; tail -3 gpurun_out/r2o_pytest.log
+python bench.py --workload c5 --no-cpu-baseline --no-evaluator --steps 50 > gpurun_out/r2o_bench_c5_n1.json 2> gpurun_out/r2o_bench_c5.err; cut -c1-300 gpurun_out/r2o_bench_c5_n1.json; tail -2 gpurun_out/r2o_bench_c5.err
+python bench.py --no-cpu-baseline --no-evaluator > gpurun_out/r2o_bench_n1.json 2> gpurun_out/r2o_bench.err; cut -c1-300 gpurun_out/r2o_bench_n1.json
+O=gpurun_out/r2o_step_ab.txt
 : > $O
 timeout 120 python tools/step_ab.py --reserve 8 --rounds 1 --only forward,overlapped,decode >> $O 2>&1
-timeout 120 python tools/step_ab.py --reserve 8 --decode-ctas 0 --rounds 1 --only overlapped,decode >> $O 2>&1
-timeout 120 python tools/step_ab.py --reserve 8 --decode-ctas 4 --rounds 1 --only overlapped,decode >> $O 2>&1
-timeout 120 python tools/step_ab.py --reserve 0 --decode-ctas 8 --rounds 1 --only forward,overlapped,decode >> $O 2>&1
+timeout 120 python tools/step_ab.py --reserve 8 --tuning 0x40 --rounds 1 --only forward,overlapped >> $O 2>&1
+timeout 120 python tools/step_ab.py --reserve 8 --tuning 0x2 --rounds 1 --only forward,overlapped >> $O 2>&1
+timeout 120 python tools/step_ab.py --reserve 8 --tuning 0x42 --rounds 1 --only forward,overlapped >> $O 2>&1
 timeout 120 python tools/step_ab.py --reserve 4 --decode-ctas 4 --rounds 1 --only forward,overlapped,decode >> $O 2>&1
-timeout 120 python tools/step_ab.py --reserve 8 --rounds 1 --only forward,overlapped,decode >> $O 2>&1
+timeout 120 python tools/step_ab.py --reserve 8 --rounds 1 --only forward,overlapped >> $O 2>&1
 cat $O
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"peaks_kernel|limbs_kernel|assemble_kernel" -c 30 --csv --log-file gpurun_out/r2m_decode_launches.csv python tools/step_ab.py --reserve 8 --rounds 1 --only decode --seconds 0.05 > /dev/null 2>&1
-tail -12 gpurun_out/r2m_decode_launches.csv | cut -d, -f5,12-

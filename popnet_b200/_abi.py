@@ -27,6 +27,7 @@ TUNE_MC = 0x2
 TUNE_PAIR_RES = 0x80
 TUNE_CHAIN = 0x100
 TUNE_BALANCE = 0x1000
+TUNE_NO_PREFILL = 0x2000
 
 
 def TUNE_RESERVE_SMS(v):

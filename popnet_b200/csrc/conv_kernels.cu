@@ -431,6 +431,10 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a, uint8_t* smem, c
   const int chunks = a.chunks;
   const int chunks_all = chunks + (BRES ? 0 : a.chunks2);
   const int k8_total = chunks * 8;
+  // first fill issued from the prologue (see below): all taps' weights when they are resident, else the first kPreB tap
+  // stages of chunk 0, and the first input slab of the CTA's first tile (the grid never exceeds the tile count)
+  constexpr bool kPrefill = !MC && !CHAIN && !DBG;
+  constexpr int kPreB = (BST < TAPS) ? BST : TAPS;
   pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
@@ -441,6 +445,29 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a, uint8_t* smem, c
       mbar_init(bar0 + 8u * i, cnt);
     }
     fence_mbar_init();
+    if (kPrefill && !a.no_prefill) {
+      // Early first fill, by the thread that initialised the barriers, while the rest of the CTA loads the shift vector,
+      // allocates TMEM and meets at the barrier below: a single-tile CTA of a 28 x 28 stage layer lives 12-17 us, of which the
+      // L2 latency + transfer of its first operands (after that barrier) was more than one.  Weights first -- they do not
+      // depend on the previous layer, so they go out BEFORE griddepcontrol.wait --, then the first input slab.
+      if (BRES) {
+        mbar_expect_tx(b_full(0), (uint32_t)TAPS * kBStageBytes);
+        for (int t = 0; t < TAPS; ++t)
+          bulk_g2s(smem_u32(sB + (size_t)t * kBStageBytes), a.w + (long long)t * k8_total * NT * 8, kBStageBytes, b_full(0));
+      } else {
+#pragma unroll
+        for (int t = 0; t < kPreB; ++t) {
+          mbar_expect_tx(b_full(t), kBStageBytes);
+          bulk_g2s(smem_u32(sB + (size_t)t * kBStageBytes), a.w + (long long)t * k8_total * NT * 8, kBStageBytes, b_full(t));
+        }
+      }
+      pdl_wait();
+      const int t0 = (a.reverse ? num_tiles - 1 - cta : cta) * MT;
+      mbar_expect_tx(a_full(0), a_stage_bytes);
+      for (int g = 0; g < 8; ++g)
+        bulk_g2s(smem_u32(sA + (size_t)g * a_plane_bytes), a.in + (long long)g * a.in_plane_stride + (long long)(t0 - halo) * 8,
+                 a_plane_bytes, a_full(0));
+    }
   }
   if (MC) cluster_sync_all();       // the peer's multicast copies / commits may reach this CTA's barriers from here on
   for (int i = threadIdx.x; i < NT; i += kTcThreads) s_shift[i] = a.shift[i];
@@ -461,7 +488,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a, uint8_t* smem, c
       // ---------------- producer ----------------
       int ia = 0, ib = 0;
       bool chain_gave_up = false;
-      if (BRES) {                                   // all taps of the (single) chunk, once
+      if (BRES && !(kPrefill && !a.no_prefill)) {   // all taps of the (single) chunk, once
         mbar_expect_tx(b_full(0), (uint32_t)TAPS * kBStageBytes);
         for (int t = 0; t < TAPS; ++t)
           bulk_g2s(smem_u32(sB + (size_t)t * kBStageBytes), a.w + (long long)t * k8_total * NT * 8, kBStageBytes, b_full(0));
@@ -491,7 +518,9 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a, uint8_t* smem, c
             const long long pstride = ex ? a.in2_plane_stride : a.in_plane_stride;
             const int as = ia % ast;
             if (ia >= ast) mbar_wait_relaxed(a_empty(as), ((ia / ast) - 1) & 1);
-            if ((dbg & 16) && ia >= ast) mbar_arrive(a_full(as));      // tuning: no copy traffic after the first fill
+            if (kPrefill && !a.no_prefill && ia == 0) {
+              // (issued from the prologue)
+            } else if ((dbg & 16) && ia >= ast) mbar_arrive(a_full(as));      // tuning: no copy traffic after the first fill
             else {
               mbar_expect_tx(a_full(as), a_stage_bytes);
               for (int g = 0; g < 8; ++g)
@@ -504,7 +533,9 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a, uint8_t* smem, c
           for (int t = 0; t < ntap && !BRES; ++t, ++ib) {
             const int bs = ib % BST;
             if (ib >= BST) mbar_wait_relaxed(b_empty(bs), ((ib / BST) - 1) & 1);
-            if ((dbg & 16) && ib >= BST) mbar_arrive(b_full(bs));
+            if (kPrefill && !a.no_prefill && ib < kPreB) {
+              // (issued from the prologue: chunk 0, taps 0 .. kPreB-1 of the first tile)
+            } else if ((dbg & 16) && ib >= BST) mbar_arrive(b_full(bs));
             else {
               const long long woff = ex ? ((long long)TAPS * k8_total + (c - chunks) * 8) * NT * 8
                                         : ((long long)t * k8_total + c * 8) * NT * 8;

@@ -372,6 +372,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     a.pair_res = (cfg->tuning & POPNET_TUNE_PAIR_RES) ? 1 : 0;
     a.grid_cap = 148 - 4 * (int)((cfg->tuning >> 9) & 7u);
     a.balance = (cfg->tuning & POPNET_TUNE_BALANCE) ? 1 : 0;
+    a.no_prefill = (cfg->tuning & POPNET_TUNE_NO_PREFILL) ? 1 : 0;
   };
   auto run_conv = [&](int li) -> int {
     const Layer& l = p.layers[li];

@@ -226,3 +226,23 @@ def test_strict_overflow_raises(cuda_backend):
         est.infer(x)
     est = pipeline.PoseEstimator(m, max_persons=32, strict=False)
     assert est.infer(x)["flags"].all()
+
+
+def test_calibrate_changes_the_sm_split_not_the_records(cuda_backend):
+    """PoseEstimator.calibrate() times the forward / decode SM splits and keeps one; set_reserve() re-captures the graphs.
+    The pose records must be byte-identical for every split (the split is a launch schedule, not arithmetic)."""
+    m, _ = _model()
+    x = _frames(64)
+    est = pipeline.PoseEstimator(m, max_persons=32)
+    ref = {k: np.array(v) for k, v in est.infer(x).items()}
+    res = est.calibrate(torch.from_numpy(x).cuda(), candidates=(4, 8, 16), steps=6)
+    assert set(res) == {4, 8, 16} and all(v > 0 for v in res.values()) and est.reserve_sms in res
+    assert est.params.max_ctas == est.reserve_sms and (m.tuning >> 9) & 7 == est.reserve_sms // 4
+    for sms in (est.reserve_sms, 24, 4):
+        est.set_reserve(sms)
+        got = est.infer(x)
+        n = ref["n_person"]
+        assert np.array_equal(got["n_person"], n) and np.array_equal(got["flags"], ref["flags"]) and int(n.sum()) > 64
+        for f in range(64):
+            for k in ("person_peak", "person_score", "person_njoint", "pose2d", "pose3d", "pose_conf"):
+                assert np.array_equal(got[k][f, :n[f]], ref[k][f, :n[f]]), (sms, k, f)

@@ -25,6 +25,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <cstring>
 
 #include "common.cuh"
@@ -104,7 +105,9 @@ __device__ __forceinline__ void refine_peak(const float* __restrict__ s_map, int
   float best = -CUDART_INF_F;
   int bidx = 0x7fffffff;
   // vertical pass: the 8 output rows 8 cy .. 8 cy + 7 of column dx from the scratch rows cy - 2 .. cy + 2 (clamped)
-  auto vpass = [&](int dx, int cy_first, int cy_step) {
+  // (a lane meets the candidates of its first column in ascending index order, so a strict > keeps the first maximum there;
+  //  the spread-out last columns come afterwards with smaller and larger indices: `ordered` = false compares the index too)
+  auto vpass = [&](int dx, int cy_first, int cy_step, auto ordered) {
     for (int cy = cy_first; cy < ph; cy += cy_step) {
       const float tm2 = tmp[clampi(cy - 2, 0, ph - 1) * 40 + dx], tm1 = tmp[clampi(cy - 1, 0, ph - 1) * 40 + dx];
       const float t00 = tmp[cy * 40 + dx];
@@ -115,12 +118,12 @@ __device__ __forceinline__ void refine_peak(const float* __restrict__ s_map, int
         // ry < 4: first tap row cy - 2 (c_ofs = -1); ry >= 4: first tap row cy - 1
         const float r0 = ry < 4 ? tm2 : tm1, r1 = ry < 4 ? tm1 : t00, r2 = ry < 4 ? t00 : tp1, r3 = ry < 4 ? tp1 : tp2;
         const float v = r0 * c_coef[ry][0] + (r1 * c_coef[ry][1] + (r2 * c_coef[ry][2] + r3 * c_coef[ry][3]));
-        if (v > best || (v == best && i < bidx)) { best = v; bidx = i; }
+        if (decltype(ordered)::value ? (v > best) : (v > best || (v == best && i < bidx))) { best = v; bidx = i; }
       }
     }
   };
-  if (lane < uw) vpass(lane, 0, 1);
-  if (uw > 32) vpass(32 + (lane & 7), lane >> 3, 4);
+  if (lane < uw) vpass(lane, 0, 1, std::true_type{});
+  if (uw > 32) vpass(32 + (lane & 7), lane >> 3, 4, std::false_type{});
 #pragma unroll
   for (int ofs = 16; ofs > 0; ofs >>= 1) {
     const float ov = __shfl_xor_sync(kFull, best, ofs);

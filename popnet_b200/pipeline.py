@@ -113,35 +113,52 @@ class PoseEstimator:
             for slot in self._slots:
                 slot["graphs"] = None
 
-    def calibrate(self, frames_dev, candidates=(4, 8, 12, 16, 24), steps=24):
+    def calibrate(self, frames_dev, candidates=(4, 8, 12, 16, 24), steps=None, min_ms=150.0):
         """Choose the SM split between the forward and the overlapped decode for THIS workload: the decode's work grows with
         the number of people per frame (peaks x pairs), the forward's does not, so crowded scenes need more than the default
         8 SMs or the decode becomes the longer of the two (measured, 12-16 persons at batch 256: decode 5.3 ms on 8 SMs next to
-        a 3.6 ms forward).  Times `steps` pipelined steps per candidate on ``frames_dev`` [B,1,H,W] (device, representative
-        frames) and keeps the fastest; returns {sms: ms per step}.  Every rank of a multi-GPU job must call it (same
-        candidates, same step counts: the record exchange is part of the step)."""
+        a 3.6 ms forward).  Times pipelined steps on ``frames_dev`` [B,1,H,W] (device, representative frames) for every
+        candidate -- at least ``min_ms`` of them (or exactly ``steps``) -- and keeps the fastest; returns {sms: ms per step}.
+        Every rank of a multi-GPU job must call it (same arguments): the record exchange is part of the step, the ranks
+        agree on the slowest rank's time per candidate and therefore on the split."""
         B = frames_dev.shape[0]
         slots = self._buffers(B)
         for slot in slots:
             slot["x"].copy_(frames_dev)
-        res = {}
-        for sms in candidates:
-            self.set_reserve(sms)
-            for i in range(2 * self.NSLOT):
-                self._run_slot(slots[i % self.NSLOT])
-            torch.cuda.synchronize()
+
+        def timed(n):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for i in range(steps):
+            for i in range(n):
                 self._run_slot(slots[i % self.NSLOT])
             torch.cuda.current_stream().wait_stream(self.decode_stream)
             e1.record()
             torch.cuda.synchronize()
-            res[self.reserve_sms] = e0.elapsed_time(e1) / steps
-        # the fastest split; between candidates within 0.5 % of it the LARGER decode share wins (headroom for frames with more
+            return e0.elapsed_time(e1) / n
+
+        def agree(v, op):
+            if self.peers is None:
+                return v
+            import torch.distributed as dist
+            t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=op, group=self.peers.group)
+            return float(t[0])
+
+        res = {}
+        for sms in candidates:
+            self.set_reserve(sms)
+            t = timed(2 * self.NSLOT)                                  # graph capture + warm-up
+            if steps is None:
+                import torch.distributed as dist
+                n = int(agree(max(8, min_ms / max(t, 1e-3)), dist.ReduceOp.MAX if self.peers is not None else None))
+            else:
+                n = steps
+            import torch.distributed as dist
+            res[self.reserve_sms] = agree(timed(n), dist.ReduceOp.MAX if self.peers is not None else None)
+        # the fastest split; between candidates within 0.3 % of it the LARGER decode share wins (headroom for frames with more
         # people than the calibration batch: once the decode is the longer half, the step time is the decode's)
         best = min(res.values())
-        self.set_reserve(max(k for k, v in res.items() if v <= 1.005 * best))
+        self.set_reserve(max(k for k, v in res.items() if v <= 1.003 * best))
         return res
 
     # the two halves of a step, as plain launch sequences on the current stream

@@ -57,7 +57,10 @@ with open(os.path.join(PROF, tag + "_launch_shares.txt"), "w") as f:
     f.write("# per-kernel share of one bench step (batch 64, B200), from profiles/%s_launches_bench.csv\n" % tag)
     f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv python bench.py --steps 2 --warmup 3 --min-timed-s 0 --no-cpu-baseline --no-evaluator\n")
     f.write("# (cold-cache, serialised launches: compare SHARES; in the real step the three branch chains of a stage run concurrently\n")
-    f.write("#  and the decode of step i overlaps the forward of step i+1 -- see %s_forward_timeline.txt for the real overlap)\n" % tag)
+    f.write("#  and the decode of step i overlaps the forward of step i+1 -- see %s_forward_timeline.txt for the real overlap.\n" % tag)
+    f.write("#  The three decode kernels are limited to the few SMs the conv grids leave free (8 or fewer CTAs each): serialised\n")
+    f.write("#  here they count with their full 8-SM duration, in the step they run UNDER the next forward and cost it < 2 %;\n")
+    f.write("#  forward share of the step as the bench measures it with events: roofline.forward_ms / ms_per_step = 0.98.)\n")
     f.write("one step: %d launches, %.1f us serialised; conv_tc_kernel (all shapes) + stem_kernel = %.1f%% of the step\n" % (len(step), tot, 100 * conv / tot))
     for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write("  %-36s x%-3d %8.1f us  %5.1f%%\n" % (n[:36], c, t, 100 * t / tot))

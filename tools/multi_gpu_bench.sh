@@ -10,7 +10,7 @@ run() {
 import json
 try:
     d = json.loads(open("gpurun_out/$n.json").read().strip().splitlines()[-1])
-    print(round(d["value"]), round(d["e2e"]["value"]), round(d["ms_per_step"], 4), d["config"].get("global_batch"), d["scaling"], d["config"].get("decode_sms"), d["check"], d["clocks"])
+    print(round(d["value"]), round(d["e2e"]["value"]), round(d["ms_per_step"], 4), d["config"].get("global_batch"), d["scaling"], d.get("schedule", {}).get("decode_sms"), d["check"], d["clocks"])
 except Exception as e:
     print("ERR", e); print(open("gpurun_out/$n.err").read()[-1500:])
 PY

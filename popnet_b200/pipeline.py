@@ -113,14 +113,16 @@ class PoseEstimator:
             for slot in self._slots:
                 slot["graphs"] = None
 
-    def calibrate(self, frames_dev, candidates=(4, 8, 12, 16, 24), steps=None, min_ms=150.0):
+    def calibrate(self, frames_dev, candidates=(8, 12, 16, 24), steps=None, min_ms=150.0):
         """Choose the SM split between the forward and the overlapped decode for THIS workload: the decode's work grows with
         the number of people per frame (peaks x pairs), the forward's does not, so crowded scenes need more than the default
         8 SMs or the decode becomes the longer of the two (measured, 12-16 persons at batch 256: decode 5.3 ms on 8 SMs next to
         a 3.6 ms forward).  Times pipelined steps on ``frames_dev`` [B,1,H,W] (device, representative frames) for every
         candidate -- at least ``min_ms`` of them (or exactly ``steps``) -- and keeps the fastest; returns {sms: ms per step}.
         Every rank of a multi-GPU job must call it (same arguments): the record exchange is part of the step, the ranks
-        agree on the slowest rank's time per candidate and therefore on the split."""
+        agree on the slowest rank's time per candidate and therefore on the split.  (4 SMs are not a default candidate: for
+        1-6 persons per frame they give the device-resident step +0.5 % but leave the decode 0.78 of the step long, and the
+        host-fed pipeline (submit / collect) then runs 1 % SLOWER than with 8 -- profiles/r2_bench_spread.txt.)"""
         B = frames_dev.shape[0]
         slots = self._buffers(B)
         for slot in slots:

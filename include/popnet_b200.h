@@ -56,6 +56,11 @@ POPNET_API int popnet_last_cuda_error(void);
 /* number of kernels this library has launched since load (all entry points); bench.py reports the
  * delta over its timed region as "gpu_launches" */
 POPNET_API long long popnet_launch_count(void);
+/* The only objects the library keeps between calls are plumbing: per (device, caller stream) two auxiliary streams and four
+ * events that popnet_forward forks its branch chains onto (created on first use).  This destroys those of the CURRENT device
+ * (after synchronising them); a later popnet_forward re-creates them.  Captured CUDA graphs that contain a forward keep
+ * working (graph nodes do not reference the capture streams).  Returns the number of stream sets released. */
+POPNET_API int popnet_release_streams(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Decode + lift.  Replaces, batched and on the device:

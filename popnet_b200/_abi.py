@@ -115,6 +115,7 @@ PROTOTYPES = {
     "popnet_abi_version": (C.c_int, []),
     "popnet_last_cuda_error": (C.c_int, []),
     "popnet_launch_count": (C.c_longlong, []),
+    "popnet_release_streams": (C.c_int, []),
     "popnet_decode": (C.c_int, [vp, vp, vp, C.c_int, C.POINTER(DecodeParams), C.POINTER(DecodeOut), vp]),
     "popnet_decode_push": (C.c_int, [vp, vp, vp, C.c_int, C.POINTER(DecodeParams), C.POINTER(DecodeOut),
                                      C.POINTER(PeerPush), vp]),

@@ -286,9 +286,11 @@ struct AuxStreams {
   cudaStream_t s[2];
   cudaEvent_t fork, join[2], nfused;
 };
+std::mutex g_aux_mu;
+std::vector<AuxStreams*> g_aux_sets;
 AuxStreams* aux_streams(cudaStream_t owner) {
-  static std::mutex mu;
-  static std::vector<AuxStreams*> sets;
+  std::mutex& mu = g_aux_mu;
+  std::vector<AuxStreams*>& sets = g_aux_sets;
   int device = 0;
   if (cudaGetDevice(&device) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lock(mu);
@@ -318,6 +320,24 @@ AuxStreams* aux_streams(cudaStream_t owner) {
   return aux;
 }
 }  // namespace
+
+extern "C" int popnet_release_streams(void) {
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess) return 0;
+  std::lock_guard<std::mutex> lock(g_aux_mu);
+  int released = 0;
+  for (size_t i = 0; i < g_aux_sets.size();) {
+    AuxStreams* a = g_aux_sets[i];
+    if (a->device != device) { ++i; continue; }
+    for (int k = 0; k < 2; ++k) { cudaStreamSynchronize(a->s[k]); cudaStreamDestroy(a->s[k]); cudaEventDestroy(a->join[k]); }
+    cudaEventDestroy(a->fork);
+    cudaEventDestroy(a->nfused);
+    delete a;
+    g_aux_sets.erase(g_aux_sets.begin() + (long)i);
+    ++released;
+  }
+  return released;
+}
 
 extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev, const float* x, int batch,
                               float* paf, float* heat, float* depth, float* s1_paf, float* s1_heat, float* s1_depth,

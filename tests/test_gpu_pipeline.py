@@ -246,3 +246,17 @@ def test_calibrate_changes_the_sm_split_not_the_records(cuda_backend):
         for f in range(64):
             for k in ("person_peak", "person_score", "person_njoint", "pose2d", "pose3d", "pose_conf"):
                 assert np.array_equal(got[k][f, :n[f]], ref[k][f, :n[f]]), (sms, k, f)
+
+
+def test_release_streams_and_run_again(cuda_backend):
+    """popnet_release_streams destroys the branch streams / events the forward keeps per (device, caller stream); the next
+    forward re-creates them and gives the same maps."""
+    from popnet_b200 import _lib
+    m, _ = _model("fp16")
+    x = torch.from_numpy(_frames(64)[:8]).cuda()
+    (paf, heat, depth), _ = m(x)
+    torch.cuda.synchronize()
+    assert _lib.get().popnet_release_streams() >= 1
+    assert _lib.get().popnet_release_streams() == 0
+    (paf2, heat2, depth2), _ = m(x)
+    assert torch.equal(paf, paf2) and torch.equal(heat, heat2) and torch.equal(depth, depth2)

@@ -71,6 +71,29 @@ __device__ __forceinline__ float bicubic_at(const float* m, int pitch, int H, in
   return rows[0] * c_coef[ry][0] + (rows[1] * c_coef[ry][1] + (rows[2] * c_coef[ry][2] + rows[3] * c_coef[ry][3]));
 }
 
+// the same value for TWO maps of identical geometry (the x and y planes of a PAF limb) at one point: phases, clamped tap
+// columns / rows and weights are computed once; per map the arithmetic is bicubic_at's, statement for statement
+__device__ __forceinline__ void bicubic2_at(const float* mx, const float* my, int pitch, int H, int W, int X, int Y, float& vx,
+                                            float& vy) {
+  const int rx = X & 7, ry = Y & 7;
+  const int bx = (X >> 3) + c_ofs[rx], by = (Y >> 3) + c_ofs[ry];
+  const float a0 = c_coef[rx][0], a1 = c_coef[rx][1], a2 = c_coef[rx][2], a3 = c_coef[rx][3];
+  const int x0 = clampi(bx - 1, 0, W - 1), x1 = clampi(bx, 0, W - 1), x2 = clampi(bx + 1, 0, W - 1),
+            x3 = clampi(bx + 2, 0, W - 1);
+  float rowsx[4], rowsy[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ro = clampi(by - 1 + j, 0, H - 1) * pitch;
+    const float* rwx = mx + ro;
+    const float* rwy = my + ro;
+    rowsx[j] = ((rwx[x0] * a0 + rwx[x1] * a1) + rwx[x2] * a2) + rwx[x3] * a3;
+    rowsy[j] = ((rwy[x0] * a0 + rwy[x1] * a1) + rwy[x2] * a2) + rwy[x3] * a3;
+  }
+  const float b0 = c_coef[ry][0], b1 = c_coef[ry][1], b2 = c_coef[ry][2], b3 = c_coef[ry][3];
+  vx = rowsx[0] * b0 + (rowsx[1] * b1 + (rowsx[2] * b2 + rowsx[3] * b3));
+  vy = rowsy[0] * b0 + (rowsy[1] * b1 + (rowsy[2] * b2 + rowsy[3] * b3));
+}
+
 // ------------------------------------------------------------------------------------------------
 // D2 for ONE peak by one warp (paf_to_pose.py:96-118): the 8x bicubic of the clipped 5x5 patch around `cell` and the FIRST
 // arg-max of the (<= 40 x 40) result in row-major order.
@@ -237,7 +260,9 @@ __device__ __forceinline__ int line_point(int a, int b, int i, int n) {
 __device__ __forceinline__ double pair_point(const float* __restrict__ s_px, const float* __restrict__ s_py, int W, int H,
                                              int ax, int ay, int bx, int by, double ux, double uy, int t, int NP, int body) {
   const int X = line_point(ax, bx, t, NP), Y = line_point(ay, by, t, NP);
-  const double px = (double)bicubic_at(s_px, W, H, W, X, Y), py = (double)bicubic_at(s_py, W, H, W, X, Y);
+  float fx, fy;
+  bicubic2_at(s_px, s_py, W, H, W, X, Y, fx, fy);
+  const double px = (double)fx, py = (double)fy;
   // ndarray.dot -> OpenBLAS dgemv: vector body fma(px,ux,py*uy), scalar tail fma(py,uy,px*ux)
   return (t < body) ? fma(px, ux, py * uy) : fma(py, uy, px * ux);
 }

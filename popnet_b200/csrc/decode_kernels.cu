@@ -163,7 +163,7 @@ __device__ __forceinline__ void refine_peak(const float* __restrict__ s_map, int
 // ------------------------------------------------------------------------------------------------
 // per-warp shared-memory slice of peaks_kernel: [cells (padded to 4)] map | [5*40] scratch | [MP] peak cells
 __host__ __device__ inline size_t peaks_warp_bytes(int cells, int MP) {
-  return ((((size_t)cells + 3) & ~(size_t)3) + 200 + (size_t)MP) * 4;
+  return (((((size_t)cells + 3) & ~(size_t)3) + 200 + (size_t)MP) * 4 + 15) & ~(size_t)15;      // slices stay 16-byte aligned (float4 fills)
 }
 
 __global__ void __launch_bounds__(1024) peaks_kernel(const float* __restrict__ heat, int batch, PopnetDecodeParams p,

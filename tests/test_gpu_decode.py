@@ -140,3 +140,14 @@ def test_decode_rejects_mismatched_shapes(cuda_backend):
     d20 = np.ascontiguousarray(np.concatenate([depth, depth[:, :5]], 1))
     a, b = cuda_backend.decode(heat, paf, d20, p20), cuda_backend.decode(heat, paf, depth, params)
     assert helpers.records_equal(a, b) == []                                                     # joint j reads plane j
+
+
+@schedules
+def test_decode_odd_capacities(schedule, cuda_backend, oracle_lib):
+    """Capacities that are not multiples of 4 / 8 (max_peaks 37, max_persons 21): every per-warp shared-memory slice of the
+    decode kernels must stay aligned, and truncation / overflow flags must match the oracle's."""
+    heat, paf, depth, _ = synth.map_batch(24, seed=909, persons=(8, 14), noise=0.02)
+    params = helpers.params_for("MP3DHP", max_ctas=schedule, max_peaks=37, max_persons=21)
+    dev = cuda_backend.decode(heat, paf, depth, params)
+    ora = oracle_lib.decode(heat, paf, depth, params)
+    assert helpers.records_equal(dev, ora) == []

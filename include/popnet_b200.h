@@ -305,6 +305,7 @@ typedef struct PopnetNetConfig {
                                                decode of the previous batch, which runs concurrently on its own stream       */
 #define POPNET_TUNE_BALANCE 0x1000u         /* persistent grids sized so that every CTA walks the same number of tiles        */
 #define POPNET_TUNE_NO_PREFILL 0x2000u      /* first operand loads after the CTA-wide prologue barrier instead of before it  */
+#define POPNET_TUNE_CLUSTER_ALL 0x4000u     /* every 28 x 28 stage launch as clusters of two CTAs (pairs of SMs are taken and freed together) */
 #define POPNET_TUNE_CHAIN 0x100u            /* the four 64 -> 64 layers of the 112 x 112 block as ONE spatially pipelined launch
                                                (CTA slices linked by per-tile progress counters; tensors travel through the L2)
                                                instead of four launches: bit-identical, measured 3 % slower per forward      */

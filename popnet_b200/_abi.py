@@ -28,6 +28,7 @@ TUNE_PAIR_RES = 0x80
 TUNE_CHAIN = 0x100
 TUNE_BALANCE = 0x1000
 TUNE_NO_PREFILL = 0x2000
+TUNE_CLUSTER_ALL = 0x4000
 
 
 def TUNE_RESERVE_SMS(v):

@@ -75,6 +75,7 @@ struct ConvArgs {
   unsigned long long* trace;    // optional [4] globaltimer stamps {first CTA in, first CTA past griddepcontrol.wait, last CTA out, sum of CTA lifetimes}
   int grid_cap;                 // persistent grid size limit (0 = all 148 SMs): tuning, leaves SMs to the concurrently running decode
   int balance;                  // tuning: size the persistent grid so that every CTA walks the same number of tiles
+  int cluster2;                 // tuning: launch as clusters of two CTAs (see launch_tc_inst)
   int no_prefill;               // tuning: first operand loads from the producer loop (after the CTA-wide barrier) instead of the prologue
 };
 

@@ -445,7 +445,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a, uint8_t* smem, c
       mbar_init(bar0 + 8u * i, cnt);
     }
     fence_mbar_init();
-    if (kPrefill && !a.no_prefill) {
+    if (kPrefill && !a.no_prefill && cta < num_tiles) {
       // Early first fill, by the thread that initialised the barriers, while the rest of the CTA loads the shift vector,
       // allocates TMEM and meets at the barrier below: a single-tile CTA of a 28 x 28 stage layer lives 12-17 us, of which the
       // L2 latency + transfer of its first operands (after that barrier) was more than one.  Weights first -- they do not
@@ -488,7 +488,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a, uint8_t* smem, c
       // ---------------- producer ----------------
       int ia = 0, ib = 0;
       bool chain_gave_up = false;
-      if (BRES && !(kPrefill && !a.no_prefill)) {   // all taps of the (single) chunk, once
+      if (BRES && !(kPrefill && !a.no_prefill && cta < num_tiles)) {   // all taps of the (single) chunk, once
         mbar_expect_tx(b_full(0), (uint32_t)TAPS * kBStageBytes);
         for (int t = 0; t < TAPS; ++t)
           bulk_g2s(smem_u32(sB + (size_t)t * kBStageBytes), a.w + (long long)t * k8_total * NT * 8, kBStageBytes, b_full(0));
@@ -1156,13 +1156,16 @@ constexpr size_t kSmemLimit = 227 * 1024;
 
 // launch configuration with programmatic stream serialization (PDL) enabled; the attribute lives in the caller's frame
 struct PdlConfig {
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cudaLaunchConfig_t cfg;
-  PdlConfig(dim3 grid, dim3 block, size_t smem, cudaStream_t st) : cfg{} {
+  // cluster2: launch as clusters of two CTAs (the kernel itself does not use the cluster; the grid must be even)
+  PdlConfig(dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool cluster2 = false) : cfg{} {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = cluster2 ? 2 : 1;
   }
   PdlConfig(const PdlConfig&) = delete;
 };
@@ -1184,7 +1187,10 @@ int launch_tc_inst(const ConvArgs& a, size_t smem, cudaStream_t st) {
     const int per = (tiles + cap - 1) / cap;
     grid = (tiles + per - 1) / per;
   }
-  PdlConfig pc(dim3(grid), dim3(kTcThreads), smem, st);
+  // tuning (POPNET_TUNE_CLUSTER_ALL): every stage launch as clusters of two, so that SM pairs are taken and released together
+  // and the multicast kernels of the concurrent PAF branch always find whole pairs; an odd grid gets one CTA without tiles
+  if (a.cluster2) grid = (grid + 1) & ~1;
+  PdlConfig pc(dim3(grid), dim3(kTcThreads), smem, st, a.cluster2 != 0);
   ConvArgs at = a;
   at.trace = next_trace_slot(NT * 1000 + NACC * 100 + TAPS * 10);
   POPNET_CUDA_TRY(cudaLaunchKernelEx(&pc.cfg, kern, at));
@@ -1237,7 +1243,8 @@ int launch_tc_mc(const ConvArgs& a, cudaStream_t st) {
   POPNET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   POPNET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int tiles = (a.P + NACC * 128 - 1) / (NACC * 128);
-  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  const int cap = (a.grid_cap > 0 && a.grid_cap < kNumSMs) ? (a.grid_cap & ~1) : kNumSMs;
+  int grid = tiles < cap ? tiles : cap;
   grid = (grid + 1) & ~1;                                      // whole clusters (148 is even)
   cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

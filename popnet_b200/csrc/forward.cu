@@ -393,6 +393,7 @@ extern "C" int popnet_forward(const PopnetNetConfig* cfg, const void* packed_dev
     a.grid_cap = 148 - 4 * (int)((cfg->tuning >> 9) & 7u);
     a.balance = (cfg->tuning & POPNET_TUNE_BALANCE) ? 1 : 0;
     a.no_prefill = (cfg->tuning & POPNET_TUNE_NO_PREFILL) ? 1 : 0;
+    a.cluster2 = ((cfg->tuning & POPNET_TUNE_CLUSTER_ALL) && l.stage >= 1) ? 1 : 0;
   };
   auto run_conv = [&](int li) -> int {
     const Layer& l = p.layers[li];

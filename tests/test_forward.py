@@ -186,3 +186,20 @@ def test_cuda_forward_other_input_sizes(hw, cuda_backend):
     for name, a, b in (("paf", paf, opaf), ("heat", heat, oheat), ("depth", depth, odepth), ("paf1", saved[0], osaved[0])):
         err = float((a.cpu() - b).abs().max())
         assert np.isfinite(err) and err <= TOL, (name, err)
+
+
+@pytest.mark.gpu
+def test_cuda_forward_schedule_switches_identical(cuda_backend):
+    """The round-2 launch-schedule switches -- SM reserve, balanced grids, 256-position stage tiles, prologue prefill off,
+    cluster-of-two stage launches (with and without the multicast kernels) -- only change WHO computes a tile and when:
+    the maps must be bit-identical to the default schedule, at a batch with few tiles (3: odd tile counts, CTAs without
+    tiles in the cluster launches) and at the bench batch."""
+    from popnet_b200 import _abi
+    tun = {"default": 0, "reserve8": _abi.TUNE_RESERVE_SMS(2), "reserve28": _abi.TUNE_RESERVE_SMS(7),
+           "balance": _abi.TUNE_BALANCE, "nacc2-balance": _abi.TUNE_BALANCE | _abi.tune_stage_nacc(2),
+           "no-prefill": _abi.TUNE_NO_PREFILL, "cluster-all": _abi.TUNE_CLUSTER_ALL,
+           "cluster-all-mc-reserve": _abi.TUNE_CLUSTER_ALL | _abi.TUNE_MC | _abi.TUNE_RESERVE_SMS(2)}
+    outs = _maps_for_tunings(tun)
+    for tag in tun:
+        for a, b in zip(outs["default"], outs[tag]):
+            assert torch.equal(a, b), tag
